@@ -1,0 +1,231 @@
+"""Pythonic Net on top of the C ABI: the surface of the reference's pycaffe
+(caffe_3d/python/caffe/pycaffe.py:21-281 over _caffe.cpp:209-317), so scripts such as
+scripts/online_recognition/online_recognition.py run unchanged with this package on sys.path:
+
+    net = caffe.Net(prototxt, caffemodel, caffe.TEST)
+    net.blobs['data'].data[...] = frames
+    out = net.forward()                      # {'fc8': ndarray}
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _caffe
+from ._caffe import Blob, Layer, check, lib
+
+TRAIN = 0  # caffe.proto Phase
+TEST = 1
+
+
+class Net(object):
+    """caffe.Net(prototxt, phase) / caffe.Net(prototxt, caffemodel, phase)  (_caffe.cpp:89-108)."""
+
+    def __init__(self, *args, **kwargs):
+        if len(args) == 2:
+            model_file, phase = args
+            weights = None
+        elif len(args) == 3:
+            model_file, weights, phase = args
+        else:
+            raise TypeError("Net(prototxt, phase) or Net(prototxt, caffemodel, phase)")
+        self._h = C.c_void_p()
+        text = kwargs.get("prototxt_text")
+        if text is None:
+            # same file check as the reference, which raises RuntimeError (_caffe.cpp:57-64)
+            if not os.path.isfile(model_file):
+                raise RuntimeError("Could not open file " + str(model_file))
+            check(lib().eco_net_create(os.fsencode(model_file), int(phase), C.byref(self._h)))
+        else:
+            check(lib().eco_net_create_from_string(text.encode(), int(phase), C.byref(self._h)))
+        for k, v in kwargs.get("options", {}).items():
+            check(lib().eco_net_set_option(self._h, k.encode(), int(v)))
+        if weights is not None:
+            if not os.path.isfile(weights):
+                raise RuntimeError("Could not open file " + str(weights))
+            self.copy_from(weights)
+        self._refresh_registry()
+
+    @classmethod
+    def from_string(cls, text, phase, **options):
+        return cls("<string>", phase, prototxt_text=text, options=options)
+
+    def _refresh_registry(self):
+        L = lib()
+        self._layer_names = [L.eco_net_layer_name(self._h, i).decode() for i in range(L.eco_net_num_layers(self._h))]
+        self._blob_names = [L.eco_net_blob_name(self._h, i).decode() for i in range(L.eco_net_num_blobs(self._h))]
+        self._blobs = [Blob(self, i) for i in range(len(self._blob_names))]
+        self.layers = [Layer(self, i) for i in range(len(self._layer_names))]
+        self._inputs = [L.eco_net_input_blob(self._h, i) for i in range(L.eco_net_num_inputs(self._h))]
+        self._outputs = [L.eco_net_output_blob(self._h, i) for i in range(L.eco_net_num_outputs(self._h))]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().eco_net_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- registry -------------------------------------------------------------------
+    @property
+    def name(self):
+        return lib().eco_net_name(self._h).decode()
+
+    @property
+    def blobs(self):
+        return OrderedDict(zip(self._blob_names, self._blobs))
+
+    @property
+    def params(self):
+        out = OrderedDict()
+        for name, lr in zip(self._layer_names, self.layers):
+            b = lr.blobs
+            if len(b) > 0:
+                out[name] = b
+        return out
+
+    @property
+    def inputs(self):
+        return [self._blob_names[i] for i in self._inputs]
+
+    @property
+    def outputs(self):
+        return [self._blob_names[i] for i in self._outputs]
+
+    # ---- execution ------------------------------------------------------------------
+    def _forward(self, start, end):
+        loss = C.c_float(0)
+        check(lib().eco_net_forward(self._h, int(start), int(end), C.byref(loss)))
+        return loss.value
+
+    def _backward(self, start, end):
+        check(lib().eco_net_backward(self._h, int(start), int(end)))
+
+    def forward(self, blobs=None, start=None, end=None, **kwargs):
+        blobs = list(blobs or [])
+        start_ind = self._layer_names.index(start) if start is not None else 0
+        if end is not None:
+            end_ind = self._layer_names.index(end)
+            outputs = set([end] + blobs)
+        else:
+            end_ind = len(self.layers) - 1
+            outputs = set(self.outputs + blobs)
+        if kwargs:
+            if set(kwargs.keys()) != set(self.inputs):
+                raise Exception("Input blob arguments do not match net inputs.")
+            allb = self.blobs
+            for in_, arr in kwargs.items():
+                if arr.shape[0] != allb[in_].shape[0]:
+                    raise Exception("Input is not batch sized")
+                allb[in_].data[...] = arr
+        self._forward(start_ind, end_ind)
+        allb = self.blobs
+        return {out: allb[out].data for out in outputs}
+
+    def backward(self, diffs=None, start=None, end=None, **kwargs):
+        start_ind = self._layer_names.index(start) if start is not None else len(self.layers) - 1
+        end_ind = self._layer_names.index(end) if end is not None else 0
+        self._backward(start_ind, end_ind)
+        return {}
+
+    def forward_all(self, blobs=None, **kwargs):
+        all_outs = {out: [] for out in set(self.outputs + list(blobs or []))}
+        n = len(next(iter(kwargs.values())))
+        for batch in self._batch(kwargs):
+            outs = self.forward(blobs=blobs, **batch)
+            for out, arr in outs.items():
+                all_outs[out].extend(arr.copy())
+        for out in all_outs:
+            all_outs[out] = np.asarray(all_outs[out])[:n]
+        return all_outs
+
+    def _batch(self, blobs):
+        num = len(next(iter(blobs.values())))
+        batch_size = self.blobs[self.inputs[0]].shape[0]
+        for i in range(0, num - num % batch_size, batch_size):
+            yield {name: blobs[name][i:i + batch_size] for name in blobs}
+        rem = num % batch_size
+        if rem:
+            padded = {}
+            for name in blobs:
+                pad = np.zeros((batch_size - rem,) + blobs[name].shape[1:], np.float32)
+                padded[name] = np.concatenate([blobs[name][-rem:], pad])
+            yield padded
+
+    def reshape(self):
+        check(lib().eco_net_reshape(self._h))
+
+    def sync(self):
+        check(lib().eco_net_sync(self._h))
+
+    # ---- weights --------------------------------------------------------------------
+    def copy_from(self, path):
+        check(lib().eco_net_copy_from(self._h, os.fsencode(path)))
+
+    def save(self, path):
+        check(lib().eco_net_save(self._h, os.fsencode(path)))
+
+    def share_with(self, other):
+        """caffe shares the parameter storage (net.cpp ShareTrainedLayersWith); here the values are
+        copied once, matched by layer name."""
+        src = other.params
+        for name, blobs in self.params.items():
+            if name in src:
+                for a, b in zip(blobs, src[name]):
+                    a.data[...] = b.data
+
+    # ---- extensions beyond pycaffe ---------------------------------------------------
+    def set_option(self, key, value):
+        check(lib().eco_net_set_option(self._h, key.encode(), int(value)))
+
+    def set_stream(self, cuda_stream_ptr):
+        check(lib().eco_net_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr))))
+
+    def set_input_device(self, blob_name, dev_ptr, count):
+        check(lib().eco_net_set_input_device(self._h, self._blob_names.index(blob_name), C.c_void_p(int(dev_ptr)),
+                                             int(count)))
+
+    def blob_device_ptr(self, blob_name):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        check(lib().eco_blob_device_f32(self._h, self._blob_names.index(blob_name), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def last_launch_count(self):
+        n = C.c_int()
+        check(lib().eco_net_last_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def profile_forward(self, cap=1024):
+        arr = (_caffe.OpTime * cap)()
+        n = C.c_int()
+        check(lib().eco_net_profile_forward(self._h, arr, cap, C.byref(n)))
+        return [dict(name=arr[i].name.decode(), kind=arr[i].kind, ms=arr[i].ms, flops=arr[i].flops,
+                     bytes=arr[i].bytes) for i in range(n.value)]
+
+
+def set_mode_gpu():
+    check(lib().eco_set_mode(1))
+
+
+def set_mode_cpu():
+    # accepted like caffe.set_mode_cpu(); a forward in this mode raises: there is no CPU path
+    check(lib().eco_set_mode(0))
+
+
+def set_device(i):
+    check(lib().eco_set_device(int(i)))
+
+
+def set_logging_disabled():
+    pass
+
+
+def device_count():
+    n = C.c_int()
+    check(lib().eco_device_count(C.byref(n)))
+    return n.value

@@ -1,0 +1,310 @@
+// aux_kernels.cu -- HBM-bound helper kernels (sm_100a).  All of these are streaming byte movers:
+// one pass over the tensor, 16-byte vector accesses along the channel axis, grid sized from the
+// element count.  Caffe semantics cited per kernel.
+#include "aux_kernels.cuh"
+
+#include <cfloat>
+#include <stdint.h>
+
+namespace eco {
+namespace {
+
+constexpr int kThreads = 256;
+inline int blocks_for(long long n) { return (int)((n + kThreads - 1) / kThreads); }
+
+// ---------------------------------------------------------------- layout transforms
+__global__ void f32_to_cl_kernel(const float* __restrict__ src, ClView d) {
+  // one thread per (o, i, c); c fastest so the bf16 writes coalesce
+  const long long total = d.outer * d.inner * d.C;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % d.C);
+    const long long oi = t / d.C;
+    const long long i = oi % d.inner, o = oi / d.inner;
+    const float v = src[(o * d.C + c) * d.inner + i];
+    d.ptr[oi * d.cs + d.coff + c] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void cl_to_f32_kernel(ClView s, float* __restrict__ dst) {
+  // one thread per (o, c, i); i fastest so the fp32 writes coalesce
+  const long long total = s.outer * s.inner * s.C;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t % s.inner;
+    const long long oc = t / s.inner;
+    const int c = (int)(oc % s.C);
+    const long long o = oc / s.C;
+    dst[t] = __bfloat162float(s.ptr[(o * s.inner + i) * s.cs + s.coff + c]);
+  }
+}
+
+__global__ void stem_s2d_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int F, int H, int W,
+                                int CH, int CW) {
+  const long long total = (long long)F * CH * CW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(t % CW);
+    const int Y = (int)((t / CW) % CH);
+    const long long f = t / ((long long)CW * CH);
+    const float* img = src + f * 3LL * H * W;
+    __align__(16) __nv_bfloat16 cell[16];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int y = 2 * Y + dy - 3, x = 2 * X + dx - 3;
+        const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          cell[(dy * 2 + dx) * 3 + c] = __float2bfloat16_rn(ok ? img[((long long)c * H + y) * W + x] : 0.f);
+      }
+#pragma unroll
+    for (int j = 12; j < 16; ++j) cell[j] = __float2bfloat16_rn(0.f);
+    uint4* o = reinterpret_cast<uint4*>(dst + t * 16);
+    o[0] = reinterpret_cast<const uint4*>(cell)[0];
+    o[1] = reinterpret_cast<const uint4*>(cell)[1];
+  }
+}
+
+// ---------------------------------------------------------------- pooling, channels-last
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+    f[2 * j] = __low2float(t);
+    f[2 * j + 1] = __high2float(t);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(f[0], f[1]); v.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[2], f[3]); v.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[4], f[5]); v.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[6], f[7]); v.w = *reinterpret_cast<uint32_t*>(&t);
+  return v;
+}
+
+// MAX: window [o*s-p, min(start+k, in)) then start=max(start,0), init -FLT_MAX  (pooling_layer.cpp:199-224)
+// AVE: divisor = prod(min(start+k, in+p) - start) before clipping to the image      (pooling_layer.cpp:247-262)
+__global__ void pool_cl_kernel(const PoolParams p) {
+  const int cg = p.C / 8;
+  const long long total = (long long)p.NB * p.OD * p.OH * p.OW * cg;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % cg);
+    long long r = t / cg;
+    const int ox = (int)(r % p.OW); r /= p.OW;
+    const int oy = (int)(r % p.OH); r /= p.OH;
+    const int oz = (int)(r % p.OD);
+    const long long n = r / p.OD;
+    int z0 = oz * p.sD - p.pD, y0 = oy * p.sH - p.pH, x0 = ox * p.sW - p.pW;
+    int z1, y1, x1;
+    float div = 1.f;
+    if (p.is_max) {
+      z1 = min(z0 + p.KD, p.ID); y1 = min(y0 + p.KH, p.IH); x1 = min(x0 + p.KW, p.IW);
+    } else {
+      z1 = min(z0 + p.KD, p.ID + p.pD); y1 = min(y0 + p.KH, p.IH + p.pH); x1 = min(x0 + p.KW, p.IW + p.pW);
+      div = (float)((z1 - z0) * (y1 - y0) * (x1 - x0));
+      z1 = min(z1, p.ID); y1 = min(y1, p.IH); x1 = min(x1, p.IW);
+    }
+    z0 = max(z0, 0); y0 = max(y0, 0); x0 = max(x0, 0);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = p.is_max ? -FLT_MAX : 0.f;
+    for (int z = z0; z < z1; ++z)
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+          const long long pix = ((n * p.ID + z) * p.IH + y) * p.IW + x;
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.x + pix * p.x_cs + p.x_coff + g * 8));
+          float f[8];
+          unpack8(v, f);
+          if (p.is_max) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], f[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+          }
+        }
+    if (!p.is_max) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] /= div;
+    }
+    const long long opix = ((n * p.OD + oz) * p.OH + oy) * p.OW + ox;
+    *reinterpret_cast<uint4*>(p.y + opix * p.y_cs + p.y_coff + g * 8) = pack8(acc);
+  }
+}
+
+// global average: one thread per (outer, channel); consecutive threads read consecutive channels
+__global__ void global_avg_cl_kernel(ClView s, float* __restrict__ dst) {
+  const long long total = s.outer * s.C;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % s.C);
+    const long long o = t / s.C;
+    const __nv_bfloat16* px = s.ptr + o * s.inner * s.cs + s.coff + c;
+    float acc = 0.f;
+    for (long long i = 0; i < s.inner; ++i) acc += __bfloat162float(px[i * s.cs]);
+    dst[t] = acc / (float)s.inner;
+  }
+}
+
+__global__ void pool_f32_kernel(const PoolF32Params p) {
+  const long long total = (long long)p.NC * p.OD * p.OH * p.OW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    const int ox = (int)(r % p.OW); r /= p.OW;
+    const int oy = (int)(r % p.OH); r /= p.OH;
+    const int oz = (int)(r % p.OD);
+    const long long nc = r / p.OD;
+    int z0 = oz * p.sD - p.pD, y0 = oy * p.sH - p.pH, x0 = ox * p.sW - p.pW;
+    int z1, y1, x1;
+    float div = 1.f;
+    if (p.is_max) {
+      z1 = min(z0 + p.KD, p.ID); y1 = min(y0 + p.KH, p.IH); x1 = min(x0 + p.KW, p.IW);
+    } else {
+      z1 = min(z0 + p.KD, p.ID + p.pD); y1 = min(y0 + p.KH, p.IH + p.pH); x1 = min(x0 + p.KW, p.IW + p.pW);
+      div = (float)((z1 - z0) * (y1 - y0) * (x1 - x0));
+      z1 = min(z1, p.ID); y1 = min(y1, p.IH); x1 = min(x1, p.IW);
+    }
+    z0 = max(z0, 0); y0 = max(y0, 0); x0 = max(x0, 0);
+    const float* px = p.x + nc * (long long)p.ID * p.IH * p.IW;
+    float acc = p.is_max ? -FLT_MAX : 0.f;
+    for (int z = z0; z < z1; ++z)
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+          const float v = px[((long long)z * p.IH + y) * p.IW + x];
+          acc = p.is_max ? fmaxf(acc, v) : acc + v;
+        }
+    p.y[t] = p.is_max ? acc : acc / div;
+  }
+}
+
+// ---------------------------------------------------------------- inner product (one warp per output)
+__global__ void inner_product_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ b, float* __restrict__ y, int M, int N, int K) {
+  const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_id >= (long long)M * N) return;
+  const int n = (int)(warp_id % N);
+  const long long m = warp_id / N;
+  const float* xp = x + m * K;
+  const float* wp = w + (long long)n * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(xp[k], wp[k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[warp_id] = acc + (b ? b[n] : 0.f);
+}
+
+__global__ void scale_shift_relu_cl_kernel(ClView x, ClView y, const float* __restrict__ scale,
+                                           const float* __restrict__ shift, int relu) {
+  const long long total = x.outer * x.inner * x.C;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % x.C);
+    const long long pix = t / x.C;
+    float v = __bfloat162float(x.ptr[pix * x.cs + x.coff + c]);
+    v = fmaf(v, scale[c], shift[c]);
+    if (relu) v = fmaxf(v, 0.f);
+    y.ptr[pix * y.cs + y.coff + c] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void eltwise_sum_cl_kernel(ClView a, ClView b, ClView y) {
+  const long long total = a.outer * a.inner * a.C;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % a.C);
+    const long long pix = t / a.C;
+    const float v = __bfloat162float(a.ptr[pix * a.cs + a.coff + c]) + __bfloat162float(b.ptr[pix * b.cs + b.coff + c]);
+    y.ptr[pix * y.cs + y.coff + c] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void softmax_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int M, int N) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* xp = x + (long long)m * N;
+  float* yp = y + (long long)m * N;
+  float mx = xp[0];
+  for (int n = 1; n < N; ++n) mx = fmaxf(mx, xp[n]);
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) { const float e = expf(xp[n] - mx); yp[n] = e; s += e; }
+  for (int n = 0; n < N; ++n) yp[n] /= s;
+}
+
+inline int grid_cap(long long n) {
+  long long b = (n + kThreads - 1) / kThreads;
+  const long long cap = 148LL * 32;  // grid-stride above this
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+cudaError_t launch_f32_to_cl(const float* src, ClView dst, cudaStream_t st) {
+  const long long n = dst.outer * dst.inner * dst.C;
+  if (n == 0) return cudaSuccess;
+  f32_to_cl_kernel<<<grid_cap(n), kThreads, 0, st>>>(src, dst);
+  return cudaGetLastError();
+}
+cudaError_t launch_cl_to_f32(ClView src, float* dst, cudaStream_t st) {
+  const long long n = src.outer * src.inner * src.C;
+  if (n == 0) return cudaSuccess;
+  cl_to_f32_kernel<<<grid_cap(n), kThreads, 0, st>>>(src, dst);
+  return cudaGetLastError();
+}
+cudaError_t launch_stem_s2d(const float* src, __nv_bfloat16* dst, int F, int H, int W, int CH, int CW,
+                            cudaStream_t st) {
+  const long long n = (long long)F * CH * CW;
+  if (n == 0) return cudaSuccess;
+  stem_s2d_kernel<<<grid_cap(n), kThreads, 0, st>>>(src, dst, F, H, W, CH, CW);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {
+  const long long n = (long long)p.NB * p.OD * p.OH * p.OW * (p.C / 8);
+  if (n == 0) return cudaSuccess;
+  pool_cl_kernel<<<grid_cap(n), kThreads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_global_avg_cl(ClView src, float* dst, cudaStream_t st) {
+  const long long n = src.outer * src.C;
+  if (n == 0) return cudaSuccess;
+  global_avg_cl_kernel<<<grid_cap(n), kThreads, 0, st>>>(src, dst);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_f32(const PoolF32Params& p, cudaStream_t st) {
+  const long long n = (long long)p.NC * p.OD * p.OH * p.OW;
+  if (n == 0) return cudaSuccess;
+  pool_f32_kernel<<<grid_cap(n), kThreads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_inner_product(const float* x, const float* w, const float* b, float* y, int M, int N, int K,
+                                 cudaStream_t st) {
+  const long long warps = (long long)M * N;
+  if (warps == 0) return cudaSuccess;
+  inner_product_kernel<<<blocks_for(warps * 32), kThreads, 0, st>>>(x, w, b, y, M, N, K);
+  return cudaGetLastError();
+}
+cudaError_t launch_scale_shift_relu_cl(ClView x, ClView y, const float* scale, const float* shift, int relu,
+                                       cudaStream_t st) {
+  const long long n = x.outer * x.inner * x.C;
+  if (n == 0) return cudaSuccess;
+  scale_shift_relu_cl_kernel<<<grid_cap(n), kThreads, 0, st>>>(x, y, scale, shift, relu);
+  return cudaGetLastError();
+}
+cudaError_t launch_eltwise_sum_cl(ClView a, ClView b, ClView y, cudaStream_t st) {
+  const long long n = a.outer * a.inner * a.C;
+  if (n == 0) return cudaSuccess;
+  eltwise_sum_cl_kernel<<<grid_cap(n), kThreads, 0, st>>>(a, b, y);
+  return cudaGetLastError();
+}
+cudaError_t launch_softmax_f32(const float* x, float* y, int M, int N, cudaStream_t st) {
+  if (M == 0) return cudaSuccess;
+  softmax_f32_kernel<<<(M + 127) / 128, 128, 0, st>>>(x, y, M, N);
+  return cudaGetLastError();
+}
+
+}  // namespace eco

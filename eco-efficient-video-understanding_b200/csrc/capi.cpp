@@ -1,0 +1,286 @@
+// capi.cpp -- extern "C" boundary of libeco_b200.so (include/eco_b200.h).  Every entry point
+// catches C++ exceptions and turns them into a non-zero return + eco_last_error().
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+
+#include "../../include/eco_b200.h"
+#include "net.hpp"
+
+struct eco_net {
+  eco::Net* impl;
+};
+
+namespace eco {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+}  // namespace eco
+
+#define ECO_API_BEGIN try {
+#define ECO_API_END                         \
+  }                                         \
+  catch (const std::exception& e) {         \
+    eco::set_last_error(e.what());          \
+    return 1;                               \
+  }                                         \
+  catch (...) {                             \
+    eco::set_last_error("unknown error");   \
+    return 1;                               \
+  }                                         \
+  return 0;
+
+static int g_mode_gpu = 1;
+
+static eco::Net& N(eco_net* n) {
+  if (!n || !n->impl) throw std::runtime_error("null eco_net handle");
+  return *n->impl;
+}
+static const eco::Net& N(const eco_net* n) {
+  if (!n || !n->impl) throw std::runtime_error("null eco_net handle");
+  return *n->impl;
+}
+
+extern "C" {
+
+const char* eco_last_error(void) { return eco::g_last_error.c_str(); }
+const char* eco_version(void) { return "eco_b200 0.1 (sm_100a)"; }
+
+int eco_set_device(int device) {
+  ECO_API_BEGIN
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("cudaSetDevice failed: ") + cudaGetErrorString(e));
+  ECO_API_END
+}
+int eco_set_mode(int gpu) {
+  g_mode_gpu = gpu ? 1 : 0;
+  return 0;
+}
+int eco_device_count(int* count) {
+  ECO_API_BEGIN
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  if (count) *count = n;
+  ECO_API_END
+}
+
+int eco_net_create_from_string(const char* text, int phase, eco_net** out) {
+  ECO_API_BEGIN
+  if (!text || !out) throw std::runtime_error("null argument");
+  eco_net* h = new eco_net;
+  h->impl = nullptr;
+  try {
+    h->impl = new eco::Net(text, phase);
+  } catch (...) {
+    delete h;
+    throw;
+  }
+  *out = h;
+  ECO_API_END
+}
+int eco_net_create(const char* path, int phase, eco_net** out) {
+  ECO_API_BEGIN
+  if (!path) throw std::runtime_error("null path");
+  std::ifstream f(path);
+  if (!f) throw std::runtime_error(std::string("Could not open ") + path);  // _caffe.cpp:57-64
+  std::stringstream ss;
+  ss << f.rdbuf();
+  const std::string text = ss.str();
+  int rc = eco_net_create_from_string(text.c_str(), phase, out);
+  if (rc) return rc;
+  ECO_API_END
+}
+int eco_net_destroy(eco_net* net) {
+  ECO_API_BEGIN
+  if (net) {
+    delete net->impl;
+    delete net;
+  }
+  ECO_API_END
+}
+int eco_net_set_option(eco_net* net, const char* key, int value) {
+  ECO_API_BEGIN
+  N(net).set_option(key ? key : "", value);
+  ECO_API_END
+}
+int eco_net_set_stream(eco_net* net, void* s) {
+  ECO_API_BEGIN
+  N(net).set_stream(static_cast<cudaStream_t>(s));
+  ECO_API_END
+}
+
+int eco_net_copy_from(eco_net* net, const char* path) {
+  ECO_API_BEGIN
+  N(net).copy_from(path ? path : "");
+  ECO_API_END
+}
+int eco_net_save(const eco_net* net, const char* path) {
+  ECO_API_BEGIN
+  N(net).save(path ? path : "");
+  ECO_API_END
+}
+int eco_net_layer_num_params(const eco_net* net, int layer, int* n) {
+  ECO_API_BEGIN
+  *n = N(net).num_params(layer);
+  ECO_API_END
+}
+int eco_net_param_shape(const eco_net* net, int layer, int idx, int* dims, int* ndims) {
+  ECO_API_BEGIN
+  const eco::ParamBlob& b = const_cast<eco::Net&>(N(net)).param(layer, idx);
+  if (*ndims < (int)b.shape.size()) throw std::runtime_error("dims capacity too small");
+  for (size_t i = 0; i < b.shape.size(); ++i) dims[i] = b.shape[i];
+  *ndims = (int)b.shape.size();
+  ECO_API_END
+}
+int eco_net_set_param(eco_net* net, int layer, int idx, const float* data, size_t count) {
+  ECO_API_BEGIN
+  N(net).set_param(layer, idx, data, count);
+  ECO_API_END
+}
+int eco_net_get_param(const eco_net* net, int layer, int idx, float* data, size_t count) {
+  ECO_API_BEGIN
+  const eco::ParamBlob& b = const_cast<eco::Net&>(N(net)).param(layer, idx);
+  if (count != b.data.size()) throw std::runtime_error("parameter size mismatch");
+  std::memcpy(data, b.data.data(), count * sizeof(float));
+  ECO_API_END
+}
+int eco_net_param_host(eco_net* net, int layer, int idx, float** data, size_t* count) {
+  ECO_API_BEGIN
+  eco::ParamBlob& b = N(net).param(layer, idx);
+  N(net).mark_params_dirty(layer);  // caller may write through the pointer (mutable_cpu_data semantics)
+  *data = b.data.data();
+  if (count) *count = b.data.size();
+  ECO_API_END
+}
+
+const char* eco_net_name(const eco_net* net) { return net && net->impl ? net->impl->name_.c_str() : ""; }
+int eco_net_phase(const eco_net* net) { return net && net->impl ? net->impl->phase_ : -1; }
+int eco_net_num_layers(const eco_net* net) { return net && net->impl ? (int)net->impl->vis_layers_.size() : -1; }
+const char* eco_net_layer_name(const eco_net* net, int i) {
+  if (!net || !net->impl || i < 0 || i >= (int)net->impl->vis_layers_.size()) return nullptr;
+  return net->impl->vis_layers_[i].name.c_str();
+}
+const char* eco_net_layer_type(const eco_net* net, int i) {
+  if (!net || !net->impl || i < 0 || i >= (int)net->impl->vis_layers_.size()) return nullptr;
+  return net->impl->vis_layers_[i].type.c_str();
+}
+int eco_net_layer_index(const eco_net* net, const char* name) {
+  if (!net || !net->impl || !name) return -1;
+  auto it = net->impl->vis_layer_index_.find(name);
+  return it == net->impl->vis_layer_index_.end() ? -1 : it->second;
+}
+int eco_net_layer_num_bottoms(const eco_net* net, int i) {
+  if (!net || !net->impl || i < 0 || i >= (int)net->impl->vis_layers_.size()) return -1;
+  return (int)net->impl->vis_layers_[i].bottoms.size();
+}
+int eco_net_layer_bottom(const eco_net* net, int i, int j) {
+  if (eco_net_layer_num_bottoms(net, i) <= j || j < 0) return -1;
+  return net->impl->vis_layers_[i].bottoms[j];
+}
+int eco_net_layer_num_tops(const eco_net* net, int i) {
+  if (!net || !net->impl || i < 0 || i >= (int)net->impl->vis_layers_.size()) return -1;
+  return (int)net->impl->vis_layers_[i].tops.size();
+}
+int eco_net_layer_top(const eco_net* net, int i, int j) {
+  if (eco_net_layer_num_tops(net, i) <= j || j < 0) return -1;
+  return net->impl->vis_layers_[i].tops[j];
+}
+int eco_net_num_blobs(const eco_net* net) { return net && net->impl ? (int)net->impl->vis_blobs_.size() : -1; }
+const char* eco_net_blob_name(const eco_net* net, int i) {
+  if (!net || !net->impl || i < 0 || i >= (int)net->impl->vis_blobs_.size()) return nullptr;
+  return net->impl->vis_blobs_[i].name.c_str();
+}
+int eco_net_blob_index(const eco_net* net, const char* name) {
+  if (!net || !net->impl || !name) return -1;
+  auto it = net->impl->vis_blob_index_.find(name);
+  return it == net->impl->vis_blob_index_.end() ? -1 : it->second;
+}
+int eco_net_blob_shape(const eco_net* net, int i, int* dims, int* ndims) {
+  ECO_API_BEGIN
+  const eco::Net& n = N(net);
+  if (i < 0 || i >= (int)n.vis_blobs_.size()) throw std::runtime_error("blob index out of range");
+  const auto& s = n.tensors_[n.vis_blobs_[i].tensor].shape;
+  if (*ndims < (int)s.size()) throw std::runtime_error("dims capacity too small");
+  for (size_t k = 0; k < s.size(); ++k) dims[k] = s[k];
+  *ndims = (int)s.size();
+  ECO_API_END
+}
+int eco_net_num_inputs(const eco_net* net) { return net && net->impl ? (int)net->impl->inputs_.size() : -1; }
+int eco_net_input_blob(const eco_net* net, int i) {
+  if (!net || !net->impl || i < 0 || i >= (int)net->impl->inputs_.size()) return -1;
+  return net->impl->inputs_[i];
+}
+int eco_net_num_outputs(const eco_net* net) { return net && net->impl ? (int)net->impl->outputs_.size() : -1; }
+int eco_net_output_blob(const eco_net* net, int i) {
+  if (!net || !net->impl || i < 0 || i >= (int)net->impl->outputs_.size()) return -1;
+  return net->impl->outputs_[i];
+}
+
+int eco_blob_reshape(eco_net* net, int blob, const int* dims, int ndims) {
+  ECO_API_BEGIN
+  N(net).reshape_blob(blob, std::vector<int>(dims, dims + ndims));
+  ECO_API_END
+}
+int eco_net_reshape(eco_net* net) {
+  ECO_API_BEGIN
+  N(net).reshape();
+  ECO_API_END
+}
+
+int eco_net_forward(eco_net* net, int start, int end, float* loss) {
+  ECO_API_BEGIN
+  if (!g_mode_gpu)
+    throw std::runtime_error("set_mode_cpu() was requested: libeco_b200 has no CPU execution path (call set_mode_gpu())");
+  const float l = N(net).forward(start, end);
+  if (loss) *loss = l;
+  ECO_API_END
+}
+int eco_net_backward(eco_net* net, int start, int end) {
+  ECO_API_BEGIN
+  (void)start;
+  (void)end;
+  N(net);
+  throw std::runtime_error("Backward is not implemented in this round (training config is a later row of SURVEY.md section 8)");
+  ECO_API_END
+}
+int eco_net_sync(eco_net* net) {
+  ECO_API_BEGIN
+  N(net).sync();
+  ECO_API_END
+}
+
+int eco_blob_host_data(eco_net* net, int blob, int for_write, float** data, size_t* count) {
+  ECO_API_BEGIN
+  *data = N(net).host_data(blob, for_write != 0, count);
+  ECO_API_END
+}
+int eco_blob_host_diff(eco_net* net, int blob, int for_write, float** data, size_t* count) {
+  ECO_API_BEGIN
+  *data = N(net).host_diff(blob, for_write != 0, count);
+  ECO_API_END
+}
+int eco_net_set_input_device(eco_net* net, int blob, const void* dev, size_t count) {
+  ECO_API_BEGIN
+  N(net).set_input_device(blob, dev, count);
+  ECO_API_END
+}
+int eco_blob_device_f32(eco_net* net, int blob, const float** dev, size_t* count) {
+  ECO_API_BEGIN
+  *dev = N(net).device_f32(blob, count);
+  ECO_API_END
+}
+int eco_net_last_launch_count(const eco_net* net, int* launches) {
+  ECO_API_BEGIN
+  *launches = N(net).last_launches();
+  ECO_API_END
+}
+int eco_net_profile_forward(eco_net* net, eco_op_time* out, int cap, int* n) {
+  ECO_API_BEGIN
+  *n = N(net).profile(out, cap);
+  ECO_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,375 @@
+// conv_umma.cu -- fused implicit-GEMM convolution on tcgen05 tensor cores (sm_100a only).
+//
+// Tile: 128 output positions (TMEM lanes) x block_n output channels (TMEM fp32 columns),
+// K consumed in 64-element blocks (one tap x 64 channels) through an mbarrier ring:
+//
+//   warp 0 (1 lane)  : TMA producer -- weights [Cout, K] K-major via cp.async.bulk.tensor.2d,
+//                      activations via cp.async.bulk.tensor.{4,5}d im2col (A_TMA_IM2COL)
+//   warps 2-5        : A_GATHER mode: cp.async zero-filling software im2col into the same
+//                      128B-swizzled layout, completion tracked by cp.async.mbarrier.arrive.noinc;
+//                      afterwards (both modes) the epilogue: tcgen05.ld -> +bias (+residual)
+//                      -> optional raw store -> BN scale/shift -> ReLU -> bf16 store into a
+//                      channel slice of the destination (concat fusion)
+//   warp 1 (1 lane)  : tcgen05.mma issuer, accumulators in TMEM; owns TMEM alloc/dealloc
+//
+// Every mbarrier wait is bounded: a wait that exceeds ~2 s sets *error_flag and traps, so a
+// protocol bug fails loudly instead of hanging the GPU.
+#include "conv_umma.cuh"
+
+namespace eco {
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (err) atomicExch(err, code);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w,
+                                              int h, int n, uint16_t ow, uint16_t oh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+      : "memory");
+}
+__device__ __forceinline__ void tma_im2col_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w,
+                                              int h, int d, int n, uint16_t ow, uint16_t oh, uint16_t od) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"(ow),
+      "h"(oh), "h"(od)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 "version 1"):
+//   rows are 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused (=1) for swizzled K-major.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (ignored for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=block_n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const float (&f)[16], int nvalid) {
+  if (nvalid >= 16) {
+    uint4 a, b;
+    a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
+    a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
+    b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
+    b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
+    reinterpret_cast<uint4*>(dst)[0] = a;
+    reinterpret_cast<uint4*>(dst)[1] = b;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) dst[j] = __float2bfloat16_rn(f[j]);
+  }
+}
+__device__ __forceinline__ void load16_bf16_add(const __nv_bfloat16* src, float (&f)[16], int nvalid) {
+  if (nvalid >= 16) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+      f[2 * j] += __low2float(t);
+      f[2 * j + 1] += __high2float(t);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) f[j] += __bfloat162float(src[j]);
+  }
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_umma_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap tmA,
+                 const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const int S = p.stages;
+  const int BN = p.block_n;
+  const uint32_t a_stage_bytes = kBlockM * 128;
+  const uint32_t b_stage_bytes = (uint32_t)BN * 128;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + S * a_stage_bytes;
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)S * a_stage_bytes + (size_t)S * b_stage_bytes);
+  float* s_scale = s_bias + 256;
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  const uint32_t bar_full = smem_u32(bars);             // [S]
+  const uint32_t bar_empty = bar_full + 8 * S;          // [S]
+  const uint32_t bar_tmem_full = bar_empty + 8 * S;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int n0 = blockIdx.y * BN;
+  const bool tma_a = (p.a_mode == A_TMA_IM2COL);
+
+  if (threadIdx.x == 0) {
+    const uint32_t full_count = tma_a ? 1u : 1u + 128u;
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, full_count);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    // stage per-channel epilogue constants for this N tile
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      const int c = n0 + i;
+      const bool ok = c < p.Cout;
+      s_bias[i] = (ok && p.bias) ? p.bias[c] : 0.f;
+      s_scale[i] = (ok && p.scale) ? p.scale[c] : 1.f;
+      s_shift[i] = (ok && p.scale) ? p.shift[c] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = p.num_kb;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int q = 0, pp = 0, z = 0, n = 0;
+      if (tma_a) {
+        int t = m0;
+        q = t % p.OW; t /= p.OW;
+        pp = t % p.OH; t /= p.OH;
+        z = t % p.OD; n = t / p.OD;
+      }
+      const int cw = q * p.sW - p.pW, chh = pp * p.sH - p.pH, cd = z * p.sD - p.pD;
+      int cb = 0, kx = 0, ky = 0, kz = 0;
+      const uint32_t tx_bytes = b_stage_bytes + (tma_a ? a_stage_bytes : 0u);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (uint32_t)(kb / S) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
+        mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
+        tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
+        if (tma_a) {
+          if (p.nsp == 3)
+            tma_im2col_5d(sA + s * a_stage_bytes, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, cd, n,
+                          (uint16_t)kx, (uint16_t)ky, (uint16_t)kz);
+          else
+            tma_im2col_4d(sA + s * a_stage_bytes, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, n,
+                          (uint16_t)kx, (uint16_t)ky);
+        }
+        if (++cb == p.cblocks) {
+          cb = 0;
+          if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++kz; } }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (uint32_t)(kb / S) & 1u;
+        mbar_wait(bar_full + 8 * s, ph, p.error_flag, 2);
+        if (!tma_a) fence_proxy_async_smem();  // cp.async (generic proxy) writes -> async-proxy reads
+        tc_fence_after();
+        const uint64_t adesc = make_sw128_desc(sA + s * a_stage_bytes);
+        const uint64_t bdesc = make_sw128_desc(sB + s * b_stage_bytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+        }
+        umma_commit(bar_empty + 8 * s);  // frees the smem slot when these MMAs retire
+      }
+      umma_commit(bar_tmem_full);        // accumulator complete
+    }
+  } else {
+    // ===================== gather producers (A_GATHER) then epilogue =====================
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    if (!tma_a) {
+      int q = 0, pp = 0, z = 0, n = 0;
+      if (row_ok) {
+        int t = m;
+        q = t % p.OW; t /= p.OW;
+        pp = t % p.OH; t /= p.OH;
+        z = t % p.OD; n = t / p.OD;
+      }
+      const int x0 = q * p.sW - p.pW, y0 = pp * p.sH - p.pH, z0 = z * p.sD - p.pD;
+      const __nv_bfloat16* xn = p.x + (long long)n * p.x_sN;
+      const uint32_t row_off = (uint32_t)row * 128u;
+      const uint32_t sw = (uint32_t)(row & 7);
+      int cb = 0, kx = 0, ky = 0, kz = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (uint32_t)(kb / S) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 3);
+        const int iz = z0 + kz, iy = y0 + ky, ix = x0 + kx;
+        const bool ok = row_ok && (unsigned)iz < (unsigned)p.ID && (unsigned)iy < (unsigned)p.IH &&
+                        (unsigned)ix < (unsigned)p.IW;
+        const __nv_bfloat16* src =
+            ok ? xn + (long long)iz * p.x_sD + (long long)iy * p.x_sH + (long long)ix * p.x_sW + cb * kBlockK : p.x;
+        const int crem = p.Cin - cb * kBlockK;  // channels left in this tap
+        const uint32_t dst = sA + s * a_stage_bytes + row_off;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool cok = ok && (j * 8 < crem);
+          cp_async_16(dst + ((((uint32_t)j) ^ sw) << 4), cok ? (const void*)(src + j * 8) : (const void*)p.x,
+                      cok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(bar_full + 8 * s);
+        if (++cb == p.cblocks) {
+          cb = 0;
+          if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++kz; } }
+        }
+      }
+    }
+    // ---------------- epilogue ----------------
+    mbar_wait(bar_tmem_full, 0, p.error_flag, 4);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const bool has_scale = p.scale != nullptr;
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      const int cg = n0 + c0;
+      const int nvalid = p.Cout - cg;
+      if (row_ok && nvalid > 0) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+        if (p.res) load16_bf16_add(p.res + (long long)m * p.res_cs + p.res_coff + cg, f, nvalid);
+        if (p.raw) store16_bf16(p.raw + (long long)m * p.raw_cs + p.raw_coff + cg, f, nvalid);
+        if (p.out) {
+          if (has_scale) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaf(f[j], s_scale[c0 + j], s_shift[c0 + j]);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          store16_bf16(p.out + (long long)m * p.out_cs + p.out_coff + cg, f, nvalid);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+}  // namespace
+
+cudaError_t conv_umma_configure() {
+  return cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_conv_umma(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                             cudaStream_t stream) {
+  dim3 grid((p.M + kBlockM - 1) / kBlockM, (p.Cout + p.block_n - 1) / p.block_n, 1);
+  const size_t smem = conv_smem_bytes(p.block_n, p.stages);
+  conv_umma_kernel<<<grid, kConvThreads, smem, stream>>>(p, tmA, tmB);
+  return cudaGetLastError();
+}
+
+}  // namespace eco

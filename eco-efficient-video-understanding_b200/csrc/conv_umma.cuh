@@ -1,0 +1,71 @@
+// conv_umma.cuh -- parameters of the fused implicit-GEMM convolution kernel (sm_100a).
+//
+// One kernel family serves every Convolution on ECO's path (2-D 1x1/3x3/7x7-stem, 3-D 3x3x3,
+// stride 1/2): GEMM M = output positions (N*D*H*W, channels-last), N = Cout, K = taps * Cin.
+// Replaces the reference's per-image im2col + SGEMM (caffe_3d/src/caffe/layers/conv_layer.cpp:28-43,
+// base_conv_layer.cpp:264-287, util/im2col.cu:12-161) and the BN / ReLU / Eltwise / Concat layers
+// that follow it (bn_layer.cu:12-124, relu_layer.cu:10-27, eltwise_layer.cu:48-54,
+// concat_layer.cu:10-27), which are folded into the epilogue.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace eco {
+
+constexpr int kBlockM = 128;      // UMMA M (cta_group::1), one TMEM lane per output position
+constexpr int kBlockK = 64;       // bf16 elements per K block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
+constexpr int kConvThreads = 192; // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-5: gather/epilogue
+
+enum AMode : int {
+  A_GATHER = 0,      // cp.async software im2col into the 128B-swizzled tile (any geometry)
+  A_TMA_IM2COL = 1,  // one cp.async.bulk.tensor ... im2col per K block
+};
+
+struct ConvKernelParams {
+  // ---- A operand: bf16 channels-last activations, element strides ----
+  const __nv_bfloat16* x;
+  long long x_sN, x_sD, x_sH, x_sW;  // strides in elements (channel stride is 1)
+  int Cin;                           // channels per tap actually present (tail of a 64-block is zero-filled)
+  int ID, IH, IW;                    // input extent (D = 1 for 2-D)
+  int OD, OH, OW;                    // output extent
+  int KD, KH, KW;
+  int sD, sH, sW;
+  int pD, pH, pW;
+  int M;                             // NB * OD * OH * OW
+  int cblocks;                       // ceil(Cin / 64)
+  int num_kb;                        // KD*KH*KW*cblocks
+  int a_mode;
+  int nsp;                           // 2 or 3 spatial dims (selects the 4-D / 5-D TMA form)
+  // ---- tile shape ----
+  int block_n;                       // multiple of 16, <= 256
+  int stages;
+  int tmem_cols;                     // power of two >= block_n, >= 32
+  // ---- epilogue:  raw = acc + bias (+ res);  y = relu?(raw * scale + shift) ----
+  int Cout;
+  const float* bias;                 // [Cout] or null
+  const float* scale;                // [Cout] or null (then y = raw)
+  const float* shift;                // [Cout] (with scale)
+  int relu;
+  __nv_bfloat16* out;   long long out_cs;  int out_coff;   // y   (null -> not stored)
+  __nv_bfloat16* raw;   long long raw_cs;  int raw_coff;   // raw (null -> not stored)
+  const __nv_bfloat16* res; long long res_cs; int res_coff;  // residual added into raw (null -> none)
+  int* error_flag;                   // set non-zero if an mbarrier wait times out
+};
+
+// dynamic shared memory needed for (block_n, stages)
+inline size_t conv_smem_bytes(int block_n, int stages) {
+  size_t a = (size_t)stages * kBlockM * 128;
+  size_t b = (size_t)stages * block_n * 128;
+  size_t epi = 3 * 256 * sizeof(float);
+  size_t bars = 64 * 8;
+  return 1024 /*alignment slack*/ + a + b + epi + bars;
+}
+
+cudaError_t launch_conv_umma(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                             cudaStream_t stream);
+cudaError_t conv_umma_configure();  // sets max dynamic smem attribute once
+
+}  // namespace eco

@@ -1,0 +1,1704 @@
+// net.cpp -- graph construction (caffe-visible names), shape inference, the fusing planner and
+// the executor.  Reference behaviour followed, by function:
+//   build_graph      Net::Init / FilterNet / InsertSplits   caffe_3d/src/caffe/net.cpp:39-316,319-346;
+//                                                           util/insert_splits.cpp:13-142
+//   infer_shapes     each layer's Reshape: conv_layer.cpp:12-25, pooling_layer.cpp:117-163,
+//                    concat_layer.cpp:17-50, reshape_layer.cpp:31-90, permute_layer.cpp:29-73,
+//                    inner_product_layer.cpp:13-77, bn_layer.cpp:11-90
+//   init_params      fillers (include/caffe/filler.hpp) -- values are NOT bit-identical to caffe's
+//                    boost RNG; the parity harness always writes its own weights
+//   plan / run_op    replaces Layer::Forward dispatch (layer.hpp:444-477) with fused sm_100a ops
+#include "net.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <random>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+
+#include "../../include/eco_b200.h"
+
+namespace eco {
+
+#define ECO_CHECK(cond, msg)                                                       \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      std::ostringstream _o;                                                       \
+      _o << msg << "  [" << #cond << " @ " << __FILE__ << ":" << __LINE__ << "]"; \
+      throw std::runtime_error(_o.str());                                          \
+    }                                                                              \
+  } while (0)
+
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      std::ostringstream _o;                                                                       \
+      _o << "CUDA error " << cudaGetErrorName(_e) << ": " << cudaGetErrorString(_e) << " in " #expr \
+         << " @ " << __FILE__ << ":" << __LINE__;                                                  \
+      throw std::runtime_error(_o.str());                                                          \
+    }                                                                                              \
+  } while (0)
+
+static int g_device_ok = -1;  // -1 unknown, 0 none, 1 ok
+static bool device_available() {
+  if (g_device_ok < 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    g_device_ok = n > 0 ? 1 : 0;
+  }
+  return g_device_ok == 1;
+}
+
+void HostBuf::release() {
+  if (p) {
+    if (pinned) cudaFreeHost(p);
+    else std::free(p);
+  }
+  p = nullptr;
+  n = 0;
+  pinned = false;
+}
+void HostBuf::resize(size_t count, bool try_pin) {
+  if (count == n && p) return;
+  release();
+  if (count == 0) return;
+  if (try_pin && device_available()) {
+    void* q = nullptr;
+    if (cudaMallocHost(&q, count * sizeof(float)) == cudaSuccess) {
+      p = static_cast<float*>(q);
+      pinned = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  if (!p) p = static_cast<float*>(std::malloc(count * sizeof(float)));
+  ECO_CHECK(p != nullptr, "host allocation of " << count * 4 << " bytes failed");
+  std::memset(p, 0, count * sizeof(float));
+  n = count;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static bool is_data_layer(const std::string& t) {
+  return t == "VideoData" || t == "Data" || t == "ImageData" || t == "MemoryData" || t == "Input" ||
+         t == "DummyData" || t == "HDF5Data" || t == "WindowData" || t == "SegData";
+}
+
+// ---- FilterNet restricted to phase rules (net.cpp:319-346, StateMeetsRule :349-411) ----
+static bool rule_ok(const pt::Msg& rule, const std::string& phase) {
+  if (rule.has("phase") && rule.str("phase") != phase) return false;
+  return true;  // level / stage rules are not used by models_ECO_*
+}
+static bool layer_in_phase(const pt::Msg& l, int phase) {
+  const std::string ph = phase == ECO_PHASE_TRAIN ? "TRAIN" : "TEST";
+  auto inc = l.all("include");
+  auto exc = l.all("exclude");
+  if (!inc.empty()) {
+    for (auto* r : inc)
+      if (r->msg && rule_ok(*r->msg, ph)) return true;
+    return false;
+  }
+  for (auto* r : exc)
+    if (r->msg && r->msg->has("phase") && r->msg->str("phase") == ph) return false;
+  return true;
+}
+
+// kernel_size / stride / pad: once, once per axis, or the 2-D *_h/*_w forms
+// (base_conv_layer.cpp:13-110, pooling_layer.cpp:17-114)
+static std::vector<int> nd_param(const pt::Msg& p, const char* key, const char* hw, int nsp, int def) {
+  std::string h = std::string(hw) + "_h", w = std::string(hw) + "_w";
+  if (p.has(h) || p.has(w)) {
+    ECO_CHECK(nsp == 2, hw << "_h/_w can only be used for 2-D layers");
+    return {(int)p.integer(h, def), (int)p.integer(w, def)};
+  }
+  auto v = p.integers(key);
+  if (v.empty()) {
+    ECO_CHECK(def >= 0, key << " must be specified");
+    return std::vector<int>(nsp, def);
+  }
+  if (v.size() == 1) return std::vector<int>(nsp, (int)v[0]);
+  ECO_CHECK((int)v.size() == nsp, key << " specified " << v.size() << " times for " << nsp << " spatial axes");
+  return std::vector<int>(v.begin(), v.end());
+}
+
+static int pool_out_dim(int in, int k, int s, int p) {
+  int out = (int)std::ceil((float)(in + 2 * p - k) / (float)s) + 1;  // pooling_layer.cpp:131-136
+  if (p && (out - 1) * s >= in + p) --out;                           // :137-147
+  return out;
+}
+
+// =====================================================================================
+Net::Net(const std::string& text, int phase) : phase_(phase) {
+  proto_ = pt::parse(text);
+  build_graph();
+  infer_shapes();
+  init_params();
+}
+
+Net::~Net() {
+  free_plan();
+  if (own_stream_ && stream_) cudaStreamDestroy(stream_);
+}
+
+int Net::add_tensor(const std::string& name) {
+  auto it = tensor_index_.find(name);
+  if (it != tensor_index_.end()) return it->second;
+  Tensor t;
+  t.name = name;
+  tensors_.push_back(std::move(t));
+  tensor_index_[name] = (int)tensors_.size() - 1;
+  return (int)tensors_.size() - 1;
+}
+
+void Net::build_graph() {
+  const pt::Msg& net = *proto_;
+  name_ = net.str("name");
+  ECO_CHECK(!net.has("layers"), "V1 'layers' net definitions are not supported (upgrade_net_proto_text first)");
+
+  // ---- net inputs: `input:` + `input_dim:` x4 (deprecated form, net.cpp:55-73) or `input_shape` ----
+  std::vector<std::string> in_names = net.strs("input");
+  std::vector<long> in_dims = net.integers("input_dim");
+  auto in_shapes = net.all("input_shape");
+  std::vector<std::pair<std::string, std::vector<int>>> net_inputs;
+  for (size_t i = 0; i < in_names.size(); ++i) {
+    std::vector<int> shp;
+    if (!in_shapes.empty()) {
+      ECO_CHECK(i < in_shapes.size() && in_shapes[i]->msg, "input_shape missing for input " << in_names[i]);
+      for (long d : in_shapes[i]->msg->integers("dim")) shp.push_back((int)d);
+    } else {
+      ECO_CHECK(in_dims.size() >= 4 * (i + 1), "input_dim must be given 4 times per input");
+      for (int k = 0; k < 4; ++k) shp.push_back((int)in_dims[4 * i + k]);
+    }
+    net_inputs.emplace_back(in_names[i], shp);
+  }
+
+  // ---- layers of this phase ----
+  std::vector<const pt::Msg*> lmsgs;
+  for (auto* v : net.all("layer"))
+    if (v->msg && layer_in_phase(*v->msg, phase_)) lmsgs.push_back(v->msg.get());
+
+  for (auto& ni : net_inputs) {
+    int t = add_tensor(ni.first);
+    tensors_[t].shape = ni.second;
+  }
+  for (const pt::Msg* m : lmsgs) {
+    OrigLayer L;
+    L.name = m->str("name");
+    L.type = m->str("type");
+    L.msg = m;
+    for (auto& b : m->strs("bottom")) {
+      auto it = tensor_index_.find(b);
+      ECO_CHECK(it != tensor_index_.end(),
+                "Unknown bottom blob '" << b << "' (layer '" << L.name << "')");  // net.cpp:428-431
+      L.bottoms.push_back(it->second);
+    }
+    for (auto& t : m->strs("top")) L.tops.push_back(add_tensor(t));
+    layers_.push_back(std::move(L));
+  }
+  // data layers feed their tops from the host: treat like net inputs with a declared shape
+  for (size_t li = 0; li < layers_.size(); ++li) {
+    OrigLayer& L = layers_[li];
+    if (!is_data_layer(L.type)) continue;
+    const pt::Msg* vp = L.msg->msg("video_data_param");
+    const pt::Msg* tp = L.msg->msg("transform_param");
+    int batch = vp ? (int)vp->integer("batch_size", 1) : 1;
+    int segs = vp ? (int)vp->integer("num_segments", 1) : 1;
+    int len = vp ? (int)vp->integer("new_length", 1) : 1;
+    int crop = tp ? (int)tp->integer("crop_size", 224) : 224;
+    std::string modality = vp ? vp->str("modality", "RGB") : "RGB";
+    int cpf = modality == "FLOW" ? 2 : 3;  // video_data_layer.cpp: channels per frame
+    if (L.tops.size() >= 1) tensors_[L.tops[0]].shape = {batch, cpf * segs * len, crop, crop};
+    if (L.tops.size() >= 2) tensors_[L.tops[1]].shape = {batch, 1, 1, 1};
+  }
+  // producers / consumers
+  for (size_t li = 0; li < layers_.size(); ++li) {
+    for (int b : layers_[li].bottoms) tensors_[b].consumers.push_back((int)li);
+    for (int t : layers_[li].tops) tensors_[t].producer = (int)li;
+  }
+
+  // ---- visible registry: replicate InsertSplits (insert_splits.cpp:13-142) ----
+  typedef std::pair<int, int> TopRef;  // (layer idx or -1 for net input, top idx)
+  std::map<std::string, TopRef> last_top;
+  std::map<TopRef, int> use_count;
+  std::map<std::pair<int, int>, TopRef> bottom_src;
+  for (size_t i = 0; i < net_inputs.size(); ++i) last_top[net_inputs[i].first] = TopRef(-1, (int)i);
+  for (size_t li = 0; li < layers_.size(); ++li) {
+    const OrigLayer& L = layers_[li];
+    for (size_t j = 0; j < L.bottoms.size(); ++j) {
+      const TopRef src = last_top[tensors_[L.bottoms[j]].name];
+      bottom_src[{(int)li, (int)j}] = src;
+      use_count[src]++;
+    }
+    for (size_t j = 0; j < L.tops.size(); ++j) last_top[tensors_[L.tops[j]].name] = TopRef((int)li, (int)j);
+  }
+  auto vis_blob = [&](const std::string& nm, int tensor) {
+    auto it = vis_blob_index_.find(nm);
+    if (it != vis_blob_index_.end()) return it->second;
+    vis_blobs_.push_back({nm, tensor});
+    vis_blob_index_[nm] = (int)vis_blobs_.size() - 1;
+    return (int)vis_blobs_.size() - 1;
+  };
+  auto split_layer_name = [](const std::string& layer, const std::string& blob, int idx) {
+    return blob + "_" + layer + "_" + std::to_string(idx) + "_split";
+  };
+  std::map<TopRef, int> next_split;
+  auto add_split = [&](const std::string& layer_name, const std::string& blob, int top_idx, int tensor, int count) {
+    VisLayer S;
+    S.name = split_layer_name(layer_name, blob, top_idx);
+    S.type = "Split";
+    S.bottoms.push_back(vis_blob(blob, tensor));
+    for (int k = 0; k < count; ++k) S.tops.push_back(vis_blob(S.name + "_" + std::to_string(k), tensor));
+    vis_layer_index_[S.name] = (int)vis_layers_.size();
+    vis_layers_.push_back(std::move(S));
+  };
+  for (size_t i = 0; i < net_inputs.size(); ++i) {
+    int t = tensor_index_[net_inputs[i].first];
+    inputs_.push_back(vis_blob(net_inputs[i].first, t));
+  }
+  for (size_t i = 0; i < net_inputs.size(); ++i) {
+    const TopRef r(-1, (int)i);
+    if (use_count[r] > 1) add_split("input", net_inputs[i].first, (int)i, tensor_index_[net_inputs[i].first], use_count[r]);
+  }
+  for (size_t li = 0; li < layers_.size(); ++li) {
+    OrigLayer& L = layers_[li];
+    VisLayer V;
+    V.name = L.name;
+    V.type = L.type;
+    V.orig = (int)li;
+    for (size_t j = 0; j < L.bottoms.size(); ++j) {
+      const TopRef src = bottom_src[{(int)li, (int)j}];
+      const std::string& blob = tensors_[L.bottoms[j]].name;
+      if (use_count[src] > 1) {
+        const std::string src_layer = src.first < 0 ? "input" : layers_[src.first].name;
+        const int k = next_split[src]++;
+        const std::string nm = split_layer_name(src_layer, blob, src.second) + "_" + std::to_string(k);
+        V.bottoms.push_back(vis_blob(nm, L.bottoms[j]));
+      } else {
+        V.bottoms.push_back(vis_blob(blob, L.bottoms[j]));
+      }
+    }
+    for (size_t j = 0; j < L.tops.size(); ++j) V.tops.push_back(vis_blob(tensors_[L.tops[j]].name, L.tops[j]));
+    L.vis_index = (int)vis_layers_.size();
+    vis_layer_index_[V.name] = (int)vis_layers_.size();
+    vis_layers_.push_back(std::move(V));
+    for (size_t j = 0; j < L.tops.size(); ++j) {
+      const TopRef r((int)li, (int)j);
+      if (use_count[r] > 1) add_split(L.name, tensors_[L.tops[j]].name, (int)j, L.tops[j], use_count[r]);
+    }
+    if (is_data_layer(L.type))
+      for (int t : L.tops) inputs_.push_back(vis_blob_index_[tensors_[t].name]);
+  }
+  // net outputs: blobs nobody consumes (net.cpp:283-291)
+  {
+    std::set<std::string> avail;
+    std::vector<std::string> order;
+    for (auto& ni : net_inputs) { avail.insert(ni.first); order.push_back(ni.first); }
+    for (auto& V : vis_layers_) {
+      for (int b : V.bottoms) avail.erase(vis_blobs_[b].name);
+      for (int t : V.tops)
+        if (avail.insert(vis_blobs_[t].name).second) order.push_back(vis_blobs_[t].name);
+    }
+    for (auto& nm : order)
+      if (avail.count(nm)) { outputs_.push_back(vis_blob_index_[nm]); avail.erase(nm); }
+  }
+}
+
+// =====================================================================================
+void Net::infer_shapes() {
+  for (size_t li = 0; li < layers_.size(); ++li) {
+    OrigLayer& L = layers_[li];
+    const std::string& t = L.type;
+    if (is_data_layer(t)) continue;
+    auto bshape = [&](int j) -> const std::vector<int>& {
+      ECO_CHECK(j < (int)L.bottoms.size(), "layer " << L.name << " needs bottom " << j);
+      return tensors_[L.bottoms[j]].shape;
+    };
+    auto set_top = [&](int j, const std::vector<int>& s) {
+      ECO_CHECK(j < (int)L.tops.size(), "layer " << L.name << " needs top " << j);
+      tensors_[L.tops[j]].shape = s;
+    };
+    auto set_param_shape = [&](size_t idx, const std::vector<int>& s) {
+      if (L.params.size() <= idx) L.params.resize(idx + 1);
+      if (L.params[idx].shape != s) {
+        ECO_CHECK(L.params[idx].shape.empty(), "layer " << L.name << ": parameter shape changes on reshape");
+        L.params[idx].shape = s;
+      }
+    };
+    if (t == "Convolution") {
+      const pt::Msg* p = L.msg->msg("convolution_param");
+      ECO_CHECK(p, "convolution_param missing in " << L.name);
+      const auto& b = bshape(0);
+      const int nsp = (int)b.size() - 2;
+      ECO_CHECK(nsp >= 1 && nsp <= 3, "Convolution " << L.name << ": " << nsp << " spatial axes unsupported");
+      auto k = nd_param(*p, "kernel_size", "kernel", nsp, -1);
+      auto s = nd_param(*p, "stride", "stride", nsp, 1);
+      auto pd = nd_param(*p, "pad", "pad", nsp, 0);
+      ECO_CHECK(p->integer("group", 1) == 1, "grouped convolution is not on ECO's path");
+      const int nout = (int)p->integer("num_output", 0);
+      ECO_CHECK(nout > 0, "num_output missing in " << L.name);
+      std::vector<int> o = {b[0], nout};
+      for (int i = 0; i < nsp; ++i) {
+        ECO_CHECK(k[i] > 0 && s[i] > 0, "Filter/stride dimensions must be nonzero (" << L.name << ")");
+        o.push_back((b[2 + i] + 2 * pd[i] - k[i]) / s[i] + 1);  // conv_layer.cpp:21-22
+        ECO_CHECK(o.back() > 0, "Convolution " << L.name << " output collapses");
+      }
+      set_top(0, o);
+      std::vector<int> ws = {nout, b[1]};
+      ws.insert(ws.end(), k.begin(), k.end());
+      set_param_shape(0, ws);
+      if (p->boolean("bias_term", true)) set_param_shape(1, {nout});
+    } else if (t == "BN") {
+      const auto& b = bshape(0);
+      set_top(0, b);
+      for (size_t i = 0; i < 4; ++i) set_param_shape(i, {1, b[1]});  // bn_layer.cpp:20-41
+    } else if (t == "ReLU" || t == "Dropout" || t == "Softmax") {
+      set_top(0, bshape(0));
+    } else if (t == "Pooling") {
+      const pt::Msg* p = L.msg->msg("pooling_param");
+      ECO_CHECK(p, "pooling_param missing in " << L.name);
+      const auto& b = bshape(0);
+      const int nsp = (int)b.size() - 2;
+      ECO_CHECK(nsp >= 1 && nsp <= 3, "Pooling " << L.name << ": " << nsp << " spatial axes unsupported");
+      std::vector<int> k;
+      if (p->boolean("global_pooling", false)) k.assign(b.begin() + 2, b.end());
+      else k = nd_param(*p, "kernel_size", "kernel", nsp, -1);
+      auto s = nd_param(*p, "stride", "stride", nsp, 1);
+      auto pd = nd_param(*p, "pad", "pad", nsp, 0);
+      std::vector<int> o = {b[0], b[1]};
+      for (int i = 0; i < nsp; ++i) {
+        ECO_CHECK(pd[i] < k[i], "pad must be smaller than kernel (" << L.name << ")");  // pooling_layer.cpp:112
+        o.push_back(pool_out_dim(b[2 + i], k[i], s[i], pd[i]));
+      }
+      set_top(0, o);
+    } else if (t == "Concat") {
+      const pt::Msg* p = L.msg->msg("concat_param");
+      const int axis = p ? (int)p->integer("axis", p->integer("concat_dim", 1)) : 1;
+      std::vector<int> o = bshape(0);
+      ECO_CHECK(axis >= 0 && axis < (int)o.size(), "Concat axis out of range in " << L.name);
+      for (size_t j = 1; j < L.bottoms.size(); ++j) {
+        const auto& b = bshape((int)j);
+        ECO_CHECK(b.size() == o.size(), "All inputs must have the same #axes (" << L.name << ")");
+        for (size_t a = 0; a < o.size(); ++a)
+          ECO_CHECK((int)a == axis || b[a] == o[a], "All inputs must have the same shape, except at concat_axis ("
+                                                        << L.name << ")");
+        o[axis] += b[axis];
+      }
+      set_top(0, o);
+    } else if (t == "Eltwise") {
+      ECO_CHECK(L.bottoms.size() >= 2, "Eltwise needs 2 bottoms (" << L.name << ")");
+      for (size_t j = 1; j < L.bottoms.size(); ++j)
+        ECO_CHECK(bshape((int)j) == bshape(0), "Eltwise bottoms must agree in shape (" << L.name << ")");
+      set_top(0, bshape(0));
+    } else if (t == "Reshape") {
+      const pt::Msg* p = L.msg->msg("reshape_param");
+      ECO_CHECK(p && p->msg("shape"), "reshape_param.shape missing in " << L.name);
+      ECO_CHECK(p->integer("axis", 0) == 0 && p->integer("num_axes", -1) == -1,
+                "reshape_param axis/num_axes are not used on ECO's path");
+      auto dims = p->msg("shape")->integers("dim");
+      const auto& b = bshape(0);
+      long long cnt = 1;
+      for (int d : b) cnt *= d;
+      std::vector<int> o;
+      int infer = -1;
+      long long known = 1;
+      for (size_t i = 0; i < dims.size(); ++i) {
+        if (dims[i] == 0) {
+          ECO_CHECK(i < b.size(), "reshape dim 0 copies a non-existent axis (" << L.name << ")");
+          o.push_back(b[i]);
+          known *= b[i];
+        } else if (dims[i] == -1) {
+          ECO_CHECK(infer < 0, "at most one -1 in reshape (" << L.name << ")");
+          infer = (int)i;
+          o.push_back(-1);
+        } else {
+          o.push_back((int)dims[i]);
+          known *= dims[i];
+        }
+      }
+      if (infer >= 0) {
+        ECO_CHECK(known > 0 && cnt % known == 0, "bottom count must be divisible by the product of the specified dims ("
+                                                     << L.name << ")");
+        o[infer] = (int)(cnt / known);
+        known *= o[infer];
+      }
+      ECO_CHECK(known == cnt, "output count must match input count (" << L.name << ")");
+      set_top(0, o);
+    } else if (t == "Permute") {
+      const pt::Msg* p = L.msg->msg("permute_param");
+      ECO_CHECK(p, "permute_param missing in " << L.name);
+      const auto& b = bshape(0);
+      std::vector<int> order;
+      for (long o : p->integers("order")) {
+        ECO_CHECK(o >= 0 && o < (long)b.size(), "order should be less than the input dimension");
+        ECO_CHECK(std::find(order.begin(), order.end(), (int)o) == order.end(), "there are duplicate orders");
+        order.push_back((int)o);
+      }
+      for (int i = 0; i < (int)b.size(); ++i)
+        if (std::find(order.begin(), order.end(), i) == order.end()) order.push_back(i);  // permute_layer.cpp:44-50
+      std::vector<int> o;
+      for (int a : order) o.push_back(b[a]);
+      set_top(0, o);
+    } else if (t == "InnerProduct") {
+      const pt::Msg* p = L.msg->msg("inner_product_param");
+      ECO_CHECK(p, "inner_product_param missing in " << L.name);
+      const auto& b = bshape(0);
+      const int nout = (int)p->integer("num_output", 0);
+      ECO_CHECK(p->integer("axis", 1) == 1, "InnerProduct axis != 1 is not used on ECO's path");
+      long long k = 1;
+      for (size_t i = 1; i < b.size(); ++i) k *= b[i];
+      set_top(0, {b[0], nout});
+      set_param_shape(0, {nout, (int)k});
+      if (p->boolean("bias_term", true)) set_param_shape(1, {nout});
+    } else if (t == "SoftmaxWithLoss" || t == "Accuracy") {
+      set_top(0, {});
+    } else if (t == "Split") {
+      for (size_t j = 0; j < L.tops.size(); ++j) set_top((int)j, bshape(0));
+    } else {
+      ECO_CHECK(false, "Unknown layer type: " << t << " (layer '" << L.name
+                                              << "'); only the layer types of models_ECO_* are implemented");
+    }
+  }
+}
+
+static void fill(ParamBlob& b, const pt::Msg* filler, std::mt19937& rng, float def_const) {
+  long long n = 1;
+  for (int d : b.shape) n *= d;
+  b.data.assign((size_t)n, def_const);
+  b.diff.assign((size_t)n, 0.f);
+  if (!filler) return;
+  const std::string type = filler->str("type", "constant");
+  if (type == "constant") {
+    std::fill(b.data.begin(), b.data.end(), (float)filler->num("value", 0.0));
+  } else if (type == "xavier") {  // filler.hpp:149-163: U(+-sqrt(3/fan_in))
+    const long long fan_in = b.shape.empty() ? 1 : n / b.shape[0];
+    const float a = std::sqrt(3.0f / (float)fan_in);
+    std::uniform_real_distribution<float> d(-a, a);
+    for (auto& v : b.data) v = d(rng);
+  } else if (type == "gaussian") {
+    std::normal_distribution<float> d((float)filler->num("mean", 0.0), (float)filler->num("std", 1.0));
+    for (auto& v : b.data) v = d(rng);
+  } else if (type == "uniform") {
+    std::uniform_real_distribution<float> d((float)filler->num("min", 0.0), (float)filler->num("max", 1.0));
+    for (auto& v : b.data) v = d(rng);
+  } else if (type == "msra") {
+    const long long fan_in = b.shape.empty() ? 1 : n / b.shape[0];
+    std::normal_distribution<float> d(0.f, std::sqrt(2.0f / (float)fan_in));
+    for (auto& v : b.data) v = d(rng);
+  } else {
+    ECO_CHECK(false, "Unknown filler name: " << type);
+  }
+}
+
+void Net::init_params() {
+  std::mt19937 rng(1701);
+  for (auto& L : layers_) {
+    if (L.type == "Convolution" || L.type == "InnerProduct") {
+      const pt::Msg* p = L.msg->msg(L.type == "Convolution" ? "convolution_param" : "inner_product_param");
+      fill(L.params[0], p->msg("weight_filler"), rng, 0.f);
+      if (L.params.size() > 1) fill(L.params[1], p->msg("bias_filler"), rng, 0.f);
+    } else if (L.type == "BN") {
+      const pt::Msg* p = L.msg->msg("bn_param");
+      const bool frozen = p ? p->boolean("frozen", false) : false;
+      fill(L.params[0], p ? p->msg("slope_filler") : nullptr, rng, 1.f);
+      fill(L.params[1], p ? p->msg("bias_filler") : nullptr, rng, 0.f);
+      fill(L.params[2], nullptr, rng, 0.f);                  // running mean 0       (bn_layer.cpp:34-36)
+      fill(L.params[3], nullptr, rng, frozen ? 1.f : 0.f);   // running variance     (bn_layer.cpp:38-41)
+    }
+    L.params_dirty = true;
+  }
+}
+
+// =====================================================================================
+void Net::set_option(const std::string& key, int v) {
+  if (key == "keep_all_blobs") keep_all_ = v != 0;
+  else if (key == "a_mode") a_mode_ = v;
+  else if (key == "use_graph") use_graph_ = v != 0;
+  else ECO_CHECK(false, "unknown option '" << key << "'");
+  free_plan();
+}
+
+void Net::set_stream(cudaStream_t s) {
+  if (own_stream_ && stream_) cudaStreamDestroy(stream_);
+  stream_ = s;
+  own_stream_ = false;
+  graph_valid_ = false;
+}
+
+void Net::reshape_blob(int vb, const std::vector<int>& dims) {
+  ECO_CHECK(vb >= 0 && vb < (int)vis_blobs_.size(), "blob index out of range");
+  Tensor& t = tensors_[vis_blobs_[vb].tensor];
+  for (int d : dims) ECO_CHECK(d >= 0, "negative dimension in reshape");
+  t.shape = dims;
+  free_plan();
+}
+
+void Net::reshape() {
+  free_plan();
+  infer_shapes();
+}
+
+int Net::num_params(int vl) const {
+  ECO_CHECK(vl >= 0 && vl < (int)vis_layers_.size(), "layer index out of range");
+  const int o = vis_layers_[vl].orig;
+  return o < 0 ? 0 : (int)layers_[o].params.size();
+}
+ParamBlob& Net::param(int vl, int idx) {
+  ECO_CHECK(vl >= 0 && vl < (int)vis_layers_.size(), "layer index out of range");
+  const int o = vis_layers_[vl].orig;
+  ECO_CHECK(o >= 0 && idx >= 0 && idx < (int)layers_[o].params.size(),
+            "layer '" << vis_layers_[vl].name << "' has no parameter blob " << idx);
+  return layers_[o].params[idx];
+}
+void Net::set_param(int vl, int idx, const float* data, size_t count) {
+  ParamBlob& b = param(vl, idx);
+  ECO_CHECK(count == b.data.size(), "parameter size mismatch for layer '" << vis_layers_[vl].name << "' blob " << idx
+                                                                       << ": got " << count << ", expected "
+                                                                       << b.data.size());
+  std::memcpy(b.data.data(), data, count * sizeof(float));
+  layers_[vis_layers_[vl].orig].params_dirty = true;
+}
+void Net::mark_params_dirty(int vl) {
+  const int o = vis_layers_[vl].orig;
+  if (o >= 0) layers_[o].params_dirty = true;
+}
+
+// =====================================================================================
+// device plumbing
+void Net::ensure_device() {
+  ECO_CHECK(device_available(),
+            "no CUDA device is visible: libeco_b200 has no CPU execution path (the reference's CPU mode is not replaced)");
+  if (!stream_) {
+    CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    own_stream_ = true;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    ECO_CHECK(prop.major == 10, "libeco_b200 is built for sm_100a only; device is sm_" << prop.major << prop.minor);
+    CUDA_OK(conv_umma_configure());
+    configured = true;
+  }
+}
+
+void* Net::dalloc(size_t bytes, bool zero) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  CUDA_OK(cudaMalloc(&p, bytes));
+  if (zero) CUDA_OK(cudaMemsetAsync(p, 0, bytes, stream_));
+  allocs_.push_back(p);
+  return p;
+}
+
+void Net::free_plan() {
+  if (graph_exec_) {
+    cudaGraphExecDestroy(graph_exec_);
+    graph_exec_ = nullptr;
+  }
+  graph_valid_ = false;
+  if (!allocs_.empty()) {
+    if (stream_) cudaStreamSynchronize(stream_);
+    for (void* p : allocs_) cudaFree(p);
+    allocs_.clear();
+  }
+  ops_.clear();
+  convs_.clear();
+  error_flag_dev_ = nullptr;
+  for (auto& t : tensors_) {
+    t.dev = nullptr;
+    t.dev_bytes = 0;
+    t.owns = false;
+    t.materialized = false;
+    t.root = -1;
+    t.cs = 0;
+    t.coff = 0;
+    t.dev_newer = false;
+  }
+  for (auto& L : layers_) L.params_dirty = true;
+  planned_ = false;
+}
+
+ClView Net::view(const Tensor& t) const {
+  ClView v;
+  v.ptr = static_cast<__nv_bfloat16*>(t.dev);
+  v.outer = t.outer();
+  v.inner = t.inner();
+  v.C = t.C();
+  v.cs = t.cs;
+  v.coff = t.coff;
+  return v;
+}
+
+// ---- cuTensorMapEncode* through the runtime's driver entry points (no link-time libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static void* driver_fn(const char* name) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q);
+  ECO_CHECK(e == cudaSuccess && fn && q == cudaDriverEntryPointSuccess, "driver entry point " << name << " unavailable");
+  return fn;
+}
+
+void Net::make_tensor_maps(ConvOp& c) {
+  static EncodeTiledFn enc_tiled = (EncodeTiledFn)driver_fn("cuTensorMapEncodeTiled");
+  static EncodeIm2colFn enc_im2col = (EncodeIm2colFn)driver_fn("cuTensorMapEncodeIm2col");
+  // B: weights [Cout_pad][Ktotal] bf16, K-major; box = 64 (one swizzle row) x block_n
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)c.Ktotal, (cuuint64_t)c.Cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)c.Ktotal * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)c.kp.block_n};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc_tiled(&c.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.w_dev, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ECO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed with " << (int)r << " for layer "
+                                                                                << layers_[c.conv_layer].name);
+  }
+  if (c.kp.a_mode != A_TMA_IM2COL) return;
+  // A: activations, channels-last.  dims fastest-first {C, W, H, [D], N}; traversal strides = conv stride;
+  // base pixel box = [-pad, pad - (k-1)] per axis (the convention of CUTLASS' im2col TMA descriptors).
+  const int nsp = c.kp.nsp;
+  const int rank = nsp + 2;
+  cuuint64_t dims[5];
+  cuuint64_t strides[4];
+  int lower[3], upper[3];
+  cuuint32_t es[5];
+  const ConvKernelParams& k = c.kp;
+  dims[0] = (cuuint64_t)k.Cin;
+  es[0] = 1;
+  if (nsp == 3) {
+    dims[1] = k.IW; dims[2] = k.IH; dims[3] = k.ID; dims[4] = c.NB;
+    strides[0] = k.x_sW * 2; strides[1] = k.x_sH * 2; strides[2] = k.x_sD * 2; strides[3] = k.x_sN * 2;
+    lower[0] = -k.pW; lower[1] = -k.pH; lower[2] = -k.pD;
+    upper[0] = k.pW - (k.KW - 1); upper[1] = k.pH - (k.KH - 1); upper[2] = k.pD - (k.KD - 1);
+    es[1] = k.sW; es[2] = k.sH; es[3] = k.sD; es[4] = 1;
+  } else {
+    dims[1] = k.IW; dims[2] = k.IH; dims[3] = c.NB;
+    strides[0] = k.x_sW * 2; strides[1] = k.x_sH * 2; strides[2] = k.x_sN * 2;
+    lower[0] = -k.pW; lower[1] = -k.pH;
+    upper[0] = k.pW - (k.KW - 1); upper[1] = k.pH - (k.KH - 1);
+    es[1] = k.sW; es[2] = k.sH; es[3] = 1;
+  }
+  CUresult r = enc_im2col(&c.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)k.x, dims, strides, lower,
+                          upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ECO_CHECK(a_mode_ != A_TMA_IM2COL, "cuTensorMapEncodeIm2col failed with " << (int)r << " for layer "
+                                                                              << layers_[c.conv_layer].name);
+    c.kp.a_mode = A_GATHER;  // auto mode: fall back to the software gather for this layer
+  }
+}
+
+// =====================================================================================
+// planner
+static bool is_inplace_relu(const OrigLayer& L, int tensor) {
+  if (L.type != "ReLU" || L.bottoms.size() != 1 || L.tops.size() != 1) return false;
+  if (L.bottoms[0] != tensor || L.tops[0] != tensor) return false;
+  const pt::Msg* p = L.msg ? L.msg->msg("relu_param") : nullptr;
+  return !p || p->num("negative_slope", 0.0) == 0.0;
+}
+
+void Net::plan_conv_group(int li, std::vector<bool>& done) {
+  OrigLayer& L = layers_[li];
+  ConvOp c;
+  c.conv_layer = li;
+  c.in_tensor = L.bottoms[0];
+  const int T0 = L.tops[0];
+  int last = li;
+  int pre = T0;
+  bool raw_only = false;
+  {
+    const auto& cons = tensors_[T0].consumers;
+    if (cons.size() == 1 && layers_[cons[0]].type == "Eltwise" && !done[cons[0]]) {
+      const OrigLayer& E = layers_[cons[0]];
+      const pt::Msg* ep = E.msg->msg("eltwise_param");
+      bool plain_sum = E.bottoms.size() == 2 && (!ep || (ep->str("operation", "SUM") == "SUM" && !ep->has("coeff")));
+      const int other = E.bottoms[0] == T0 ? E.bottoms[1] : E.bottoms[0];
+      if (plain_sum && other != T0 && tensors_[other].producer < li && tensors_[other].kind == Kind::CL) {
+        c.elt_layer = cons[0];
+        c.res_tensor = other;
+        pre = E.tops[0];
+        done[cons[0]] = true;
+        last = std::max(last, cons[0]);
+      } else {
+        raw_only = true;  // this conv is produced first: keep its raw output for the later add
+      }
+    }
+  }
+  int bn = -1;
+  if (!raw_only) {
+    int nbn = 0;
+    for (int ci : tensors_[pre].consumers) {
+      const OrigLayer& B = layers_[ci];
+      if (B.type == "BN" && B.tops[0] != pre && !done[ci]) {
+        const pt::Msg* bp = B.msg->msg("bn_param");
+        const bool frozen = bp ? bp->boolean("frozen", false) : false;
+        if (phase_ == ECO_PHASE_TEST || frozen) {
+          ++nbn;
+          bn = ci;
+        }
+      }
+    }
+    if (nbn != 1) bn = -1;
+  }
+  if (bn >= 0) {
+    c.bn_layer = bn;
+    done[bn] = true;
+    last = std::max(last, bn);
+    const int y = layers_[bn].tops[0];
+    c.out_tensor = y;
+    const auto& yc = tensors_[y].consumers;
+    if (!yc.empty() && is_inplace_relu(layers_[yc[0]], y) && !done[yc[0]]) {
+      c.relu = true;
+      done[yc[0]] = true;
+      last = std::max(last, yc[0]);
+    }
+    if (tensors_[pre].consumers.size() > 1 || keep_all_) c.raw_tensor = pre;
+  } else {
+    c.raw_tensor = pre;
+    const auto& pc = tensors_[pre].consumers;
+    if (!raw_only && !pc.empty() && is_inplace_relu(layers_[pc[0]], pre) && !done[pc[0]]) {
+      // conv -> in-place ReLU: store only the rectified value (what caffe leaves in the blob)
+      c.out_tensor = pre;
+      c.raw_tensor = -1;
+      c.relu = true;
+      done[pc[0]] = true;
+      last = std::max(last, pc[0]);
+    }
+  }
+  done[li] = true;
+  if (c.out_tensor >= 0) tensors_[c.out_tensor].materialized = true;
+  if (c.raw_tensor >= 0) tensors_[c.raw_tensor].materialized = true;
+
+  Op op;
+  op.type = Op::CONV;
+  op.name = L.name;
+  op.first_layer = li;
+  op.last_layer = last;
+  op.conv = (int)convs_.size();
+  convs_.push_back(c);
+  ops_.push_back(op);
+}
+
+static int pow2_at_least(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+void Net::plan() {
+  free_plan();
+  ensure_device();
+  infer_shapes();
+  const int NL = (int)layers_.size();
+
+  // ---- 1. kinds ----
+  for (auto& t : tensors_) {
+    t.kind = Kind::F32;
+    t.ch_axis = 1;
+  }
+  std::vector<int> view_of(tensors_.size(), -1);  // top is a pure view of this tensor
+  std::vector<bool> needs_convert(NL, false);     // Reshape that cannot stay channels-last
+  for (int li = 0; li < NL; ++li) {
+    OrigLayer& L = layers_[li];
+    const std::string& t = L.type;
+    if (is_data_layer(t) || L.tops.empty()) continue;
+    Tensor* b0 = L.bottoms.empty() ? nullptr : &tensors_[L.bottoms[0]];
+    Tensor& top = tensors_[L.tops[0]];
+    if (t == "Convolution") {
+      top.kind = Kind::CL;
+      top.ch_axis = 1;
+      ECO_CHECK(top.shape[1] % 8 == 0, "Convolution " << L.name << ": num_output must be a multiple of 8 for the bf16 "
+                                                                  "channels-last path (got " << top.shape[1] << ")");
+      if (b0->kind == Kind::CL) ECO_CHECK(b0->ch_axis == 1, "Convolution " << L.name << " input is not N,C,... ordered");
+    } else if (t == "BN" || t == "ReLU" || t == "Dropout" || t == "Eltwise") {
+      top.kind = b0->kind;
+      top.ch_axis = b0->ch_axis;
+      if (t == "Dropout" && L.tops[0] != L.bottoms[0]) view_of[L.tops[0]] = L.bottoms[0];
+      if (t == "Eltwise")
+        for (int b : L.bottoms) ECO_CHECK(tensors_[b].kind == b0->kind, "Eltwise " << L.name << " mixes layouts");
+    } else if (t == "Pooling") {
+      if (b0->kind == Kind::CL) {
+        ECO_CHECK(b0->ch_axis == 1, "Pooling " << L.name << " input is not N,C,... ordered");
+        bool collapses = true;
+        for (size_t i = 2; i < top.shape.size(); ++i) collapses &= top.shape[i] == 1;
+        top.kind = collapses ? Kind::F32 : Kind::CL;
+        top.ch_axis = 1;
+      }
+    } else if (t == "Concat") {
+      const pt::Msg* p = L.msg->msg("concat_param");
+      const int axis = p ? (int)p->integer("axis", p->integer("concat_dim", 1)) : 1;
+      top.kind = b0->kind;
+      top.ch_axis = b0->ch_axis;
+      for (int b : L.bottoms) {
+        ECO_CHECK(tensors_[b].kind == b0->kind && tensors_[b].ch_axis == b0->ch_axis,
+                  "Concat " << L.name << " mixes layouts");
+      }
+      if (top.kind == Kind::CL) ECO_CHECK(axis == top.ch_axis, "Concat " << L.name << ": only channel concat on feature maps");
+      else ECO_CHECK(axis == 1 || axis == 0, "Concat " << L.name << ": axis " << axis << " unsupported on plain blobs");
+    } else if (t == "Reshape") {
+      if (b0->kind == Kind::CL) {
+        // stays channels-last iff the channel axis and everything after it are preserved as the
+        // trailing axes (r2Dto3D: [B*N,96,28,28] -> [B,N,96,28,28])
+        const int tail = (int)b0->shape.size() - b0->ch_axis;
+        bool ok = (int)top.shape.size() >= tail + 1 || (int)top.shape.size() == tail;
+        ok = (int)top.shape.size() >= tail;
+        for (int i = 0; ok && i < tail; ++i)
+          ok = top.shape[top.shape.size() - tail + i] == b0->shape[b0->ch_axis + i];
+        if (ok) {
+          top.kind = Kind::CL;
+          top.ch_axis = (int)top.shape.size() - tail;
+          view_of[L.tops[0]] = L.bottoms[0];
+        } else {
+          needs_convert[li] = true;  // materialise as plain fp32
+        }
+      } else {
+        view_of[L.tops[0]] = L.bottoms[0];
+      }
+    } else if (t == "Permute") {
+      const pt::Msg* p = L.msg->msg("permute_param");
+      std::vector<int> order;
+      for (long o : p->integers("order")) order.push_back((int)o);
+      for (int i = 0; i < (int)b0->shape.size(); ++i)
+        if (std::find(order.begin(), order.end(), i) == order.end()) order.push_back(i);
+      if (b0->kind == Kind::CL) {
+        // physical order of the bottom: axes with the channel axis moved last
+        std::vector<int> phys_b;
+        for (int i = 0; i < (int)b0->shape.size(); ++i)
+          if (i != b0->ch_axis) phys_b.push_back(i);
+        phys_b.push_back(b0->ch_axis);
+        int ch_top = -1;
+        for (int i = 0; i < (int)order.size(); ++i)
+          if (order[i] == b0->ch_axis) ch_top = i;
+        std::vector<int> phys_t;
+        for (int i = 0; i < (int)order.size(); ++i)
+          if (i != ch_top) phys_t.push_back(order[i]);
+        phys_t.push_back(order[ch_top]);
+        ECO_CHECK(phys_t == phys_b, "Permute " << L.name << " is not a layout no-op in channels-last storage; general "
+                                                            "permutes are outside ECO's path");
+        top.kind = Kind::CL;
+        top.ch_axis = ch_top;
+        view_of[L.tops[0]] = L.bottoms[0];
+      } else {
+        bool ident = true;
+        for (int i = 0; i < (int)order.size(); ++i) ident &= order[i] == i;
+        ECO_CHECK(ident, "Permute " << L.name << " on a plain blob is outside ECO's path");
+        view_of[L.tops[0]] = L.bottoms[0];
+      }
+    } else if (t == "Split") {
+      for (int tp : L.tops) {
+        tensors_[tp].kind = b0->kind;
+        tensors_[tp].ch_axis = b0->ch_axis;
+        view_of[tp] = L.bottoms[0];
+      }
+    }
+    // InnerProduct / Softmax / losses: plain fp32 (default)
+  }
+
+  // ---- 2. ops (fusion) ----
+  std::vector<bool> done(NL, false);
+  for (int vb : inputs_) tensors_[vis_blobs_[vb].tensor].materialized = true;
+  for (int li = 0; li < NL; ++li) {
+    if (done[li]) continue;
+    OrigLayer& L = layers_[li];
+    const std::string& t = L.type;
+    Op op;
+    op.first_layer = op.last_layer = li;
+    op.layer = li;
+    op.name = L.name;
+    if (is_data_layer(t)) {
+      done[li] = true;
+    } else if (t == "Convolution") {
+      plan_conv_group(li, done);
+    } else if (t == "BN" || t == "ReLU") {
+      Tensor& x = tensors_[L.bottoms[0]];
+      ECO_CHECK(x.kind == Kind::CL, t << " layer " << L.name << " on a plain blob is outside ECO's path");
+      op.type = Op::SSR;
+      op.in0 = L.bottoms[0];
+      op.out = L.tops[0];
+      op.relu = (t == "ReLU");
+      if (t == "BN") {
+        const pt::Msg* bp = L.msg->msg("bn_param");
+        const bool frozen = bp ? bp->boolean("frozen", false) : false;
+        ECO_CHECK(phase_ == ECO_PHASE_TEST || frozen, "TRAIN-phase BN (batch statistics) is not implemented in this round");
+        const auto& yc = tensors_[op.out].consumers;
+        for (int ci : yc)
+          if (ci > li && is_inplace_relu(layers_[ci], op.out) && !done[ci]) {
+            // only fuse when the ReLU is the first reader after the BN
+            bool first = true;
+            for (int cj : yc) first &= (cj >= ci || cj <= li);
+            if (first) { op.relu = true; done[ci] = true; op.last_layer = ci; }
+            break;
+          }
+      }
+      tensors_[op.out].materialized = true;
+      done[li] = true;
+      ops_.push_back(op);
+    } else if (t == "Pooling") {
+      Tensor& x = tensors_[L.bottoms[0]];
+      Tensor& y = tensors_[L.tops[0]];
+      if (x.kind == Kind::CL && y.kind == Kind::F32) op.type = Op::GLOBAL_AVG;
+      else if (x.kind == Kind::CL) op.type = Op::POOL_CL;
+      else op.type = Op::POOL_F32;
+      op.in0 = L.bottoms[0];
+      op.out = L.tops[0];
+      y.materialized = true;
+      done[li] = true;
+      ops_.push_back(op);
+    } else if (t == "Eltwise") {
+      const pt::Msg* ep = L.msg->msg("eltwise_param");
+      ECO_CHECK(L.bottoms.size() == 2 && (!ep || (ep->str("operation", "SUM") == "SUM" && !ep->has("coeff"))),
+                "Eltwise " << L.name << ": only the 2-input SUM of ECO's residual blocks is implemented");
+      ECO_CHECK(tensors_[L.bottoms[0]].kind == Kind::CL, "Eltwise on plain blobs is outside ECO's path");
+      op.type = Op::ELTWISE;
+      op.in0 = L.bottoms[0];
+      op.in1 = L.bottoms[1];
+      op.out = L.tops[0];
+      tensors_[op.out].materialized = true;
+      done[li] = true;
+      ops_.push_back(op);
+    } else if (t == "Concat") {
+      tensors_[L.tops[0]].materialized = true;
+      done[li] = true;  // copy ops (if any) are added after aliasing is known
+    } else if (t == "Reshape") {
+      if (needs_convert[li]) {
+        op.type = Op::CL_TO_F32;
+        op.in0 = L.bottoms[0];
+        op.out = L.tops[0];
+        tensors_[op.out].materialized = true;
+        ops_.push_back(op);
+      }
+      done[li] = true;
+    } else if (t == "Permute" || t == "Dropout" || t == "Split") {
+      ECO_CHECK(t != "Dropout" || phase_ == ECO_PHASE_TEST, "TRAIN-phase Dropout is not implemented in this round");
+      done[li] = true;
+    } else if (t == "InnerProduct") {
+      ECO_CHECK(tensors_[L.bottoms[0]].kind == Kind::F32,
+                "InnerProduct " << L.name << " directly on a feature map is outside ECO's path (pool first)");
+      op.type = Op::FC;
+      op.in0 = L.bottoms[0];
+      op.out = L.tops[0];
+      tensors_[op.out].materialized = true;
+      done[li] = true;
+      ops_.push_back(op);
+    } else if (t == "Softmax") {
+      op.type = Op::SOFTMAX;
+      op.in0 = L.bottoms[0];
+      op.out = L.tops[0];
+      tensors_[op.out].materialized = true;
+      done[li] = true;
+      ops_.push_back(op);
+    } else {
+      ECO_CHECK(false, "layer type " << t << " (" << L.name << ") has no device implementation in this round");
+    }
+  }
+
+  // ---- 3. storage: views, zero-copy concat, allocation ----
+  for (size_t i = 0; i < tensors_.size(); ++i) tensors_[i].root = (int)i;
+  // concat aliasing, later concats first so nested concats resolve outward-in
+  std::vector<std::pair<int, int>> concat_copies;  // (layer, bottom idx) that need a copy
+  std::vector<char> aliased(tensors_.size(), 0);
+  for (int li = NL - 1; li >= 0; --li) {
+    OrigLayer& L = layers_[li];
+    if (L.type != "Concat") continue;
+    Tensor& top = tensors_[L.tops[0]];
+    if (top.kind == Kind::CL && top.cs == 0) {
+      top.cs = round_up(top.C(), 8);
+      top.coff = 0;
+    }
+    int off = 0;
+    for (size_t j = 0; j < L.bottoms.size(); ++j) {
+      Tensor& b = tensors_[L.bottoms[j]];
+      const int width = top.kind == Kind::CL ? b.C() : 0;
+      bool can_alias = top.kind == Kind::CL && b.consumers.size() == 1 && b.materialized && view_of[L.bottoms[j]] < 0 &&
+                       !aliased[L.bottoms[j]] && b.producer >= 0 && !is_data_layer(layers_[b.producer].type) &&
+                       layers_[b.producer].type != "Concat" && (off % 8 == 0);
+      // a tensor that other tensors view must keep its own buffer
+      for (size_t q = 0; can_alias && q < view_of.size(); ++q)
+        if (view_of[q] == L.bottoms[j]) can_alias = false;
+      if (can_alias) {
+        b.root = top.root;
+        b.cs = top.cs;
+        b.coff = top.coff + off;
+        aliased[L.bottoms[j]] = 1;
+      } else {
+        concat_copies.emplace_back(li, (int)j);
+      }
+      off += width;
+    }
+  }
+  // views inherit storage (resolve chains in layer order: a view's source is always earlier)
+  for (int li = 0; li < NL; ++li)
+    for (int tp : layers_[li].tops)
+      if (view_of[tp] >= 0) {
+        Tensor& s = tensors_[view_of[tp]];
+        Tensor& v = tensors_[tp];
+        v.root = s.root;
+        v.cs = s.cs;  // may still be 0 here; fixed after allocation below
+        v.coff = s.coff;
+        v.materialized = s.materialized;
+      }
+  error_flag_dev_ = static_cast<int*>(dalloc(sizeof(int), true));
+  for (size_t i = 0; i < tensors_.size(); ++i) {
+    Tensor& t = tensors_[i];
+    if (t.root != (int)i || !t.materialized || view_of[i] >= 0) continue;
+    if (t.kind == Kind::CL) {
+      if (t.cs == 0) t.cs = round_up(t.C(), 8);
+      ECO_CHECK(t.C() % 8 == 0 || t.cs >= t.C(), "bad channel stride");
+      t.dev_bytes = (size_t)(t.outer() * t.inner()) * (size_t)t.cs * 2;
+      t.dev = dalloc(t.dev_bytes, t.cs != t.C());
+    } else {
+      t.dev_bytes = (size_t)std::max<long long>(t.count(), 1) * 4;
+      t.dev = dalloc(t.dev_bytes, true);
+    }
+    t.owns = true;
+  }
+  for (int pass = 0; pass < 2; ++pass)
+    for (int li = 0; li < NL; ++li)
+      for (int tp : layers_[li].tops) {
+        Tensor& v = tensors_[tp];
+        if (view_of[tp] >= 0) {
+          Tensor& s = tensors_[view_of[tp]];
+          v.dev = s.dev; v.cs = s.cs; v.coff = s.coff; v.root = s.root; v.dev_bytes = s.dev_bytes;
+          v.materialized = s.materialized;
+        } else if (v.root != tp) {
+          Tensor& r = tensors_[v.root];
+          v.dev = r.dev; v.dev_bytes = r.dev_bytes;
+        }
+      }
+  // copies for concat bottoms that could not be aliased; inserted right after the producer of the
+  // last bottom, i.e. appended in layer order
+  if (!concat_copies.empty()) {
+    std::vector<Op> extra;
+    for (auto& cc : concat_copies) {
+      OrigLayer& L = layers_[cc.first];
+      Tensor& top = tensors_[L.tops[0]];
+      Tensor& b = tensors_[L.bottoms[cc.second]];
+      ECO_CHECK(b.materialized && b.dev, "Concat " << L.name << ": bottom " << b.name << " has no storage");
+      Op op;
+      op.type = Op::COPY2D;
+      op.name = L.name + ":copy" + std::to_string(cc.second);
+      op.first_layer = op.last_layer = cc.first;
+      op.layer = cc.first;
+      op.in0 = L.bottoms[cc.second];
+      op.out = L.tops[0];
+      if (top.kind == Kind::CL) {
+        int off = 0;
+        for (int j = 0; j < cc.second; ++j) off += tensors_[L.bottoms[j]].C();
+        op.rows = (size_t)(b.outer() * b.inner());
+        op.width_bytes = (size_t)b.C() * 2;
+        op.src_pitch = (size_t)b.cs * 2;
+        op.dst_pitch = (size_t)top.cs * 2;
+        op.src_off = (size_t)b.coff * 2;
+        op.dst_off = (size_t)(top.coff + off) * 2;
+      } else {
+        const pt::Msg* p = L.msg->msg("concat_param");
+        const int axis = p ? (int)p->integer("axis", p->integer("concat_dim", 1)) : 1;
+        long long outer = 1, in_w = 1, top_w = 1, off = 0;
+        for (int a = 0; a < axis; ++a) outer *= top.shape[a];
+        for (size_t a = axis; a < b.shape.size(); ++a) in_w *= b.shape[a];
+        for (size_t a = axis; a < top.shape.size(); ++a) top_w *= top.shape[a];
+        for (int j = 0; j < cc.second; ++j) {
+          long long w = 1;
+          for (size_t a = axis; a < tensors_[L.bottoms[j]].shape.size(); ++a) w *= tensors_[L.bottoms[j]].shape[a];
+          off += w;
+        }
+        op.rows = (size_t)outer;
+        op.width_bytes = (size_t)in_w * 4;
+        op.src_pitch = (size_t)in_w * 4;
+        op.dst_pitch = (size_t)top_w * 4;
+        op.src_off = 0;
+        op.dst_off = (size_t)off * 4;
+      }
+      op.launches = 0;
+      extra.push_back(op);
+    }
+    // merge into ops_ keeping layer order (copy goes where the Concat layer sits)
+    std::vector<Op> merged;
+    size_t e = 0;
+    std::stable_sort(extra.begin(), extra.end(), [](const Op& a, const Op& b) { return a.first_layer < b.first_layer; });
+    for (auto& op : ops_) {
+      while (e < extra.size() && extra[e].first_layer < op.first_layer) merged.push_back(extra[e++]);
+      merged.push_back(op);
+    }
+    while (e < extra.size()) merged.push_back(extra[e++]);
+    ops_.swap(merged);
+  }
+
+  // ---- 4. bind ops ----
+  for (auto& op : ops_) {
+    OrigLayer* Lp = op.layer >= 0 ? &layers_[op.layer] : nullptr;
+    switch (op.type) {
+      case Op::CONV: {
+        ConvOp& c = convs_[op.conv];
+        OrigLayer& L = layers_[c.conv_layer];
+        const pt::Msg* p = L.msg->msg("convolution_param");
+        Tensor& x = tensors_[c.in_tensor];
+        const int nsp = (int)x.shape.size() - 2;
+        ECO_CHECK(nsp == 2 || nsp == 3, "Convolution " << L.name << ": only 2-D and 3-D convolutions are implemented");
+        auto k = nd_param(*p, "kernel_size", "kernel", nsp, -1);
+        auto s = nd_param(*p, "stride", "stride", nsp, 1);
+        auto pd = nd_param(*p, "pad", "pad", nsp, 0);
+        ECO_CHECK(p->integer("dilation", 1) == 1, "dilated convolution is not on ECO's path");
+        c.nsp = nsp;
+        c.NB = x.shape[0];
+        c.Cin = x.shape[1];
+        c.Cout = L.params[0].shape[0];
+        for (int i = 0; i < nsp; ++i) {
+          const int a = 3 - nsp + i;
+          c.K[a] = k[i]; c.S[a] = s[i]; c.P[a] = pd[i];
+          c.I[a] = x.shape[2 + i];
+          c.O[a] = (x.shape[2 + i] + 2 * pd[i] - k[i]) / s[i] + 1;
+        }
+        ConvKernelParams& kp = c.kp;
+        kp = ConvKernelParams{};
+        kp.nsp = nsp;
+        kp.OD = c.O[0]; kp.OH = c.O[1]; kp.OW = c.O[2];
+        kp.M = c.NB * c.O[0] * c.O[1] * c.O[2];
+        c.stem = (x.kind == Kind::F32 && nsp == 2 && c.Cin == 3 && k[0] == 7 && k[1] == 7 && s[0] == 2 && s[1] == 2 &&
+                  pd[0] == 3 && pd[1] == 3);
+        if (c.stem) {
+          // 7x7/s2/p3 over 3 channels == 4x4/s1 over 2x2 space-to-depth cells of the zero-padded image;
+          // the 4 horizontally adjacent cells (4 x 16 ch) of a window are contiguous in memory, so the
+          // conv is presented to the GEMM as a 4(h) x 1(w) kernel over 64 "channels" with pixel stride 16.
+          c.stem_CH = c.O[1] + 3;
+          c.stem_CW = c.O[2] + 3;
+          c.stem_bytes = (size_t)c.NB * c.stem_CH * c.stem_CW * 16 * 2 + 256;
+          c.stem_in = static_cast<__nv_bfloat16*>(dalloc(c.stem_bytes, true));
+          kp.x = c.stem_in;
+          kp.x_sW = 16; kp.x_sH = (long long)c.stem_CW * 16; kp.x_sD = 0;
+          kp.x_sN = (long long)c.stem_CH * c.stem_CW * 16;
+          kp.Cin = 64; c.Cin_k = 64;
+          kp.ID = 1; kp.IH = c.stem_CH; kp.IW = c.O[2];
+          kp.KD = 1; kp.KH = 4; kp.KW = 1;
+          kp.sD = kp.sH = kp.sW = 1;
+          kp.pD = kp.pH = kp.pW = 0;
+        } else {
+          if (x.kind == Kind::F32) {
+            // generic fp32 input: convert to channels-last bf16 with channels padded to 8
+            const int c8 = round_up(c.Cin, 8);
+            c.stem_bytes = (size_t)c.NB * c.I[0] * c.I[1] * c.I[2] * c8 * 2;
+            c.stem_in = static_cast<__nv_bfloat16*>(dalloc(c.stem_bytes, true));
+            kp.x = c.stem_in;
+            kp.x_sW = c8;
+            c.Cin_k = c8;
+          } else {
+            ECO_CHECK(x.dev, "Convolution " << L.name << ": input " << x.name << " is not materialised");
+            ECO_CHECK(x.C() % 8 == 0 && x.coff % 8 == 0 && x.cs % 8 == 0, "channel alignment");
+            kp.x = static_cast<__nv_bfloat16*>(x.dev) + x.coff;
+            kp.x_sW = x.cs;
+            c.Cin_k = c.Cin;
+          }
+          kp.x_sH = kp.x_sW * c.I[2];
+          kp.x_sD = kp.x_sH * c.I[1];
+          kp.x_sN = kp.x_sD * c.I[0];
+          kp.Cin = c.Cin_k;
+          kp.ID = c.I[0]; kp.IH = c.I[1]; kp.IW = c.I[2];
+          kp.KD = c.K[0]; kp.KH = c.K[1]; kp.KW = c.K[2];
+          kp.sD = c.S[0]; kp.sH = c.S[1]; kp.sW = c.S[2];
+          kp.pD = c.P[0]; kp.pH = c.P[1]; kp.pW = c.P[2];
+        }
+        kp.cblocks = (kp.Cin + kBlockK - 1) / kBlockK;
+        kp.num_kb = kp.KD * kp.KH * kp.KW * kp.cblocks;
+        c.Ktotal = (long long)kp.num_kb * kBlockK;
+        kp.Cout = c.Cout;
+        const int ntiles = (c.Cout + 255) / 256;
+        kp.block_n = round_up((c.Cout + ntiles - 1) / ntiles, 16);
+        c.Cout_pad = round_up(c.Cout, kp.block_n);
+        const size_t per_stage = (size_t)kBlockM * 128 + (size_t)kp.block_n * 128;
+        const size_t budget = kp.block_n <= 128 ? 100 * 1024 : 200 * 1024;
+        kp.stages = (int)std::max<size_t>(2, std::min<size_t>(6, budget / per_stage));
+        kp.tmem_cols = pow2_at_least(kp.block_n);
+        kp.a_mode = a_mode_ < 0 ? A_TMA_IM2COL : a_mode_;
+        kp.error_flag = error_flag_dev_;
+        kp.relu = c.relu ? 1 : 0;
+        c.w_dev = static_cast<__nv_bfloat16*>(dalloc((size_t)c.Cout_pad * c.Ktotal * 2, true));
+        c.bias_dev = static_cast<float*>(dalloc((size_t)c.Cout * 4, true));
+        if (c.bn_layer >= 0) {
+          c.scale_dev = static_cast<float*>(dalloc((size_t)c.Cout * 4, true));
+          c.shift_dev = static_cast<float*>(dalloc((size_t)c.Cout * 4, true));
+        }
+        kp.bias = c.bias_dev;
+        kp.scale = c.scale_dev;
+        kp.shift = c.shift_dev;
+        auto bind = [&](int tid, __nv_bfloat16*& ptr, long long& cs, int& coff) {
+          if (tid < 0) { ptr = nullptr; cs = 0; coff = 0; return; }
+          Tensor& t = tensors_[tid];
+          ECO_CHECK(t.dev && t.kind == Kind::CL, "conv " << L.name << ": tensor " << t.name << " has no channels-last storage");
+          ECO_CHECK(t.cs % 8 == 0 && t.coff % 8 == 0, "channel alignment of " << t.name);
+          ptr = static_cast<__nv_bfloat16*>(t.dev);
+          cs = t.cs;
+          coff = t.coff;
+        };
+        bind(c.out_tensor, kp.out, kp.out_cs, kp.out_coff);
+        bind(c.raw_tensor, kp.raw, kp.raw_cs, kp.raw_coff);
+        __nv_bfloat16* rp = nullptr;
+        bind(c.res_tensor, rp, kp.res_cs, kp.res_coff);
+        kp.res = rp;
+        make_tensor_maps(c);
+        const double taps = (double)c.K[0] * c.K[1] * c.K[2];
+        c.flops = 2.0 * kp.M * c.Cout * taps * c.Cin;
+        c.bytes = 2.0 * ((double)c.NB * c.I[0] * c.I[1] * c.I[2] * c.Cin + (double)kp.M * c.Cout + (double)c.Cout * taps * c.Cin);
+        op.flops = c.flops;
+        op.bytes = c.bytes;
+        op.launches = 1 + (c.stem_in ? 1 : 0);
+        break;
+      }
+      case Op::POOL_CL: {
+        const pt::Msg* p = Lp->msg->msg("pooling_param");
+        Tensor& x = tensors_[op.in0];
+        Tensor& y = tensors_[op.out];
+        const int nsp = (int)x.shape.size() - 2;
+        std::vector<int> k;
+        if (p->boolean("global_pooling", false)) k.assign(x.shape.begin() + 2, x.shape.end());
+        else k = nd_param(*p, "kernel_size", "kernel", nsp, -1);
+        auto s = nd_param(*p, "stride", "stride", nsp, 1);
+        auto pd = nd_param(*p, "pad", "pad", nsp, 0);
+        const std::string method = p->str("pool", "MAX");
+        ECO_CHECK(method == "MAX" || method == "AVE", "pooling method " << method << " is not on ECO's path");
+        ECO_CHECK(x.C() % 8 == 0, "Pooling " << Lp->name << ": channels must be a multiple of 8");
+        PoolParams& q = op.pool;
+        q = PoolParams{};
+        q.x = static_cast<__nv_bfloat16*>(x.dev); q.x_cs = x.cs; q.x_coff = x.coff;
+        q.y = static_cast<__nv_bfloat16*>(y.dev); q.y_cs = y.cs; q.y_coff = y.coff;
+        q.NB = x.shape[0]; q.C = x.C();
+        int I[3] = {1, 1, 1}, O[3] = {1, 1, 1}, K[3] = {1, 1, 1}, S[3] = {1, 1, 1}, P[3] = {0, 0, 0};
+        for (int i = 0; i < nsp; ++i) {
+          const int a = 3 - nsp + i;
+          I[a] = x.shape[2 + i]; O[a] = y.shape[2 + i]; K[a] = k[i]; S[a] = s[i]; P[a] = pd[i];
+        }
+        q.ID = I[0]; q.IH = I[1]; q.IW = I[2]; q.OD = O[0]; q.OH = O[1]; q.OW = O[2];
+        q.KD = K[0]; q.KH = K[1]; q.KW = K[2]; q.sD = S[0]; q.sH = S[1]; q.sW = S[2];
+        q.pD = P[0]; q.pH = P[1]; q.pW = P[2];
+        q.is_max = method == "MAX";
+        op.bytes = 2.0 * ((double)x.count() + (double)y.count());
+        break;
+      }
+      case Op::GLOBAL_AVG: {
+        const pt::Msg* p = Lp->msg->msg("pooling_param");
+        Tensor& x = tensors_[op.in0];
+        const int nsp = (int)x.shape.size() - 2;
+        std::vector<int> k;
+        if (p->boolean("global_pooling", false)) k.assign(x.shape.begin() + 2, x.shape.end());
+        else k = nd_param(*p, "kernel_size", "kernel", nsp, -1);
+        auto pd = nd_param(*p, "pad", "pad", nsp, 0);
+        bool full = p->str("pool", "MAX") == "AVE";
+        for (int i = 0; i < nsp; ++i) full &= (k[i] == x.shape[2 + i] && pd[i] == 0);
+        ECO_CHECK(full, "Pooling " << Lp->name << " collapses the map but is not a full-extent AVE pool");
+        op.bytes = 2.0 * (double)x.count();
+        break;
+      }
+      case Op::POOL_F32: {
+        const pt::Msg* p = Lp->msg->msg("pooling_param");
+        Tensor& x = tensors_[op.in0];
+        Tensor& y = tensors_[op.out];
+        const int nsp = (int)x.shape.size() - 2;
+        std::vector<int> k;
+        if (p->boolean("global_pooling", false)) k.assign(x.shape.begin() + 2, x.shape.end());
+        else k = nd_param(*p, "kernel_size", "kernel", nsp, -1);
+        auto s = nd_param(*p, "stride", "stride", nsp, 1);
+        auto pd = nd_param(*p, "pad", "pad", nsp, 0);
+        const std::string method = p->str("pool", "MAX");
+        PoolF32Params& q = op.poolf;
+        q = PoolF32Params{};
+        q.x = static_cast<float*>(x.dev);
+        q.y = static_cast<float*>(y.dev);
+        q.NC = x.shape[0] * x.shape[1];
+        int I[3] = {1, 1, 1}, O[3] = {1, 1, 1}, K[3] = {1, 1, 1}, S[3] = {1, 1, 1}, P[3] = {0, 0, 0};
+        for (int i = 0; i < nsp; ++i) {
+          const int a = 3 - nsp + i;
+          I[a] = x.shape[2 + i]; O[a] = y.shape[2 + i]; K[a] = k[i]; S[a] = s[i]; P[a] = pd[i];
+        }
+        q.ID = I[0]; q.IH = I[1]; q.IW = I[2]; q.OD = O[0]; q.OH = O[1]; q.OW = O[2];
+        q.KD = K[0]; q.KH = K[1]; q.KW = K[2]; q.sD = S[0]; q.sH = S[1]; q.sW = S[2];
+        q.pD = P[0]; q.pH = P[1]; q.pW = P[2];
+        q.is_max = method == "MAX";
+        break;
+      }
+      case Op::FC: {
+        op.M = tensors_[op.in0].shape[0];
+        op.N = Lp->params[0].shape[0];
+        op.Kd = Lp->params[0].shape[1];
+        op.w_dev = static_cast<float*>(dalloc((size_t)op.N * op.Kd * 4, true));
+        op.b_dev = Lp->params.size() > 1 ? static_cast<float*>(dalloc((size_t)op.N * 4, true)) : nullptr;
+        op.flops = 2.0 * op.M * op.N * op.Kd;
+        break;
+      }
+      case Op::SSR: {
+        const int C = tensors_[op.in0].C();
+        op.scale_dev = static_cast<float*>(dalloc((size_t)C * 4, true));
+        op.shift_dev = static_cast<float*>(dalloc((size_t)C * 4, true));
+        break;
+      }
+      default:
+        break;
+    }
+  }
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  planned_ = true;
+}
+
+// =====================================================================================
+// parameters -> device
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+void Net::upload_params() {
+  bool any = false;
+  for (auto& L : layers_) any |= L.params_dirty;
+  if (!any) return;
+  // BN fold (the reference's own algebra: caffe_3d/python/gen_bn_inference.py:121-134):
+  //   y = (x - mean) * (var + eps)^-1/2 * slope + bias  ==  x * scale + shift
+  auto bn_fold = [&](const OrigLayer& B, std::vector<float>& scale, std::vector<float>& shift) {
+    const pt::Msg* bp = B.msg->msg("bn_param");
+    const float eps = bp ? (float)bp->num("eps", 1e-5) : 1e-5f;
+    const size_t C = B.params[0].data.size();
+    scale.resize(C);
+    shift.resize(C);
+    for (size_t i = 0; i < C; ++i) {
+      const float inv_std = std::pow(B.params[3].data[i] + eps, -0.5f);
+      scale[i] = B.params[0].data[i] * inv_std;
+      shift[i] = B.params[1].data[i] - B.params[2].data[i] * scale[i];
+    }
+  };
+  for (auto& op : ops_) {
+    if (op.type == Op::CONV) {
+      ConvOp& c = convs_[op.conv];
+      OrigLayer& L = layers_[c.conv_layer];
+      const bool bn_dirty = c.bn_layer >= 0 && layers_[c.bn_layer].params_dirty;
+      if (L.params_dirty) {
+        const ConvKernelParams& kp = c.kp;
+        std::vector<uint16_t> wp((size_t)c.Cout_pad * c.Ktotal, 0);
+        const std::vector<float>& w = L.params[0].data;
+        const int taps = c.K[0] * c.K[1] * c.K[2];
+        if (c.stem) {
+          for (int o = 0; o < c.Cout; ++o)
+            for (int ty = 0; ty < 4; ++ty)
+              for (int tx = 0; tx < 4; ++tx)
+                for (int dy = 0; dy < 2; ++dy)
+                  for (int dx = 0; dx < 2; ++dx)
+                    for (int ch = 0; ch < 3; ++ch) {
+                      const int ky = 2 * ty + dy, kx = 2 * tx + dx;
+                      if (ky >= 7 || kx >= 7) continue;
+                      const float v = w[(((size_t)o * 3 + ch) * 7 + ky) * 7 + kx];
+                      wp[(size_t)o * c.Ktotal + (size_t)ty * 64 + tx * 16 + (dy * 2 + dx) * 3 + ch] = f2bf(v);
+                    }
+        } else {
+          for (int o = 0; o < c.Cout; ++o)
+            for (int ch = 0; ch < c.Cin; ++ch)
+              for (int t = 0; t < taps; ++t) {
+                const float v = w[((size_t)o * c.Cin + ch) * taps + t];
+                const size_t kidx = ((size_t)t * kp.cblocks + ch / kBlockK) * kBlockK + ch % kBlockK;
+                wp[(size_t)o * c.Ktotal + kidx] = f2bf(v);
+              }
+        }
+        CUDA_OK(cudaMemcpyAsync(c.w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice, stream_));
+        if (L.params.size() > 1)
+          CUDA_OK(cudaMemcpyAsync(c.bias_dev, L.params[1].data.data(), (size_t)c.Cout * 4, cudaMemcpyHostToDevice, stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));  // wp is a temporary
+      }
+      if (bn_dirty) {
+        std::vector<float> sc, sh;
+        bn_fold(layers_[c.bn_layer], sc, sh);
+        CUDA_OK(cudaMemcpyAsync(c.scale_dev, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, stream_));
+        CUDA_OK(cudaMemcpyAsync(c.shift_dev, sh.data(), sh.size() * 4, cudaMemcpyHostToDevice, stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+      }
+    } else if (op.type == Op::FC) {
+      OrigLayer& L = layers_[op.layer];
+      if (L.params_dirty) {
+        CUDA_OK(cudaMemcpyAsync(op.w_dev, L.params[0].data.data(), L.params[0].data.size() * 4, cudaMemcpyHostToDevice, stream_));
+        if (op.b_dev)
+          CUDA_OK(cudaMemcpyAsync(op.b_dev, L.params[1].data.data(), L.params[1].data.size() * 4, cudaMemcpyHostToDevice, stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+      }
+    } else if (op.type == Op::SSR) {
+      OrigLayer& L = layers_[op.layer];
+      if (L.params_dirty || L.type == "ReLU") {
+        std::vector<float> sc, sh;
+        if (L.type == "BN") bn_fold(L, sc, sh);
+        else { sc.assign(tensors_[op.in0].C(), 1.f); sh.assign(tensors_[op.in0].C(), 0.f); }
+        CUDA_OK(cudaMemcpyAsync(op.scale_dev, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, stream_));
+        CUDA_OK(cudaMemcpyAsync(op.shift_dev, sh.data(), sh.size() * 4, cudaMemcpyHostToDevice, stream_));
+        CUDA_OK(cudaStreamSynchronize(stream_));
+      }
+    }
+  }
+  for (auto& L : layers_) L.params_dirty = false;
+}
+
+// =====================================================================================
+// host <-> device blob traffic (what SyncedMemory::to_cpu/to_gpu do lazily, syncedmem.cpp:21-70)
+static float* g_stage = nullptr;
+static size_t g_stage_bytes = 0;
+static float* staging(size_t bytes) {
+  if (bytes > g_stage_bytes) {
+    if (g_stage) cudaFree(g_stage);
+    CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g_stage), bytes));
+    g_stage_bytes = bytes;
+  }
+  return g_stage;
+}
+
+void Net::download(Tensor& t) {
+  ECO_CHECK(t.materialized && t.dev, "blob '" << t.name << "' is fused away in the current plan and has no data; create "
+                                                 "the net with option keep_all_blobs=1 to materialise every blob");
+  const size_t n = (size_t)t.count();
+  t.host.resize(n, true);
+  if (n == 0) return;
+  if (t.kind == Kind::CL) {
+    float* st = staging(n * 4);
+    CUDA_OK(launch_cl_to_f32(view(t), st, stream_));
+    CUDA_OK(cudaMemcpyAsync(t.host.p, st, n * 4, cudaMemcpyDeviceToHost, stream_));
+  } else {
+    CUDA_OK(cudaMemcpyAsync(t.host.p, t.dev, n * 4, cudaMemcpyDeviceToHost, stream_));
+  }
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  t.dev_newer = false;
+}
+
+void Net::upload(Tensor& t) {
+  const size_t n = (size_t)t.count();
+  if (n == 0 || t.host.empty()) { t.host_newer = false; return; }
+  if (!t.materialized || !t.dev) { t.host_newer = false; return; }  // nothing reads it on the device
+  if (t.kind == Kind::CL) {
+    float* st = staging(n * 4);
+    CUDA_OK(cudaMemcpyAsync(st, t.host.p, n * 4, cudaMemcpyHostToDevice, stream_));
+    CUDA_OK(launch_f32_to_cl(st, view(t), stream_));
+  } else {
+    CUDA_OK(cudaMemcpyAsync(t.dev, t.host.p, n * 4, cudaMemcpyHostToDevice, stream_));
+  }
+  t.host_newer = false;
+  t.dev_newer = false;
+}
+
+float* Net::host_data(int vb, bool for_write, size_t* count) {
+  ECO_CHECK(vb >= 0 && vb < (int)vis_blobs_.size(), "blob index out of range");
+  Tensor& t = tensors_[vis_blobs_[vb].tensor];
+  const size_t n = (size_t)t.count();
+  if (t.dev_newer && planned_) download(t);
+  if (t.host.n != n) t.host.resize(n, true);
+  if (for_write) t.host_newer = true;
+  if (count) *count = n;
+  return t.host.p;
+}
+float* Net::host_diff(int vb, bool for_write, size_t* count) {
+  ECO_CHECK(vb >= 0 && vb < (int)vis_blobs_.size(), "blob index out of range");
+  Tensor& t = tensors_[vis_blobs_[vb].tensor];
+  const size_t n = (size_t)t.count();
+  if (t.host_diff.n != n) t.host_diff.resize(n, false);
+  (void)for_write;
+  if (count) *count = n;
+  return t.host_diff.p;
+}
+
+void Net::set_input_device(int vb, const void* dev, size_t count) {
+  if (!planned_) plan();
+  ECO_CHECK(vb >= 0 && vb < (int)vis_blobs_.size(), "blob index out of range");
+  Tensor& t = tensors_[vis_blobs_[vb].tensor];
+  ECO_CHECK(t.kind == Kind::F32 && t.dev, "set_input_device: '" << t.name << "' is not a plain fp32 input blob");
+  ECO_CHECK(count == (size_t)t.count(), "set_input_device: size mismatch");
+  CUDA_OK(cudaMemcpyAsync(t.dev, dev, count * 4, cudaMemcpyDeviceToDevice, stream_));
+  t.host_newer = false;
+  t.dev_newer = true;
+}
+
+const float* Net::device_f32(int vb, size_t* count) {
+  if (!planned_) plan();
+  Tensor& t = tensors_[vis_blobs_[vb].tensor];
+  ECO_CHECK(t.kind == Kind::F32 && t.materialized && t.dev, "blob '" << t.name << "' is not a materialised plain fp32 blob");
+  if (count) *count = (size_t)t.count();
+  return static_cast<const float*>(t.dev);
+}
+
+void Net::sync() {
+  if (stream_) CUDA_OK(cudaStreamSynchronize(stream_));
+  if (error_flag_dev_) {
+    int flag = 0;
+    CUDA_OK(cudaMemcpy(&flag, error_flag_dev_, sizeof(int), cudaMemcpyDeviceToHost));
+    ECO_CHECK(flag == 0, "conv kernel pipeline timed out (code " << flag << ")");
+  }
+}
+
+// =====================================================================================
+void Net::run_op(Op& op) {
+  switch (op.type) {
+    case Op::CONV: {
+      ConvOp& c = convs_[op.conv];
+      if (c.stem_in) {
+        Tensor& x = tensors_[c.in_tensor];
+        if (c.stem) {
+          CUDA_OK(launch_stem_s2d(static_cast<const float*>(x.dev), c.stem_in, c.NB, c.I[1], c.I[2], c.stem_CH,
+                                  c.stem_CW, stream_));
+        } else {
+          ClView v;
+          v.ptr = c.stem_in;
+          v.outer = c.NB;
+          v.inner = (long long)c.I[0] * c.I[1] * c.I[2];
+          v.C = c.Cin;
+          v.cs = c.Cin_k;
+          v.coff = 0;
+          CUDA_OK(launch_f32_to_cl(static_cast<const float*>(x.dev), v, stream_));
+        }
+      }
+      CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.tmB, stream_));
+      if (c.out_tensor >= 0) tensors_[c.out_tensor].dev_newer = true;
+      if (c.raw_tensor >= 0) tensors_[c.raw_tensor].dev_newer = true;
+      break;
+    }
+    case Op::POOL_CL:
+      CUDA_OK(launch_pool_cl(op.pool, stream_));
+      break;
+    case Op::GLOBAL_AVG:
+      CUDA_OK(launch_global_avg_cl(view(tensors_[op.in0]), static_cast<float*>(tensors_[op.out].dev), stream_));
+      break;
+    case Op::POOL_F32:
+      CUDA_OK(launch_pool_f32(op.poolf, stream_));
+      break;
+    case Op::FC:
+      CUDA_OK(launch_inner_product(static_cast<const float*>(tensors_[op.in0].dev), op.w_dev, op.b_dev,
+                                   static_cast<float*>(tensors_[op.out].dev), op.M, op.N, op.Kd, stream_));
+      break;
+    case Op::SSR:
+      CUDA_OK(launch_scale_shift_relu_cl(view(tensors_[op.in0]), view(tensors_[op.out]), op.scale_dev, op.shift_dev,
+                                         op.relu ? 1 : 0, stream_));
+      break;
+    case Op::ELTWISE:
+      CUDA_OK(launch_eltwise_sum_cl(view(tensors_[op.in0]), view(tensors_[op.in1]), view(tensors_[op.out]), stream_));
+      break;
+    case Op::COPY2D: {
+      const char* src = static_cast<const char*>(tensors_[op.in0].dev) + op.src_off;
+      char* dst = static_cast<char*>(tensors_[op.out].dev) + op.dst_off;
+      CUDA_OK(cudaMemcpy2DAsync(dst, op.dst_pitch, src, op.src_pitch, op.width_bytes, op.rows, cudaMemcpyDeviceToDevice,
+                                stream_));
+      break;
+    }
+    case Op::CL_TO_F32:
+      CUDA_OK(launch_cl_to_f32(view(tensors_[op.in0]), static_cast<float*>(tensors_[op.out].dev), stream_));
+      break;
+    case Op::F32_TO_CL:
+      CUDA_OK(launch_f32_to_cl(static_cast<const float*>(tensors_[op.in0].dev), view(tensors_[op.out]), stream_));
+      break;
+    case Op::SOFTMAX:
+      CUDA_OK(launch_softmax_f32(static_cast<const float*>(tensors_[op.in0].dev), static_cast<float*>(tensors_[op.out].dev),
+                                 tensors_[op.in0].shape[0], (int)(tensors_[op.in0].count() / std::max(1, tensors_[op.in0].shape[0])),
+                                 stream_));
+      break;
+  }
+  if (op.out >= 0) tensors_[op.out].dev_newer = true;
+}
+
+float Net::forward(int start, int end) {
+  if (!planned_) plan();
+  upload_params();
+  const int NV = (int)vis_layers_.size();
+  if (end < 0) end = NV - 1;
+  ECO_CHECK(start >= 0 && end < NV && start <= end, "forward range [" << start << "," << end << "] out of bounds");
+  // visible layer range -> original layer range
+  int lo = (int)layers_.size(), hi = -1;
+  for (int v = start; v <= end; ++v)
+    if (vis_layers_[v].orig >= 0) {
+      lo = std::min(lo, vis_layers_[v].orig);
+      hi = std::max(hi, vis_layers_[v].orig);
+    }
+  const bool full = (start == 0 && end == NV - 1);
+  // host-modified blobs go up first (net inputs are always re-sent: the caller owns that memory)
+  for (int vb : inputs_) {
+    Tensor& t = tensors_[vis_blobs_[vb].tensor];
+    if (!t.host.empty() && !t.dev_newer) t.host_newer = true;
+  }
+  for (auto& t : tensors_)
+    if (t.host_newer && t.root >= 0) upload(t);
+  for (int vb : inputs_) tensors_[vis_blobs_[vb].tensor].dev_newer = false;
+
+  int launches = 0;
+  auto run_range = [&]() {
+    for (auto& op : ops_) {
+      if (!full && (op.last_layer < lo || op.first_layer > hi)) continue;
+      run_op(op);
+      launches += op.launches;
+    }
+  };
+  if (full && use_graph_) {
+    if (!graph_valid_) {
+      cudaGraph_t g = nullptr;
+      CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+      run_range();
+      CUDA_OK(cudaStreamEndCapture(stream_, &g));
+      if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+      CUDA_OK(cudaGraphInstantiate(&graph_exec_, g, 0));
+      cudaGraphDestroy(g);
+      graph_valid_ = true;
+    } else {
+      for (auto& op : ops_) {
+        launches += op.launches;
+        if (op.out >= 0) tensors_[op.out].dev_newer = true;
+        if (op.type == Op::CONV) {
+          ConvOp& c = convs_[op.conv];
+          if (c.out_tensor >= 0) tensors_[c.out_tensor].dev_newer = true;
+          if (c.raw_tensor >= 0) tensors_[c.raw_tensor].dev_newer = true;
+        }
+      }
+    }
+    CUDA_OK(cudaGraphLaunch(graph_exec_, stream_));
+  } else {
+    run_range();
+  }
+  last_launches_ = launches;
+  return 0.f;
+}
+
+int Net::profile(eco_op_time* out, int cap) {
+  if (!planned_) plan();
+  upload_params();
+  for (auto& t : tensors_)
+    if (t.host_newer && t.root >= 0) upload(t);
+  std::vector<cudaEvent_t> ev(ops_.size() + 1);
+  for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+  CUDA_OK(cudaEventRecord(ev[0], stream_));
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    run_op(ops_[i]);
+    CUDA_OK(cudaEventRecord(ev[i + 1], stream_));
+  }
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  op_names_.resize(ops_.size());
+  int n = 0;
+  for (size_t i = 0; i < ops_.size() && n < cap; ++i, ++n) {
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    op_names_[i] = ops_[i].name;
+    out[n].name = op_names_[i].c_str();
+    out[n].kind = ops_[i].type == Op::CONV ? 0 : (ops_[i].type == Op::COPY2D ? 2 : 1);
+    out[n].ms = ms;
+    out[n].flops = ops_[i].flops;
+    out[n].bytes = ops_[i].bytes;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return n;
+}
+
+}  // namespace eco

@@ -1,0 +1,230 @@
+// net.hpp -- host side of libeco_b200: the caffe-visible graph (layers / blobs / auto-Splits, names as
+// caffe_3d's Net::Init produces them, net.cpp:39-316 + util/insert_splits.cpp) and the fused
+// execution plan that runs it on sm_100a.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "conv_umma.cuh"
+#include "prototxt.hpp"
+
+struct eco_op_time;
+
+namespace eco {
+
+enum class Kind { F32, CL };  // plain fp32 in caffe layout | bf16 channels-last
+
+// fp32 host mirror; page-locked when a CUDA device is usable so uploads/downloads are async DMA
+struct HostBuf {
+  float* p = nullptr;
+  size_t n = 0;
+  bool pinned = false;
+  HostBuf() = default;
+  HostBuf(const HostBuf&) = delete;
+  HostBuf& operator=(const HostBuf&) = delete;
+  HostBuf(HostBuf&& o) noexcept : p(o.p), n(o.n), pinned(o.pinned) { o.p = nullptr; o.n = 0; }
+  HostBuf& operator=(HostBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; pinned = o.pinned; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~HostBuf() { release(); }
+  void resize(size_t count, bool try_pin);  // contents zeroed when (re)allocated
+  void release();
+  bool empty() const { return p == nullptr; }
+};
+
+// A tensor = one caffe blob of the original (pre-Split) graph.
+struct Tensor {
+  std::string name;
+  std::vector<int> shape;  // caffe logical shape
+  Kind kind = Kind::F32;
+  int ch_axis = 1;         // CL: logical axis that is the channel
+  // storage: `root` tensor owns the allocation; views / concat slices point into it
+  int root = -1;
+  long long cs = 0;        // CL channel stride (elements) of the underlying buffer
+  int coff = 0;            // CL first channel in the buffer
+  bool materialized = false;  // has device storage that the plan writes
+  void* dev = nullptr;     // device pointer (CL: bf16 base of the *buffer*, F32: float*)
+  size_t dev_bytes = 0;
+  bool owns = false;
+  // host mirror, fp32 caffe layout (shared by all Split copies, like ShareData)
+  HostBuf host, host_diff;
+  bool host_newer = false;  // host written since the last upload
+  bool dev_newer = false;   // device written since the last download
+  int producer = -1;        // orig layer index that (last) writes it, -1: net input
+  std::vector<int> consumers;  // orig layer indices reading it, in order
+
+  long long count() const {
+    long long n = 1;
+    for (int d : shape) n *= d;
+    return n;
+  }
+  int C() const { return shape[ch_axis]; }
+  long long outer() const {
+    long long n = 1;
+    for (int i = 0; i < ch_axis; ++i) n *= shape[i];
+    return n;
+  }
+  long long inner() const {
+    long long n = 1;
+    for (size_t i = ch_axis + 1; i < shape.size(); ++i) n *= shape[i];
+    return n;
+  }
+};
+
+struct ParamBlob {
+  std::vector<int> shape;
+  std::vector<float> data;
+  std::vector<float> diff;
+};
+
+struct OrigLayer {
+  std::string name, type;
+  const pt::Msg* msg = nullptr;
+  std::vector<int> bottoms, tops;  // tensor ids
+  std::vector<ParamBlob> params;
+  bool params_dirty = true;
+  int vis_index = -1;  // index in the visible layer list
+};
+
+// What caffe shows: layer list with Split layers, blob list with split outputs.
+struct VisLayer {
+  std::string name, type;
+  int orig = -1;  // OrigLayer index, -1 for auto Split
+  std::vector<int> bottoms, tops;  // visible blob ids
+};
+struct VisBlob {
+  std::string name;
+  int tensor = -1;
+};
+
+struct ConvOp {
+  int conv_layer = -1, bn_layer = -1, elt_layer = -1;
+  bool relu = false;
+  bool stem = false;  // 7x7/s2/p3 Cin=3 handled as a 4x1 conv over space-to-depth windows
+  int in_tensor = -1;
+  int out_tensor = -1;  // y (BN/ReLU applied if fused), -1 if not stored
+  int raw_tensor = -1;  // raw = conv + bias (+ residual), -1 if not stored
+  int res_tensor = -1;  // residual input
+  // geometry
+  int nsp = 2, Cin = 0, Cin_k = 0, Cout = 0, Cout_pad = 0;
+  int K[3] = {1, 1, 1}, S[3] = {1, 1, 1}, P[3] = {0, 0, 0};
+  int I[3] = {1, 1, 1}, O[3] = {1, 1, 1};
+  int NB = 0;
+  long long Ktotal = 0;
+  // device constants
+  __nv_bfloat16* w_dev = nullptr;
+  float *bias_dev = nullptr, *scale_dev = nullptr, *shift_dev = nullptr;
+  __nv_bfloat16* stem_in = nullptr;  // transformed input (stem / generic fp32 input)
+  size_t stem_bytes = 0;
+  int stem_CH = 0, stem_CW = 0;
+  ConvKernelParams kp{};
+  CUtensorMap tmA{}, tmB{};
+  double flops = 0, bytes = 0;
+};
+
+struct Op {
+  enum Type { CONV, POOL_CL, GLOBAL_AVG, POOL_F32, FC, SSR, ELTWISE, COPY2D, CL_TO_F32, F32_TO_CL, SOFTMAX };
+  Type type;
+  std::string name;
+  int first_layer = 0, last_layer = 0;  // orig layer range covered
+  int conv = -1;                        // index into convs_
+  // generic payload
+  int in0 = -1, in1 = -1, out = -1;     // tensor ids
+  int layer = -1;                       // orig layer (params, pooling geometry)
+  PoolParams pool{};
+  PoolF32Params poolf{};
+  float *scale_dev = nullptr, *shift_dev = nullptr;  // SSR
+  bool relu = false;
+  float *w_dev = nullptr, *b_dev = nullptr;          // FC
+  int M = 0, N = 0, Kd = 0;
+  // COPY2D
+  size_t width_bytes = 0, rows = 0, src_pitch = 0, dst_pitch = 0, src_off = 0, dst_off = 0;
+  double flops = 0, bytes = 0;
+  int launches = 1;
+};
+
+class Net {
+ public:
+  Net(const std::string& text, int phase);
+  ~Net();
+
+  // registry
+  std::string name_;
+  int phase_;
+  std::vector<VisLayer> vis_layers_;
+  std::vector<VisBlob> vis_blobs_;
+  std::vector<OrigLayer> layers_;
+  std::vector<Tensor> tensors_;
+  std::vector<int> inputs_, outputs_;  // visible blob ids
+  std::map<std::string, int> vis_layer_index_, vis_blob_index_;
+
+  void set_option(const std::string& key, int v);
+  void set_stream(cudaStream_t s);
+  void reshape_blob(int vis_blob, const std::vector<int>& dims);
+  void reshape();
+  float forward(int start, int end);
+  void sync();
+  float* host_data(int vis_blob, bool for_write, size_t* count);
+  float* host_diff(int vis_blob, bool for_write, size_t* count);
+  void set_input_device(int vis_blob, const void* dev, size_t count);
+  const float* device_f32(int vis_blob, size_t* count);
+  void set_param(int vis_layer, int idx, const float* data, size_t count);
+  ParamBlob& param(int vis_layer, int idx);
+  int num_params(int vis_layer) const;
+  void mark_params_dirty(int vis_layer);
+  int profile(eco_op_time* out, int cap);
+  int last_launches() const { return last_launches_; }
+  void copy_from(const std::string& path);
+  void save(const std::string& path) const;
+
+ private:
+  std::shared_ptr<pt::Msg> proto_;
+  std::vector<std::shared_ptr<pt::Msg>> keep_;
+  std::map<std::string, int> tensor_index_;
+  // options
+  bool keep_all_ = false;
+  int a_mode_ = -1;
+  bool use_graph_ = false;
+  // plan
+  bool planned_ = false;
+  std::vector<Op> ops_;
+  std::vector<ConvOp> convs_;
+  std::vector<void*> allocs_;
+  cudaStream_t stream_ = nullptr;
+  bool own_stream_ = false;
+  int* error_flag_dev_ = nullptr;
+  int last_launches_ = 0;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  bool graph_valid_ = false;
+  std::vector<std::string> op_names_;
+
+  void build_graph();
+  void init_params();
+  void infer_shapes();
+  void plan();
+  void free_plan();
+  void upload_params();
+  void upload_dirty_inputs(int first_op);
+  void run_op(Op& op);
+  void ensure_device();
+  void* dalloc(size_t bytes, bool zero);
+  Tensor& T(int i) { return tensors_[i]; }
+  int add_tensor(const std::string& name);
+  void plan_conv_group(int li, std::vector<bool>& done);
+  void make_tensor_maps(ConvOp& c);
+  void download(Tensor& t);
+  void upload(Tensor& t);
+  ClView view(const Tensor& t) const;
+};
+
+void set_last_error(const std::string& s);
+
+}  // namespace eco

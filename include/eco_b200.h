@@ -1,0 +1,127 @@
+/*
+ * eco_b200.h -- C ABI of libeco_b200.so: the drop-in boundary for ECO's hot path
+ * (2-D BN-Inception trunk -> r2Dto3D -> 3-D ResNet-18 head -> global_pool -> fc) on B200.
+ *
+ * It replaces, for that path, the caffe_3d C++ surface
+ *     caffe::Net<float>   caffe_3d/include/caffe/net.hpp:24-281   (src/caffe/net.cpp)
+ *     caffe::Blob<float>  caffe_3d/include/caffe/blob.hpp:25-282  (src/caffe/blob.cpp, syncedmem.cpp)
+ *     caffe::Caffe        caffe_3d/include/caffe/common.hpp:160-174 (set_mode / SetDevice)
+ * and is what a binding (boost.python `_caffe.cpp`, our ctypes shim, a C++ facade) links to.
+ * Plain pointers and sizes only; no torch / STL types cross this boundary.
+ *
+ * Conventions
+ *   - Every call returns 0 on success, non-zero on failure; eco_last_error() then holds a
+ *     message (thread-local).  caffe_3d aborts the process on CHECK failure
+ *     (e.g. base_conv_layer.cpp:152, blob.hpp:141); a facade that wants that behaviour calls
+ *     abort() on non-zero.
+ *   - Host views are fp32 in caffe's logical layout (row-major N,C[,D],H,W), whatever the
+ *     device layout is (bf16 channels-last).  They stay valid until eco_net_reshape /
+ *     eco_net_destroy.
+ *   - One eco_net per GPU; calls on one net must be serialised by the caller
+ *     (caffe::Net is not thread-safe either).
+ *   - There is no CPU execution path: eco_net_forward fails with an error if no CUDA
+ *     device is usable (caffe's set_mode_cpu is accepted and ignored with an error on use).
+ */
+#ifndef ECO_B200_H_
+#define ECO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct eco_net eco_net;
+
+#define ECO_PHASE_TRAIN 0 /* caffe::TRAIN, caffe.proto Phase */
+#define ECO_PHASE_TEST 1  /* caffe::TEST */
+
+/* ---- process-wide (caffe::Caffe singleton, common.hpp:160-174; _caffe.cpp:213-215) ---- */
+const char* eco_last_error(void);
+const char* eco_version(void);
+int eco_set_device(int device);          /* Caffe::SetDevice */
+int eco_set_mode(int gpu);               /* Caffe::set_mode: 1 = GPU; 0 = CPU is recorded, forward then fails */
+int eco_device_count(int* count);        /* 0 devices is not an error here */
+
+/* ---- construction (Net::Net(file, phase) net.cpp:31-36; Net::Init :39-316) ---- */
+int eco_net_create(const char* prototxt_path, int phase, eco_net** out);
+int eco_net_create_from_string(const char* prototxt_text, int phase, eco_net** out);
+int eco_net_destroy(eco_net* net);
+/* options, set before the first forward/reshape:  "keep_all_blobs" (0/1: also store blobs the
+ * fused plan would keep on chip, e.g. a conv output that only feeds its BN), "a_mode"
+ * (0 cp.async gather, 1 TMA im2col, -1 auto), "use_graph" (0/1 CUDA-graph replay of full forwards) */
+int eco_net_set_option(eco_net* net, const char* key, int value);
+/* run on a caller-owned CUDA stream (cudaStream_t as void*), default: the net's own stream */
+int eco_net_set_stream(eco_net* net, void* cuda_stream);
+
+/* ---- weights (Net::CopyTrainedLayersFrom net.cpp:852-883, ToProto :885-904; blobs() of Layer) ---- */
+int eco_net_copy_from(eco_net* net, const char* caffemodel_path);   /* match by layer name */
+int eco_net_save(const eco_net* net, const char* caffemodel_path);
+int eco_net_layer_num_params(const eco_net* net, int layer, int* n);
+int eco_net_param_shape(const eco_net* net, int layer, int blob_idx, int* dims, int* ndims /* in: capacity, out: used */);
+int eco_net_set_param(eco_net* net, int layer, int blob_idx, const float* data, size_t count);
+int eco_net_get_param(const eco_net* net, int layer, int blob_idx, float* data, size_t count);
+/* mutable host pointer to a parameter blob (caffe: layer->blobs()[i]->mutable_cpu_data()); the
+ * device copy is refreshed at the next forward */
+int eco_net_param_host(eco_net* net, int layer, int blob_idx, float** data, size_t* count);
+
+/* ---- introspection (net.hpp:101-195: name(), layer_names(), blob_names(), inputs/outputs, has_blob ...) ---- */
+const char* eco_net_name(const eco_net* net);
+int eco_net_phase(const eco_net* net);
+int eco_net_num_layers(const eco_net* net);            /* includes auto-inserted Split layers (insert_splits.cpp) */
+const char* eco_net_layer_name(const eco_net* net, int i);
+const char* eco_net_layer_type(const eco_net* net, int i);
+int eco_net_layer_index(const eco_net* net, const char* name);   /* -1 if absent */
+int eco_net_layer_num_bottoms(const eco_net* net, int i);
+int eco_net_layer_bottom(const eco_net* net, int i, int j);      /* blob index */
+int eco_net_layer_num_tops(const eco_net* net, int i);
+int eco_net_layer_top(const eco_net* net, int i, int j);
+int eco_net_num_blobs(const eco_net* net);
+const char* eco_net_blob_name(const eco_net* net, int i);
+int eco_net_blob_index(const eco_net* net, const char* name);    /* -1 if absent */
+int eco_net_blob_shape(const eco_net* net, int i, int* dims, int* ndims /* in: capacity, out: used */);
+int eco_net_num_inputs(const eco_net* net);
+int eco_net_input_blob(const eco_net* net, int i);
+int eco_net_num_outputs(const eco_net* net);
+int eco_net_output_blob(const eco_net* net, int i);
+
+/* ---- shapes (Blob::Reshape blob.cpp:22-51, Net::Reshape net.cpp:824-828) ---- */
+int eco_blob_reshape(eco_net* net, int blob, const int* dims, int ndims);   /* then eco_net_reshape */
+int eco_net_reshape(eco_net* net);
+
+/* ---- execution (Net::ForwardFromTo net.cpp:566-583, BackwardFromTo :637-706) ---- */
+int eco_net_forward(eco_net* net, int start, int end, float* loss);  /* layer indices as in caffe; end = -1: last */
+int eco_net_backward(eco_net* net, int start, int end);              /* training path: not in this round */
+int eco_net_sync(eco_net* net);                                      /* wait for the net's stream */
+
+/* ---- blob data (Blob::cpu_data / mutable_cpu_data / cpu_diff, SyncedMemory syncedmem.cpp:21-70) ---- */
+/* fp32 host mirror in caffe layout; `for_write` = 1 marks the host copy newer (mutable_cpu_data) so
+ * the next forward uploads it; 0 only syncs device -> host if the device copy is newer. */
+int eco_blob_host_data(eco_net* net, int blob, int for_write, float** data, size_t* count);
+int eco_blob_host_diff(eco_net* net, int blob, int for_write, float** data, size_t* count);
+
+/* ---- fast paths beyond caffe's surface (device-resident I/O for serving) ---- */
+/* copy `count` fp32 values already on the device (caffe layout) into an input blob, no host hop */
+int eco_net_set_input_device(eco_net* net, int blob, const void* dev_f32, size_t count);
+/* device pointer of a plain fp32 blob (e.g. fc8) valid until reshape; NULL/err for fused-away blobs */
+int eco_blob_device_f32(eco_net* net, int blob, const float** dev, size_t* count);
+
+/* ---- measurement hooks used by bench.py ---- */
+/* number of kernels this library launched for the last eco_net_forward on this net */
+int eco_net_last_launch_count(const eco_net* net, int* launches);
+/* per-op timing of one forward with CUDA events on the net's stream: fills up to `cap` entries;
+ * names are owned by the net.  kind: 0 conv(implicit GEMM), 1 other kernel, 2 memcpy */
+typedef struct eco_op_time {
+  const char* name;
+  int kind;
+  float ms;
+  double flops;       /* 2*M*N*K incl. padding taps, the algorithmic figure of SURVEY.md 8(d) */
+  double bytes;       /* algorithmic HBM bytes: input once + output once + weights once */
+} eco_op_time;
+int eco_net_profile_forward(eco_net* net, eco_op_time* out, int cap, int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECO_B200_H_ */

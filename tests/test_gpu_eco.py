@@ -1,0 +1,109 @@
+"""Whole-network GPU parity: ECO-Lite / ECO-Full through the public surface against the oracle's
+bf16-mirror forward on identical harness weights and synthetic frames (SURVEY.md 8(d) inputs),
+plus size-independent properties at the full N=16 configuration."""
+import numpy as np
+import pytest
+
+from oracle import refnet
+import gen_eco_prototxt as gen
+from eco_testlib import TOL_NET, TOL_OP, describe_mismatch, load_params, make_net, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+# blobs whose conv output is consumed by a fused residual add: never stored
+FUSED_AWAY = {"res3b_2", "res4a_down", "res4b_2", "res5a_down", "res5b_2"}
+
+
+def oracle_lite(segments, batch, classes=101, full=False):
+    txt = (gen.eco_full_deploy if full else gen.eco_lite_deploy)(segments=segments, classes=classes, batch=batch)
+    ref = refnet.RefNet(txt).init_params(4321)
+    x = refnet.eco_input(batch, segments)
+    ref.calibrate_bn(x)
+    return txt, ref, x
+
+
+@pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
+def test_eco_lite_n4_every_blob(gpu, a_mode):
+    # BASELINE config 1 geometry (N=4), every blob of deploy.prototxt
+    txt, ref, x = oracle_lite(4, 2)
+    want = ref.forward(x, bf16=True)
+    net = make_net(txt, keep_all=True, a_mode=a_mode)
+    load_params(net, ref.params_dict())
+    net.blobs["data"].data[...] = x
+    out = net.forward()
+    assert list(out.keys()) == ["fc8"]
+    blobs = net.blobs
+    worst = ("", 0.0)
+    for name, w in want.items():
+        if name in FUSED_AWAY or name not in blobs:
+            continue
+        g = blobs[name].data
+        assert g.shape == w.shape, (name, g.shape, w.shape)
+        e = min(rel_l2(g, w), rel_l2(g, refnet.round_bf16(w)))
+        if e > worst[1]:
+            worst = (name, e)
+        assert e <= TOL_NET, describe_mismatch(g, w, name)
+    print("worst blob", worst)
+    assert rel_max(out["fc8"], want["fc8"]) <= 5 * TOL_OP, describe_mismatch(out["fc8"], want["fc8"], "fc8")
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cudagraph"])
+def test_eco_lite_n4_fast_plan_matches(gpu, graph):
+    # the production plan (nothing extra materialised, optionally CUDA-graph replay) gives the same logits
+    txt, ref, x = oracle_lite(4, 2)
+    want = ref.forward(x, bf16=True)["fc8"]
+    net = make_net(txt, keep_all=False, graph=graph)
+    load_params(net, ref.params_dict())
+    for _ in range(3):
+        net.blobs["data"].data[...] = x
+        got = net.forward()["fc8"].copy()
+        assert rel_max(got, want) <= 5 * TOL_OP, describe_mismatch(got, want, "fc8")
+    with pytest.raises(RuntimeError):
+        net.blobs["conv1_7x7_s2"].data  # fused away in the fast plan: loud, not stale
+
+
+def test_eco_full_n4(gpu):
+    txt, ref, x = oracle_lite(4, 2, classes=400, full=True)
+    want = ref.forward(x, bf16=True)
+    net = make_net(txt, keep_all=True)
+    load_params(net, ref.params_dict())
+    net.blobs["data"].data[...] = x
+    out = net.forward()
+    for name in ("inception_3c_output", "inception_4e_output", "inception_5b_output", "global_pool2D",
+                 "pool_fusion_st2D", "global_pool", "global_pool_gn02_reshape", "fc8"):
+        g = net.blobs[name].data
+        w = want[name]
+        e = min(rel_l2(g, w), rel_l2(g, refnet.round_bf16(w)))
+        assert e <= TOL_NET, describe_mismatch(g, w, name)
+    assert out["fc8"].shape == (2, 400)
+
+
+def test_eco_lite_n16_properties(gpu):
+    """Full-size configuration (N=16): properties that do not need the oracle at this size --
+    determinism, per-video independence (TEST-phase BN couples nothing across videos), and
+    batch reshaping at run time (Layer::Forward re-runs Reshape, layer.hpp:447)."""
+    segments, batch = 16, 3
+    txt = gen.eco_lite_deploy(segments=segments, classes=101, batch=batch)
+    ref = refnet.RefNet(gen.eco_lite_deploy(segments=4, classes=101, batch=1)).init_params(4321)
+    ref.calibrate_bn(refnet.eco_input(1, 4))
+    net = make_net(txt, keep_all=False)
+    load_params(net, ref.params_dict())  # same parameter shapes for any N
+    x = refnet.eco_input(batch, segments)
+    net.blobs["data"].data[...] = x
+    a = net.forward()["fc8"].copy()
+    net.blobs["data"].data[...] = x
+    b = net.forward()["fc8"].copy()
+    assert np.array_equal(a, b), "forward is not deterministic"
+    perm = [2, 0, 1]
+    xp = x.reshape(batch, segments, 3, 224, 224)[perm].reshape(x.shape)
+    net.blobs["data"].data[...] = xp
+    c = net.forward()["fc8"].copy()
+    assert np.array_equal(c, a[perm]), "videos are not independent of their batch position"
+    # shrink the batch at run time: blob.reshape + net.reshape, as test_net.cpp:2269-2325 does
+    net.blobs["data"].reshape(segments, 3, 224, 224)
+    net.reshape()
+    net.blobs["data"].data[...] = x[:segments]
+    d = net.forward()["fc8"].copy()
+    assert d.shape == (1, 101)
+    assert np.array_equal(d[0], a[0])
+    assert np.isfinite(a).all() and a.std() > 1e-3

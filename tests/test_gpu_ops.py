@@ -1,0 +1,222 @@
+"""GPU parity tests for the individual fused ops, driven through the public surface
+(caffe shim -> C ABI -> sm_100a kernels) on tiny nets, checked against the oracle
+(oracle/ref_cpu.c) and against the reference's golden pooling vectors.
+Every conv case runs in both A-operand modes (cp.async gather / TMA im2col)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refnet
+from eco_testlib import TOL_OP, describe_mismatch, load_params, make_net, rel_max
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def conv_net(shape, cout, k, s, p, bn=True, relu=True):
+    nsp = len(shape) - 2
+    dims = "".join("input_dim: %d\n" % d for d in shape) if len(shape) == 4 else \
+        "input_shape { %s }\n" % " ".join("dim: %d" % d for d in shape)
+    lst = lambda v: "[%s]" % ", ".join(str(i) for i in v)
+    txt = 'name: "t"\ninput: "data"\n' + dims
+    txt += ('layer { name: "c" type: "Convolution" bottom: "data" top: "c" convolution_param { num_output: %d '
+            'kernel_size: %s stride: %s pad: %s } }\n' % (cout, lst(k), lst(s), lst(p)))
+    if bn:
+        txt += 'layer { name: "c_bn" type: "BN" bottom: "c" top: "c_bn" }\n'
+        if relu:
+            txt += 'layer { name: "c_relu" type: "ReLU" bottom: "c_bn" top: "c_bn" }\n'
+    return txt
+
+
+def two_conv_net(shape, cmid, cout, k, s, p):
+    """fp32 input -> 1x1 conv (+BN+ReLU) -> conv under test (+BN+ReLU): the second conv reads a
+    channels-last bf16 tensor exactly like every conv inside ECO."""
+    nsp = len(shape) - 2
+    one = [1] * nsp
+    zero = [0] * nsp
+    txt = conv_net(shape, cmid, one, one, zero).replace('"c"', '"a"').replace('"c_bn"', '"a_bn"').replace('"c_relu"', '"a_relu"')
+    lst = lambda v: "[%s]" % ", ".join(str(i) for i in v)
+    txt += ('layer { name: "c" type: "Convolution" bottom: "a_bn" top: "c" convolution_param { num_output: %d '
+            'kernel_size: %s stride: %s pad: %s } }\n' % (cout, lst(k), lst(s), lst(p)))
+    txt += 'layer { name: "c_bn" type: "BN" bottom: "c" top: "c_bn" }\n'
+    txt += 'layer { name: "c_relu" type: "ReLU" bottom: "c_bn" top: "c_bn" }\n'
+    return txt
+
+
+def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True):
+    ref = refnet.RefNet(txt).init_params(seed + 1)
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=shape).astype(np.float32)
+    want = ref.forward(x, bf16=True)
+    net = make_net(txt, keep_all=keep_all, a_mode=a_mode)
+    load_params(net, ref.params_dict())
+    net.blobs["data"].data[...] = x
+    net.forward()
+    got = net.blobs
+    for name in check:
+        g = got[name].data
+        assert g.shape == want[name].shape, (name, g.shape, want[name].shape)
+        # blobs the device keeps as bf16 feature maps equal the oracle's value after one more bf16
+        # rounding (raw conv sums are fp32 in the oracle); plain fp32 blobs compare directly
+        err = min(rel_max(g, want[name]), rel_max(g, refnet.round_bf16(want[name])))
+        assert err <= TOL_OP, describe_mismatch(g, want[name], name)
+    return net, want
+
+
+CONV2D = [
+    # shape, cmid, cout, k, s, p
+    ((2, 16, 12, 12), 64, 64, [1, 1], [1, 1], [0, 0]),      # pure GEMM, K=64, M=288 (ragged last tile)
+    ((2, 16, 12, 12), 64, 32, [3, 3], [1, 1], [1, 1]),      # 3x3 p1
+    ((1, 8, 28, 28), 192, 64, [1, 1], [1, 1], [0, 0]),      # inception_3a_1x1 geometry (3 K blocks)
+    ((2, 8, 14, 14), 96, 96, [3, 3], [1, 1], [1, 1]),       # Cin=96: half-empty second K block (zero fill)
+    ((2, 8, 15, 15), 64, 160, [3, 3], [2, 2], [1, 1]),      # stride 2, odd size, N=160
+    ((1, 8, 9, 9), 64, 352, [1, 1], [1, 1], [0, 0]),        # Cout 352 -> two N tiles of 176
+    ((1, 8, 7, 7), 320, 192, [1, 1], [1, 1], [0, 0]),       # K=320 (5 blocks), N=192
+]
+
+
+@pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
+@pytest.mark.parametrize("case", CONV2D, ids=["c%d" % i for i in range(len(CONV2D))])
+def test_conv2d(gpu, case, a_mode):
+    shape, cmid, cout, k, s, p = case
+    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, a_mode, check=("a_bn", "c", "c_bn"))
+
+
+CONV3D = [
+    ((1, 8, 4, 10, 10), 64, 128, [3, 3, 3], [1, 1, 1], [1, 1, 1]),
+    ((2, 8, 8, 14, 14), 128, 256, [3, 3, 3], [2, 2, 2], [1, 1, 1]),   # res4a_1 geometry (stride 2)
+    ((1, 8, 4, 7, 7), 96, 128, [3, 3, 3], [1, 1, 1], [1, 1, 1]),      # res3a_2n: Cin 96
+    ((3, 8, 2, 7, 7), 256, 512, [3, 3, 3], [1, 1, 1], [1, 1, 1]),     # res5 geometry: M=294, two N tiles
+]
+
+
+@pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
+@pytest.mark.parametrize("case", CONV3D, ids=["d%d" % i for i in range(len(CONV3D))])
+def test_conv3d(gpu, case, a_mode):
+    shape, cmid, cout, k, s, p = case
+    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, a_mode, check=("a_bn", "c", "c_bn"))
+
+
+@pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
+@pytest.mark.parametrize("hw", [(32, 32), (30, 34), (224, 224)])
+def test_stem_7x7_s2(gpu, hw, a_mode):
+    # conv1_7x7_s2 on fp32 NCHW input: space-to-depth transform + 4x1 window conv
+    shape = (2, 3) + hw
+    run_case(conv_net(shape, 64, [7, 7], [2, 2], [3, 3]), shape, a_mode, check=("c", "c_bn"))
+
+
+@pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
+def test_generic_fp32_input_conv(gpu, a_mode):
+    # a first conv that is not the 7x7 stem: channels padded to 8 on the fly
+    shape = (2, 5, 9, 11)
+    run_case(conv_net(shape, 24, [3, 3], [1, 1], [1, 1]), shape, a_mode, check=("c", "c_bn"))
+
+
+def test_conv_without_bn_and_plain_relu(gpu):
+    shape = (1, 8, 6, 6)
+    txt = conv_net(shape, 16, [3, 3], [1, 1], [1, 1], bn=False)
+    run_case(txt, shape, 0, check=("c",))
+    txt2 = txt + 'layer { name: "r" type: "ReLU" bottom: "c" top: "c" }\n'
+    run_case(txt2, shape, 0, check=("c",))
+
+
+RES_NET = """name: "res"
+input: "data" input_shape { dim: 2 dim: 8 dim: 4 dim: 6 dim: 6 }
+layer { name: "s" type: "Convolution" bottom: "data" top: "s" convolution_param { num_output: 64 kernel_size: [1,1,1] } }
+layer { name: "s_bn" type: "BN" bottom: "s" top: "s_bn" }
+layer { name: "s_relu" type: "ReLU" bottom: "s_bn" top: "s_bn" }
+layer { name: "ra_2n" type: "Convolution" bottom: "s_bn" top: "ra" convolution_param { num_output: 64 kernel_size: [3,3,3] pad: [1,1,1] } }
+layer { name: "ra_bn" type: "BN" bottom: "ra" top: "ra_bn" }
+layer { name: "ra_relu" type: "ReLU" bottom: "ra_bn" top: "ra_bn" }
+layer { name: "rb_1" type: "Convolution" bottom: "ra_bn" top: "rb_1" convolution_param { num_output: 64 kernel_size: [3,3,3] pad: [1,1,1] } }
+layer { name: "rb_1_bn" type: "BN" bottom: "rb_1" top: "rb_1_bn" }
+layer { name: "rb_1_relu" type: "ReLU" bottom: "rb_1_bn" top: "rb_1_bn" }
+layer { name: "rb_2" type: "Convolution" bottom: "rb_1_bn" top: "rb_2" convolution_param { num_output: 64 kernel_size: [3,3,3] pad: [1,1,1] } }
+layer { name: "rb" type: "Eltwise" bottom: "rb_2" bottom: "ra" top: "rb" }
+layer { name: "rb_bn" type: "BN" bottom: "rb" top: "rb_bn" }
+layer { name: "rb_relu" type: "ReLU" bottom: "rb_bn" top: "rb_bn" }
+layer { name: "rc_1" type: "Convolution" bottom: "rb_bn" top: "rc_1" convolution_param { num_output: 128 kernel_size: [3,3,3] pad: [1,1,1] stride: [2,2,2] } }
+layer { name: "rc_1_bn" type: "BN" bottom: "rc_1" top: "rc_1_bn" }
+layer { name: "rc_1_relu" type: "ReLU" bottom: "rc_1_bn" top: "rc_1_bn" }
+layer { name: "rc_2" type: "Convolution" bottom: "rc_1_bn" top: "rc_2" convolution_param { num_output: 128 kernel_size: [3,3,3] pad: [1,1,1] } }
+layer { name: "rc_down" type: "Convolution" bottom: "rb_bn" top: "rc_down" convolution_param { num_output: 128 kernel_size: [3,3,3] pad: [1,1,1] stride: [2,2,2] } }
+layer { name: "rc" type: "Eltwise" bottom: "rc_2" bottom: "rc_down" top: "rc" }
+layer { name: "rc_bn" type: "BN" bottom: "rc" top: "rc_bn" }
+layer { name: "rc_relu" type: "ReLU" bottom: "rc_bn" top: "rc_bn" }
+layer { name: "gp" type: "Pooling" bottom: "rc_bn" top: "gp" pooling_param { pool: AVE kernel_size: [2,3,3] stride: [1,1,1] } }
+layer { name: "gp_r" type: "Reshape" bottom: "gp" top: "gp_r" reshape_param { shape { dim: -1 dim: 128 } } }
+layer { name: "drop" type: "Dropout" bottom: "gp_r" top: "gp_r" dropout_param { dropout_ratio: 0.5 } }
+layer { name: "fc" type: "InnerProduct" bottom: "gp_r" top: "fc" inner_product_param { num_output: 10 } }
+"""
+
+
+@pytest.mark.parametrize("keep_all", [True, False])
+@pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
+def test_residual_block_fusion(gpu, a_mode, keep_all):
+    # pre-activation residual structure of the 3-D head: raw sums feed the shortcut,
+    # BN+ReLU after each add; both fused into the conv epilogues.
+    shape = (2, 8, 4, 6, 6)
+    check = ("ra", "ra_bn", "rb_bn", "rc_2", "rc_bn", "gp", "fc") if keep_all else ("fc",)
+    run_case(RES_NET, shape, a_mode, check=check, keep_all=keep_all)
+
+
+INCEPTION = """name: "inc"
+input: "data" input_dim: 2 input_dim: 8 input_dim: 14 input_dim: 14
+layer { name: "stem" type: "Convolution" bottom: "data" top: "stem" convolution_param { num_output: 64 kernel_size: 1 } }
+layer { name: "stem_bn" type: "BN" bottom: "stem" top: "stem_bn" }
+layer { name: "stem_relu" type: "ReLU" bottom: "stem_bn" top: "stem_bn" }
+layer { name: "b1" type: "Convolution" bottom: "stem_bn" top: "b1" convolution_param { num_output: 32 kernel_size: 1 } }
+layer { name: "b1_bn" type: "BN" bottom: "b1" top: "b1_bn" }
+layer { name: "b1_relu" type: "ReLU" bottom: "b1_bn" top: "b1_bn" }
+layer { name: "b2r" type: "Convolution" bottom: "stem_bn" top: "b2r" convolution_param { num_output: 64 kernel_size: 1 } }
+layer { name: "b2r_bn" type: "BN" bottom: "b2r" top: "b2r_bn" }
+layer { name: "b2r_relu" type: "ReLU" bottom: "b2r_bn" top: "b2r_bn" }
+layer { name: "b2" type: "Convolution" bottom: "b2r_bn" top: "b2" convolution_param { num_output: 96 kernel_size: 3 pad: 1 } }
+layer { name: "b2_bn" type: "BN" bottom: "b2" top: "b2_bn" }
+layer { name: "b2_relu" type: "ReLU" bottom: "b2_bn" top: "b2_bn" }
+layer { name: "pl" type: "Pooling" bottom: "stem_bn" top: "pl" pooling_param { pool: AVE kernel_size: 3 stride: 1 pad: 1 } }
+layer { name: "pp" type: "Convolution" bottom: "pl" top: "pp" convolution_param { num_output: 32 kernel_size: 1 } }
+layer { name: "pp_bn" type: "BN" bottom: "pp" top: "pp_bn" }
+layer { name: "pp_relu" type: "ReLU" bottom: "pp_bn" top: "pp_bn" }
+layer { name: "mp" type: "Pooling" bottom: "stem_bn" top: "mp" pooling_param { pool: MAX kernel_size: 3 stride: 1 pad: 1 } }
+layer { name: "out" type: "Concat" bottom: "b1_bn" bottom: "b2_bn" bottom: "pp_bn" bottom: "mp" top: "out" }
+layer { name: "down" type: "Pooling" bottom: "out" top: "down" pooling_param { pool: MAX kernel_size: 3 stride: 2 } }
+layer { name: "nx" type: "Convolution" bottom: "down" top: "nx" convolution_param { num_output: 64 kernel_size: 1 } }
+layer { name: "nx_bn" type: "BN" bottom: "nx" top: "nx_bn" }
+"""
+
+
+@pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
+def test_inception_block_concat_alias(gpu, a_mode):
+    # concat is zero-copy: branch epilogues / pools write channel slices of `out`
+    run_case(INCEPTION, (2, 8, 14, 14), a_mode, check=("b1_bn", "b2_bn", "pl", "pp_bn", "mp", "out", "down", "nx_bn"))
+
+
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_known_answers.json")))
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_pooling_reference_known_answers_on_device(gpu, case):
+    # the reference's golden pooling vectors through the channels-last device kernel:
+    # an identity 1x1 conv lifts the fp32 input into a bf16 channels-last blob (small integers are exact)
+    nsp = len(case["in_shape"])
+    shape = [2, 8] + case["in_shape"]
+    lst = lambda v: "[%s]" % ", ".join(str(i) for i in v)
+    txt = 'name: "p"\ninput: "data"\ninput_shape { %s }\n' % " ".join("dim: %d" % d for d in shape)
+    txt += 'layer { name: "id" type: "Convolution" bottom: "data" top: "id" convolution_param { num_output: 8 kernel_size: %s bias_term: false } }\n' % lst([1] * nsp)
+    txt += ('layer { name: "pool" type: "Pooling" bottom: "id" top: "pool" pooling_param { pool: %s kernel_size: %s '
+            'stride: %s pad: %s } }\n' % (case["method"], lst(case["kernel"]), lst(case["stride"]), lst(case["pad"])))
+    net = make_net(txt, keep_all=True, a_mode=0)
+    net.params["id"][0].data[...] = np.eye(8, dtype=np.float32).reshape([8, 8] + [1] * nsp)
+    x1 = np.array(case["input"], np.float32).reshape(case["in_shape"])
+    net.blobs["data"].data[...] = np.broadcast_to(x1, shape)
+    net.forward()
+    got = net.blobs["pool"].data
+    assert list(got.shape) == [2, 8] + case["out_shape"]
+    exp = np.array(case["output"], np.float32).reshape(case["out_shape"])
+    tol = max(case["tol"], 8e-3 * np.abs(exp).max())  # bf16 storage of the averaged values (rel 2^-9)
+    if case["method"] == "MAX":
+        tol = case["tol"]
+    assert np.abs(got - exp).max() <= tol + 1e-12
