@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- ECO-Lite N=16 forward videos/s (BASELINE.json metric) on N GPUs of one node.
+
+  python bench.py --gpus 1 --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
+  python bench.py --impl reference --steps K --warmup W    # the reference arm: CPU implementation of the path
+
+A step = one forward of the hot path over one batch of synthetic clips (uint8 frames, seed 1234,
+minus the BGR mean) per GPU.  Videos are independent in TEST phase, so the batch is
+sharded across ranks with no data-path collective ("scaling": "weak").
+  value   : videos/s with the batch already resident in HBM (fp32, caffe layout) when the timed region starts
+  e2e     : the same through the reference-facing call with HOST buffers: the batch sits in the input blob's
+            host memory (where caffe's data layer writes it), forward() uploads it, the fc8 logits are read
+            back to the host -- all inside the timed region
+  roofline: all launches of the implicit-GEMM conv kernel (the dominant kernel): algorithmic FLOPs
+            (2*M*N*K per conv, SURVEY.md 8(d): 92.97 GFLOP/video) / their summed CUDA-event time
+  cpu_baseline: the oracle (a port of caffe_3d's CPU algorithm: per-image im2col + SGEMM + separate
+            BN/ReLU/pool passes) on this box's host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "eco-efficient-video-understanding_b200"),
+          os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+GFLOP_PER_VIDEO = {("lite", 16): 92.97, ("full", 16): 128.83}
+CLASSES = 101
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(tflops=d.get("bf16_tflops_sustained", d.get("bf16_tflops")), hbm=d.get("hbm_gbs"), src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0]
+        return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_forward(model, segments, steps, warmup, threads=None):
+    """The reference arm / cpu_baseline: oracle fp32 forward (caffe_3d's CPU algorithm), one clip per step."""
+    import gen_eco_prototxt as gen
+    from oracle import refnet
+    if threads:
+        refnet.lib().ref_set_num_threads(int(threads))
+    cores = int(refnet.lib().ref_num_threads())
+    txt = (gen.eco_full_deploy if model == "full" else gen.eco_lite_deploy)(segments=segments, batch=1)
+    net = refnet.RefNet(txt).init_params(4321)
+    x = refnet.eco_input(1, segments)
+    for _ in range(warmup):
+        net.forward(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        net.forward(x)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="lite", choices=["lite", "full"])
+    ap.add_argument("--segments", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=32, help="videos per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = "ECO-%s N=%d forward, %d classes, batch %d videos/GPU, synthetic 224x224x3 frames" % (
+        "Lite" if a.model == "lite" else "Full", a.segments, CLASSES if a.model == "lite" else 400, a.batch)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(a.steps, 10))
+        vps, ms, cores = cpu_reference_forward(a.model, a.segments, steps, min(a.warmup, 1))
+        line = {"impl": "reference", "metric": "ECO-Lite-16 forward videos/sec", "value": vps, "unit": "videos/s",
+                "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 1), "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "note": "reference CPU algorithm (oracle port of caffe_3d), 1 clip per step"},
+                "cpu_baseline": {"value": vps, "unit": "videos/s", "cores": cores, "kind": "port",
+                                 "sample": "%d single-clip N=%d forwards" % (steps, a.segments)},
+                "e2e": {"value": vps, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import caffe
+    import gen_eco_prototxt as gen
+    from oracle import refnet
+    from eco_testlib import load_params
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    caffe.set_device(local_rank)
+    caffe.set_mode_gpu()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+
+    B, N = a.batch, a.segments
+    classes = CLASSES if a.model == "lite" else 400
+    txt = (gen.eco_full_deploy if a.model == "full" else gen.eco_lite_deploy)(segments=N, classes=classes, batch=B)
+    net = caffe.Net.from_string(txt, caffe.TEST, keep_all_blobs=0, use_graph=0 if a.no_graph else 1)
+    # harness weights (random init of the right architecture; values do not affect timing)
+    ref = refnet.RefNet((gen.eco_full_deploy if a.model == "full" else gen.eco_lite_deploy)(segments=4, classes=classes, batch=1))
+    ref.init_params(4321)
+    load_params(net, ref.params_dict())
+    stream = torch.cuda.current_stream()
+    net.set_stream(stream.cuda_stream)
+
+    # synthetic frames: uint8 U{0..255} seed 1234 (+rank), minus BGR mean, fp32 NCHW as the data layer hands over
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234 + rank)
+    frames = torch.randint(0, 256, (B * N, 3, 224, 224), generator=g, device="cuda", dtype=torch.uint8).float()
+    frames -= torch.tensor([104.0, 117.0, 123.0], device="cuda").view(1, 3, 1, 1)
+    count = frames.numel()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: inputs resident in HBM ----------------
+    net.set_input_device("data", frames.data_ptr(), count)
+    for _ in range(max(a.warmup, 3)):
+        net._forward(0, len(net.layers) - 1)
+    net.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        net._forward(0, len(net.layers) - 1)
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.finish()
+    net.sync()
+    launches = net.last_launch_count() * a.steps
+    ms_step = ms_total / a.steps
+    value = world * B * a.steps / (ms_total / 1e3)
+
+    # ---------------- e2e: host buffers in, logits out, copies inside the timed region ----------------
+    host_in = net.blobs["data"].data  # pinned host mirror of the input blob (what caffe's data layer fills)
+    host_in[...] = frames.cpu().numpy()
+    for _ in range(2):
+        net.blobs["data"].data
+        net._forward(0, len(net.layers) - 1)
+        _ = net.blobs["fc8"].data
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(a.steps):
+        net.blobs["data"].data            # mutable_cpu_data(): marks the host copy newer -> forward uploads it
+        net._forward(0, len(net.layers) - 1)
+        logits = net.blobs["fc8"].data    # device -> host read of the step's result (syncs)
+    e1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_value = world * B * a.steps / (max(e2e_ms, wall_ms) / 1e3)
+    assert np.isfinite(logits).all()
+
+    # ---------------- roofline: the conv kernel, CUDA events per launch on the launching stream ----------------
+    net.set_input_device("data", frames.data_ptr(), count)
+    conv_ms, conv_flops, conv_n, other_ms = 0.0, 0.0, 0, 0.0
+    prof_iters = 3
+    for _ in range(prof_iters):
+        for op in net.profile_forward():
+            if op["kind"] == 0:
+                conv_ms += op["ms"]
+                conv_flops += op["flops"]
+                conv_n += 1
+            else:
+                other_ms += op["ms"]
+    pk = peaks()
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (all %d launches/step)" % (conv_n // prof_iters),
+                "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                "peak_source": pk["src"], "traffic": None,
+                "conv_ms_per_step": conv_ms / prof_iters, "other_ms_per_step": other_ms / prof_iters,
+                "share_of_step": conv_ms / max(conv_ms + other_ms, 1e-9)}
+
+    if rank != 0:
+        return
+    cpu_baseline = None
+    if not a.no_cpu_baseline and world == 1:
+        vps, ms, cores = cpu_reference_forward(a.model, N, steps=3, warmup=1)
+        cpu_baseline = {"value": vps, "unit": "videos/s", "cores": cores, "kind": "port",
+                        "sample": "3 single-clip N=%d fp32 forwards of the oracle (caffe_3d CPU algorithm)" % N}
+    line = {"metric": "ECO-Lite-16 forward videos/sec" if a.model == "lite" else "ECO-Full-16 forward videos/sec",
+            "value": value, "unit": "videos/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload, "global_batch": B * world, "parallelism": "batch-sharded x%d, no collective" % world,
+                       "l2": "inputs (%.0f MB/GPU) and activations exceed the 126 MB L2" % (count * 4 / 1e6),
+                       "cuda_graph": not a.no_graph},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "videos/s", "h2d_bytes_per_step": int(count * 4),
+                    "d2h_bytes_per_step": int(B * classes * 4), "ms_per_step": max(e2e_ms, wall_ms) / a.steps},
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gflop_per_video": GFLOP_PER_VIDEO.get((a.model, N))}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1500,6 +1500,9 @@ float* Net::host_data(int vb, bool for_write, size_t* count) {
   ECO_CHECK(vb >= 0 && vb < (int)vis_blobs_.size(), "blob index out of range");
   Tensor& t = tensors_[vis_blobs_[vb].tensor];
   const size_t n = (size_t)t.count();
+  ECO_CHECK(!planned_ || t.materialized,
+            "blob '" << t.name << "' is fused away in the current plan and has no data; create the net with option "
+                        "keep_all_blobs=1 to materialise every blob");
   if (t.dev_newer && planned_) download(t);
   if (t.host.n != n) t.host.resize(n, true);
   if (for_write) t.host_newer = true;

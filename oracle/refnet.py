@@ -339,16 +339,26 @@ class RefNet:
         return self
 
     # ---- forward ---------------------------------------------------------------
-    def forward(self, inputs, bf16=False, keep=None):
+    def forward(self, inputs, bf16=False, keep=None, teacher=None):
         """inputs: array for the single net input or {name: array}.  Returns {blob: array}
-        for every blob (in-place layers overwrite, as in caffe)."""
+        for every blob (in-place layers overwrite, as in caffe).
+
+        teacher: optional {blob: array} (e.g. the device's blobs).  After the last layer that
+        writes a blob, the oracle's own value is recorded in the result and the teacher's value is
+        substituted for all later consumers, so every layer is checked on the inputs the device
+        actually saw (no error amplification through the depth of the net)."""
         if not isinstance(inputs, dict):
             inputs = {self.inputs[0]: inputs}
-        return self._walk(inputs, bf16=bf16)
+        return self._walk(inputs, bf16=bf16, teacher=teacher)
 
-    def _walk(self, inputs, shapes_only=False, out_param_shapes=None, bf16=False, bn_hook=None):
+    def _walk(self, inputs, shapes_only=False, out_param_shapes=None, bf16=False, bn_hook=None, teacher=None):
         blobs = {}
         shp = {}
+        own = {}
+        last_writer = {}
+        for li, l in enumerate(self.layers):
+            for top in l.tops:
+                last_writer[top] = li
         R = round_bf16 if bf16 else (lambda a: a)
         if shapes_only:
             for n in self.inputs:
@@ -511,8 +521,16 @@ class RefNet:
                 raise NotImplementedError("oracle: layer type %s (%s)" % (t, l.name))
             for top in l.tops:
                 produced_order[top] = li
+                if teacher is not None and not shapes_only and last_writer[top] == li and top in blobs:
+                    own[top] = blobs[top]
+                    if top in teacher:
+                        blobs[top] = _f32(teacher[top]).reshape(blobs[top].shape)
         self.shapes = shp
         self.blobs = blobs
+        if teacher is not None and not shapes_only:
+            for k, v in blobs.items():
+                own.setdefault(k, v)
+            return own
         return blobs
 
 

@@ -9,8 +9,15 @@ DESIGN.md "Rounding contract") a blob must satisfy
 """
 import numpy as np
 
-TOL_OP = 1e-3
-TOL_NET = 2e-3
+TOL_OP = 1e-3     # fp32 blobs (fc, pooled vectors): max|a-b| <= TOL_OP * max|b|
+FLIP_FRAC = 0.03  # bf16 blobs: at most this fraction of elements may sit on the neighbouring bf16 value
+ATOL_REL = 1e-4   # bf16 blobs: fp32 accumulation-order noise near zero, relative to max|b|
+TOL_NET = 4e-2    # free-running whole net, per-blob rel-L2.  Calibrated on the oracle itself: its bf16-mirror
+                  # forward with a different fp32 summation order (naive conv vs im2col+SGEMM) already differs
+                  # from itself by rel-L2 4e-4 (inception_3a) .. 1.6e-2 (res5b_bn), 4.4e-3 on fc8, because
+                  # rounding-boundary flips of the bf16-stored maps are amplified through 32 conv layers
+                  # (DESIGN.md section 4).  The tight statement is the teacher-forced per-layer check.
+TOL_LOGITS = 2e-2 # free-running whole net, logits max|a-b| / max|b| (oracle self-noise: 4.2e-3)
 
 
 def make_net(text, keep_all=True, a_mode=None, graph=False):
@@ -38,6 +45,42 @@ def rel_max(a, b):
 
 def rel_l2(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))
+
+
+def bf16_ulp(v):
+    """spacing of bfloat16 (8 significant bits) at |v|"""
+    a = np.maximum(np.abs(v.astype(np.float64)), 2.0 ** -120)
+    return 2.0 ** (np.floor(np.log2(a)) - 7)
+
+
+def check_bf16_blob(got, want, name=""):
+    """Parity criterion for a blob the device stores as bf16: equal to the oracle's value rounded to
+    bf16, except that an element may land on the adjacent bf16 value when the two fp32 sums (different
+    summation order) straddle a rounding boundary.  Elementwise |d| <= 1 ulp + noise, few flips."""
+    from oracle import refnet
+    wr = refnet.round_bf16(want).astype(np.float64)
+    d = np.abs(got.astype(np.float64) - wr)
+    atol = ATOL_REL * max(np.abs(wr).max(), 1e-30)
+    lim = 1.001 * bf16_ulp(wr) + atol
+    ok = d <= lim
+    flips = float((d > atol).mean())
+    assert ok.all(), "%s: %d elements differ by more than one bf16 ulp; %s" % (name, (~ok).sum(), describe_mismatch(got, want, name))
+    assert flips <= FLIP_FRAC, "%s: %.4f of the elements differ from the oracle (limit %.2f)" % (name, flips, FLIP_FRAC)
+    return flips
+
+
+def teacher_blobs(ref, dev):
+    """Device blobs the oracle may consume in a teacher-forced forward: everything except raw conv /
+    eltwise sums, which the device's fused BN reads from the fp32 accumulator, not from the bf16 copy."""
+    raw = set()
+    for l in ref.layers:
+        if l.type in ("Convolution", "Eltwise"):
+            raw.update(l.tops)
+    return {k: v for k, v in dev.items() if k not in raw}
+
+
+def check_f32_blob(got, want, name=""):
+    assert rel_max(got, want) <= TOL_OP, describe_mismatch(got, want, name)
 
 
 def describe_mismatch(a, b, name=""):

@@ -6,11 +6,14 @@ import pytest
 
 from oracle import refnet
 import gen_eco_prototxt as gen
-from eco_testlib import TOL_NET, TOL_OP, describe_mismatch, load_params, make_net, rel_l2, rel_max
+from eco_testlib import (TOL_LOGITS, TOL_NET, check_bf16_blob, check_f32_blob, describe_mismatch, load_params,
+                         make_net, rel_l2, rel_max, teacher_blobs)
 
 pytestmark = pytest.mark.gpu
 
 # blobs whose conv output is consumed by a fused residual add: never stored
+PLAIN_LITE = {"global_pool", "global_pool_reshape", "fc8", "global_pool2D", "reshape_fc_st2", "pool_fusion_st2",
+              "pool_fusion_st2D", "global_pool_gn02_reshape"}
 FUSED_AWAY = {"res3b_2", "res4a_down", "res4b_2", "res5a_down", "res5b_2"}
 
 
@@ -33,18 +36,29 @@ def test_eco_lite_n4_every_blob(gpu, a_mode):
     out = net.forward()
     assert list(out.keys()) == ["fc8"]
     blobs = net.blobs
-    worst = ("", 0.0)
-    for name, w in want.items():
-        if name in FUSED_AWAY or name not in blobs:
+    dev = {name: blobs[name].data.copy() for name in want if name not in FUSED_AWAY and name in blobs}
+    # (1) teacher-forced: every blob of deploy.prototxt, each layer fed the device's own inputs
+    forced = ref.forward(x, bf16=True, teacher=teacher_blobs(ref, dev))
+    worst_flip = ("", 0.0)
+    for name, g in dev.items():
+        assert g.shape == want[name].shape, (name, g.shape, want[name].shape)
+        if name in ("data",):
             continue
-        g = blobs[name].data
-        assert g.shape == w.shape, (name, g.shape, w.shape)
-        e = min(rel_l2(g, w), rel_l2(g, refnet.round_bf16(w)))
+        if name in PLAIN_LITE:
+            check_f32_blob(g, forced[name], name)
+        else:
+            f = check_bf16_blob(g, forced[name], name)
+            if f > worst_flip[1]:
+                worst_flip = (name, f)
+    # (2) free-running: error growth through the whole net stays within the calibrated band
+    worst = ("", 0.0)
+    for name, g in dev.items():
+        e = min(rel_l2(g, want[name]), rel_l2(g, refnet.round_bf16(want[name])))
         if e > worst[1]:
             worst = (name, e)
-        assert e <= TOL_NET, describe_mismatch(g, w, name)
-    print("worst blob", worst)
-    assert rel_max(out["fc8"], want["fc8"]) <= 5 * TOL_OP, describe_mismatch(out["fc8"], want["fc8"], "fc8")
+        assert e <= TOL_NET, describe_mismatch(g, want[name], name)
+    print("worst flip fraction", worst_flip, "worst free-running rel_l2", worst)
+    assert rel_max(out["fc8"], want["fc8"]) <= TOL_LOGITS, describe_mismatch(out["fc8"], want["fc8"], "fc8")
 
 
 @pytest.mark.parametrize("graph", [False, True], ids=["eager", "cudagraph"])
@@ -57,7 +71,7 @@ def test_eco_lite_n4_fast_plan_matches(gpu, graph):
     for _ in range(3):
         net.blobs["data"].data[...] = x
         got = net.forward()["fc8"].copy()
-        assert rel_max(got, want) <= 5 * TOL_OP, describe_mismatch(got, want, "fc8")
+        assert rel_max(got, want) <= TOL_LOGITS, describe_mismatch(got, want, "fc8")
     with pytest.raises(RuntimeError):
         net.blobs["conv1_7x7_s2"].data  # fused away in the fast plan: loud, not stale
 
@@ -69,10 +83,17 @@ def test_eco_full_n4(gpu):
     load_params(net, ref.params_dict())
     net.blobs["data"].data[...] = x
     out = net.forward()
+    blobs = net.blobs
+    dev = {name: blobs[name].data.copy() for name in want if name not in FUSED_AWAY and name in blobs and name != "data"}
+    forced = ref.forward(x, bf16=True, teacher=teacher_blobs(ref, dev))
+    for name, g in dev.items():
+        if name in PLAIN_LITE:
+            check_f32_blob(g, forced[name], name)
+        else:
+            check_bf16_blob(g, forced[name], name)
     for name in ("inception_3c_output", "inception_4e_output", "inception_5b_output", "global_pool2D",
                  "pool_fusion_st2D", "global_pool", "global_pool_gn02_reshape", "fc8"):
-        g = net.blobs[name].data
-        w = want[name]
+        g, w = dev[name], want[name]
         e = min(rel_l2(g, w), rel_l2(g, refnet.round_bf16(w)))
         assert e <= TOL_NET, describe_mismatch(g, w, name)
     assert out["fc8"].shape == (2, 400)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import refnet
-from eco_testlib import TOL_OP, describe_mismatch, load_params, make_net, rel_max
+from eco_testlib import check_bf16_blob, check_f32_blob, load_params, make_net, teacher_blobs
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -45,6 +45,9 @@ def two_conv_net(shape, cmid, cout, k, s, p):
     return txt
 
 
+PLAIN = {"gp", "gp_r", "fc"}  # blobs that are plain fp32 on the device
+
+
 def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True):
     ref = refnet.RefNet(txt).init_params(seed + 1)
     rng = np.random.default_rng(seed)
@@ -55,13 +58,17 @@ def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True):
     net.blobs["data"].data[...] = x
     net.forward()
     got = net.blobs
+    dev = {name: got[name].data.copy() for name in check}
+    # teacher forcing: every checked blob is recomputed by the oracle from the device's own upstream
+    # blobs, so each fused op is judged on identical inputs
+    forced = ref.forward(x, bf16=True, teacher=teacher_blobs(ref, dev))
     for name in check:
-        g = got[name].data
+        g = dev[name]
         assert g.shape == want[name].shape, (name, g.shape, want[name].shape)
-        # blobs the device keeps as bf16 feature maps equal the oracle's value after one more bf16
-        # rounding (raw conv sums are fp32 in the oracle); plain fp32 blobs compare directly
-        err = min(rel_max(g, want[name]), rel_max(g, refnet.round_bf16(want[name])))
-        assert err <= TOL_OP, describe_mismatch(g, want[name], name)
+        if name in PLAIN:
+            check_f32_blob(g, forced[name], name)
+        else:
+            check_bf16_blob(g, forced[name], name)
     return net, want
 
 
