@@ -172,7 +172,7 @@ def main():
     ref = refnet.RefNet((gen.eco_full_deploy if a.model == "full" else gen.eco_lite_deploy)(segments=4, classes=classes, batch=1))
     ref.init_params(4321)
     load_params(net, ref.params_dict())
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-legacy) stream: the events below are recorded on it
     net.set_stream(stream.cuda_stream)
 
     # synthetic frames: uint8 U{0..255} seed 1234 (+rank), minus BGR mean, fp32 NCHW as the data layer hands over
@@ -181,6 +181,7 @@ def main():
     frames = torch.randint(0, 256, (B * N, 3, 224, 224), generator=g, device="cuda", dtype=torch.uint8).float()
     frames -= torch.tensor([104.0, 117.0, 123.0], device="cuda").view(1, 3, 1, 1)
     count = frames.numel()
+    torch.cuda.synchronize()
 
     def barrier():
         torch.cuda.synchronize()

@@ -88,17 +88,18 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // MAX: window [o*s-p, min(start+k, in)) then start=max(start,0), init -FLT_MAX  (pooling_layer.cpp:199-224)
 // AVE: divisor = prod(min(start+k, in+p) - start) before clipping to the image      (pooling_layer.cpp:247-262)
-__global__ void pool_cl_kernel(const PoolParams p) {
-  const int cg = p.C / 8;
-  const long long total = (long long)p.NB * p.OD * p.OH * p.OW * cg;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % cg);
-    long long r = t / cg;
-    const int ox = (int)(r % p.OW); r /= p.OW;
-    const int oy = (int)(r % p.OH); r /= p.OH;
-    const int oz = (int)(r % p.OD);
-    const long long n = r / p.OD;
+// One thread = one output pixel x 8 channels (16 B); 32-bit index math (the host checks the range).
+__global__ void __launch_bounds__(256) pool_cl_kernel(const PoolParams p) {
+  const int cg = p.C >> 3;
+  const unsigned total = (unsigned)p.NB * p.OD * p.OH * p.OW * cg;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const unsigned pix = t / (unsigned)cg;
+    const int g = (int)(t - pix * cg);
+    unsigned r = pix;
+    const int ox = (int)(r % (unsigned)p.OW); r /= (unsigned)p.OW;
+    const int oy = (int)(r % (unsigned)p.OH); r /= (unsigned)p.OH;
+    const int oz = (int)(r % (unsigned)p.OD);
+    const int n = (int)(r / (unsigned)p.OD);
     int z0 = oz * p.sD - p.pD, y0 = oy * p.sH - p.pH, x0 = ox * p.sW - p.pW;
     int z1, y1, x1;
     float div = 1.f;
@@ -113,11 +114,12 @@ __global__ void pool_cl_kernel(const PoolParams p) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = p.is_max ? -FLT_MAX : 0.f;
+    const __nv_bfloat16* base = p.x + p.x_coff + g * 8;
     for (int z = z0; z < z1; ++z)
-      for (int y = y0; y < y1; ++y)
+      for (int y = y0; y < y1; ++y) {
+        const long long rowpix = ((long long)(n * p.ID + z) * p.IH + y) * p.IW;
         for (int x = x0; x < x1; ++x) {
-          const long long pix = ((n * p.ID + z) * p.IH + y) * p.IW + x;
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.x + pix * p.x_cs + p.x_coff + g * 8));
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (rowpix + x) * p.x_cs));
           float f[8];
           unpack8(v, f);
           if (p.is_max) {
@@ -128,12 +130,13 @@ __global__ void pool_cl_kernel(const PoolParams p) {
             for (int j = 0; j < 8; ++j) acc[j] += f[j];
           }
         }
+      }
     if (!p.is_max) {
+      // true division like pooling_layer.cpp:262 (x * (1/d) is not bit-identical in general)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] /= div;
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] / div;
     }
-    const long long opix = ((n * p.OD + oz) * p.OH + oy) * p.OW + ox;
-    *reinterpret_cast<uint4*>(p.y + opix * p.y_cs + p.y_coff + g * 8) = pack8(acc);
+    *reinterpret_cast<uint4*>(p.y + (long long)pix * p.y_cs + p.y_coff + g * 8) = pack8(acc);
   }
 }
 
@@ -266,7 +269,9 @@ cudaError_t launch_stem_s2d(const float* src, __nv_bfloat16* dst, int F, int H, 
 cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {
   const long long n = (long long)p.NB * p.OD * p.OH * p.OW * (p.C / 8);
   if (n == 0) return cudaSuccess;
-  pool_cl_kernel<<<grid_cap(n), kThreads, 0, st>>>(p);
+  if (n >= (1LL << 31)) return cudaErrorInvalidValue;  // 32-bit index math in the kernel
+  const long long blocks = (n + kThreads - 1) / kThreads;
+  pool_cl_kernel<<<(unsigned)(blocks > 148LL * 64 ? 148LL * 64 : blocks), kThreads, 0, st>>>(p);
   return cudaGetLastError();
 }
 cudaError_t launch_global_avg_cl(ClView src, float* dst, cudaStream_t st) {

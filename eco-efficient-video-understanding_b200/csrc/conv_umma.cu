@@ -161,6 +161,38 @@ __device__ __forceinline__ void load16_bf16_add(const __nv_bfloat16* src, float 
   }
 }
 
+// One epilogue warp's share of a tile: TMEM lane = output position `m`, columns = output channels.
+//   raw = acc + bias (+ residual) -> optional bf16 store ; y = relu?(raw*scale + shift) -> bf16 store
+__device__ __forceinline__ void epilogue_rows(const ConvKernelParams& p, uint32_t taddr, int m, bool row_ok, int n0,
+                                              int BN, const float* s_bias, const float* s_scale,
+                                              const float* s_shift) {
+  const bool has_scale = p.scale != nullptr;
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(taddr + (uint32_t)c0, v);
+    const int cg = n0 + c0;
+    const int nvalid = p.Cout - cg;
+    if (row_ok && nvalid > 0) {
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+      if (p.res) load16_bf16_add(p.res + (long long)m * p.res_cs + p.res_coff + cg, f, nvalid);
+      if (p.raw) store16_bf16(p.raw + (long long)m * p.raw_cs + p.raw_coff + cg, f, nvalid);
+      if (p.out) {
+        if (has_scale) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaf(f[j], s_scale[c0 + j], s_shift[c0 + j]);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        store16_bf16(p.out + (long long)m * p.out_cs + p.out_coff + cg, f, nvalid);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmB) {
@@ -322,30 +354,166 @@ conv_umma_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap t
     // ---------------- epilogue ----------------
     mbar_wait(bar_tmem_full, 0, p.error_flag, 4);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
-    const bool has_scale = p.scale != nullptr;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + (uint32_t)c0, v);
-      const int cg = n0 + c0;
-      const int nvalid = p.Cout - cg;
-      if (row_ok && nvalid > 0) {
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
-        if (p.res) load16_bf16_add(p.res + (long long)m * p.res_cs + p.res_coff + cg, f, nvalid);
-        if (p.raw) store16_bf16(p.raw + (long long)m * p.raw_cs + p.raw_coff + cg, f, nvalid);
-        if (p.out) {
-          if (has_scale) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaf(f[j], s_scale[c0 + j], s_shift[c0 + j]);
+    epilogue_rows(p, tmem_base + ((uint32_t)(wq * 32) << 16), m, row_ok, n0, BN, s_bias, s_scale, s_shift);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant (A via TMA im2col only): one CTA per SM walks the tile list; the TMEM
+// accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1, and the
+// smem ring keeps streaming across tile boundaries.
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap tmA,
+                            const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const int S = p.stages;
+  const int BN = p.block_n;
+  const uint32_t a_stage_bytes = kBlockM * 128;
+  const uint32_t b_stage_bytes = (uint32_t)BN * 128;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + S * a_stage_bytes;
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)S * a_stage_bytes + (size_t)S * b_stage_bytes);
+  float* s_scale = s_bias + 256;
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  const uint32_t bar_full = smem_u32(bars);              // [S]
+  const uint32_t bar_empty = bar_full + 8 * S;           // [S]
+  const uint32_t bar_tmem_full = bar_empty + 8 * S;      // [2]
+  const uint32_t bar_tmem_empty = bar_tmem_full + 16;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles_n = (p.Cout + BN - 1) / BN;
+  const int n_tiles_m = (p.M + kBlockM - 1) / kBlockM;
+  const int total_tiles = n_tiles_n * n_tiles_m;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tmem_full + 8 * b, 1);
+      mbar_init(bar_tmem_empty + 8 * b, 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_kb = p.num_kb;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t tx_bytes = b_stage_bytes + a_stage_bytes;
+      uint32_t it = 0;  // running K-block counter across tiles
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n0 = (t % n_tiles_n) * BN;
+        int r = (t / n_tiles_n) * kBlockM;
+        const int q = r % p.OW; r /= p.OW;
+        const int pp = r % p.OH; r /= p.OH;
+        const int z = r % p.OD;
+        const int n = r / p.OD;
+        const int cw = q * p.sW - p.pW, chh = pp * p.sH - p.pH, cd = z * p.sD - p.pD;
+        int cb = 0, kx = 0, ky = 0, kz = 0;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)S;
+          const uint32_t ph = (it / (uint32_t)S) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
+          tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
+          if (p.nsp == 3)
+            tma_im2col_5d(sA + s * a_stage_bytes, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, cd, n,
+                          (uint16_t)kx, (uint16_t)ky, (uint16_t)kz);
+          else
+            tma_im2col_4d(sA + s * a_stage_bytes, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, n,
+                          (uint16_t)kx, (uint16_t)ky);
+          if (++cb == p.cblocks) {
+            cb = 0;
+            if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++kz; } }
           }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          store16_bf16(p.out + (long long)m * p.out_cs + p.out_coff + cg, f, nvalid);
         }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      uint32_t it = 0, tile_iter = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+        const uint32_t buf = tile_iter & 1u;
+        const uint32_t use = tile_iter >> 1;
+        mbar_wait(bar_tmem_empty + 8 * buf, (use & 1u) ^ 1u, p.error_flag, 5);  // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * (uint32_t)BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)S;
+          const uint32_t ph = (it / (uint32_t)S) & 1u;
+          mbar_wait(bar_full + 8 * s, ph, p.error_flag, 2);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_desc(sA + s * a_stage_bytes);
+          const uint64_t bdesc = make_sw128_desc(sB + s * b_stage_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tmem_full + 8 * buf);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    uint32_t tile_iter = 0;
+    int loaded_n0 = -1;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+      const int n0 = (t % n_tiles_n) * BN;
+      const int m0 = (t / n_tiles_n) * kBlockM;
+      if (n0 != loaded_n0) {  // uniform across the four epilogue warps
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+          const int c = n0 + i;
+          const bool ok = c < p.Cout;
+          s_bias[i] = (ok && p.bias) ? p.bias[c] : 0.f;
+          s_scale[i] = (ok && p.scale) ? p.scale[c] : 1.f;
+          s_shift[i] = (ok && p.scale) ? p.shift[c] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        loaded_n0 = n0;
+      }
+      const uint32_t buf = tile_iter & 1u;
+      const uint32_t use = tile_iter >> 1;
+      mbar_wait(bar_tmem_full + 8 * buf, use & 1u, p.error_flag, 4);
+      tc_fence_after();
+      const int m = m0 + row;
+      epilogue_rows(p, tmem_base + ((uint32_t)(wq * 32) << 16) + buf * (uint32_t)BN, m, m < p.M, n0, BN, s_bias,
+                    s_scale, s_shift);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tmem_empty + 8 * buf) : "memory");
       }
     }
   }
@@ -361,13 +529,21 @@ conv_umma_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap t
 }  // namespace
 
 cudaError_t conv_umma_configure() {
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 cudaError_t launch_conv_umma(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                              cudaStream_t stream) {
-  dim3 grid((p.M + kBlockM - 1) / kBlockM, (p.Cout + p.block_n - 1) / p.block_n, 1);
   const size_t smem = conv_smem_bytes(p.block_n, p.stages);
+  if (p.persistent) {
+    const int tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.Cout + p.block_n - 1) / p.block_n);
+    const int grid = tiles < p.num_sms ? tiles : p.num_sms;
+    conv_umma_persistent_kernel<<<grid, kConvThreads, smem, stream>>>(p, tmA, tmB);
+    return cudaGetLastError();
+  }
+  dim3 grid((p.M + kBlockM - 1) / kBlockM, (p.Cout + p.block_n - 1) / p.block_n, 1);
   conv_umma_kernel<<<grid, kConvThreads, smem, stream>>>(p, tmA, tmB);
   return cudaGetLastError();
 }

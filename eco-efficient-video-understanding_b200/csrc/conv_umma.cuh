@@ -42,7 +42,9 @@ struct ConvKernelParams {
   // ---- tile shape ----
   int block_n;                       // multiple of 16, <= 256
   int stages;
-  int tmem_cols;                     // power of two >= block_n, >= 32
+  int tmem_cols;                     // power of two >= block_n (x2 when persistent: double-buffered accumulator)
+  int persistent;                    // 1: conv_umma_persistent_kernel (needs a_mode == A_TMA_IM2COL)
+  int num_sms;
   // ---- epilogue:  raw = acc + bias (+ res);  y = relu?(raw * scale + shift) ----
   int Cout;
   const float* bias;                 // [Cout] or null

@@ -46,6 +46,7 @@ namespace eco {
   } while (0)
 
 static int g_device_ok = -1;  // -1 unknown, 0 none, 1 ok
+static int g_num_sms = 148;
 static bool device_available() {
   if (g_device_ok < 0) {
     int n = 0;
@@ -523,14 +524,16 @@ void Net::set_option(const std::string& key, int v) {
   if (key == "keep_all_blobs") keep_all_ = v != 0;
   else if (key == "a_mode") a_mode_ = v;
   else if (key == "use_graph") use_graph_ = v != 0;
+  else if (key == "persistent") persistent_ = v != 0;
   else ECO_CHECK(false, "unknown option '" << key << "'");
   free_plan();
 }
 
 void Net::set_stream(cudaStream_t s) {
   if (own_stream_ && stream_) cudaStreamDestroy(stream_);
-  stream_ = s;
+  stream_ = s;  // may be the legacy default stream (NULL): that is a valid choice, not "unset"
   own_stream_ = false;
+  user_stream_ = true;
   graph_valid_ = false;
 }
 
@@ -577,7 +580,7 @@ void Net::mark_params_dirty(int vl) {
 void Net::ensure_device() {
   ECO_CHECK(device_available(),
             "no CUDA device is visible: libeco_b200 has no CPU execution path (the reference's CPU mode is not replaced)");
-  if (!stream_) {
+  if (!stream_ && !user_stream_) {
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     own_stream_ = true;
   }
@@ -589,6 +592,7 @@ void Net::ensure_device() {
     CUDA_OK(cudaGetDeviceProperties(&prop, dev));
     ECO_CHECK(prop.major == 10, "libeco_b200 is built for sm_100a only; device is sm_" << prop.major << prop.minor);
     CUDA_OK(conv_umma_configure());
+    g_num_sms = prop.multiProcessorCount;
     configured = true;
   }
 }
@@ -1224,11 +1228,8 @@ void Net::plan() {
         const int ntiles = (c.Cout + 255) / 256;
         kp.block_n = round_up((c.Cout + ntiles - 1) / ntiles, 16);
         c.Cout_pad = round_up(c.Cout, kp.block_n);
-        const size_t per_stage = (size_t)kBlockM * 128 + (size_t)kp.block_n * 128;
-        const size_t budget = kp.block_n <= 128 ? 100 * 1024 : 200 * 1024;
-        kp.stages = (int)std::max<size_t>(2, std::min<size_t>(6, budget / per_stage));
-        kp.tmem_cols = pow2_at_least(kp.block_n);
         kp.a_mode = a_mode_ < 0 ? A_TMA_IM2COL : a_mode_;
+        kp.num_sms = g_num_sms;
         kp.error_flag = error_flag_dev_;
         kp.relu = c.relu ? 1 : 0;
         c.w_dev = static_cast<__nv_bfloat16*>(dalloc((size_t)c.Cout_pad * c.Ktotal * 2, true));
@@ -1254,7 +1255,20 @@ void Net::plan() {
         __nv_bfloat16* rp = nullptr;
         bind(c.res_tensor, rp, kp.res_cs, kp.res_coff);
         kp.res = rp;
-        make_tensor_maps(c);
+        make_tensor_maps(c);  // may downgrade a_mode to the gather for this layer
+        {
+          const size_t per_stage = (size_t)kBlockM * 128 + (size_t)kp.block_n * 128;
+          kp.persistent = (persistent_ && kp.a_mode == A_TMA_IM2COL) ? 1 : 0;
+          if (kp.persistent) {
+            // one CTA per SM: deep ring, double-buffered accumulator (2 x block_n TMEM columns)
+            kp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (size_t)(200 * 1024) / per_stage));
+            kp.tmem_cols = pow2_at_least(2 * kp.block_n);
+          } else {
+            const size_t budget = kp.block_n <= 128 ? 100 * 1024 : 200 * 1024;
+            kp.stages = (int)std::max<size_t>(2, std::min<size_t>(6, budget / per_stage));
+            kp.tmem_cols = pow2_at_least(kp.block_n);
+          }
+        }
         const double taps = (double)c.K[0] * c.K[1] * c.K[2];
         c.flops = 2.0 * kp.M * c.Cout * taps * c.Cin;
         c.bytes = 2.0 * ((double)c.NB * c.I[0] * c.I[1] * c.I[2] * c.Cin + (double)kp.M * c.Cout + (double)c.Cout * taps * c.Cin);
@@ -1569,8 +1583,8 @@ void Net::run_op(Op& op) {
         }
       }
       CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.tmB, stream_));
-      if (c.out_tensor >= 0) tensors_[c.out_tensor].dev_newer = true;
-      if (c.raw_tensor >= 0) tensors_[c.raw_tensor].dev_newer = true;
+      if (c.out_tensor >= 0) mark_written(c.out_tensor);
+      if (c.raw_tensor >= 0) mark_written(c.raw_tensor);
       break;
     }
     case Op::POOL_CL:
@@ -1612,7 +1626,14 @@ void Net::run_op(Op& op) {
                                  stream_));
       break;
   }
-  if (op.out >= 0) tensors_[op.out].dev_newer = true;
+  if (op.out >= 0) mark_written(op.out);
+}
+
+// every tensor that shares the written buffer (views, Split copies, concat slices <-> concat top)
+void Net::mark_written(int tid) {
+  const int root = tensors_[tid].root;
+  for (auto& t : tensors_)
+    if (t.root == root && t.materialized) t.dev_newer = true;
 }
 
 float Net::forward(int start, int end) {
@@ -1657,15 +1678,11 @@ float Net::forward(int start, int end) {
       cudaGraphDestroy(g);
       graph_valid_ = true;
     } else {
-      for (auto& op : ops_) {
-        launches += op.launches;
-        if (op.out >= 0) tensors_[op.out].dev_newer = true;
-        if (op.type == Op::CONV) {
-          ConvOp& c = convs_[op.conv];
-          if (c.out_tensor >= 0) tensors_[c.out_tensor].dev_newer = true;
-          if (c.raw_tensor >= 0) tensors_[c.raw_tensor].dev_newer = true;
-        }
-      }
+      for (auto& op : ops_) launches += op.launches;
+      std::vector<char> is_input(tensors_.size(), 0);
+      for (int vb : inputs_) is_input[vis_blobs_[vb].tensor] = 1;
+      for (size_t i = 0; i < tensors_.size(); ++i)
+        if (tensors_[i].materialized && !is_input[i]) tensors_[i].dev_newer = true;
     }
     CUDA_OK(cudaGraphLaunch(graph_exec_, stream_));
   } else {

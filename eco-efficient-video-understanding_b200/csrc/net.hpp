@@ -193,6 +193,8 @@ class Net {
   bool keep_all_ = false;
   int a_mode_ = -1;
   bool use_graph_ = false;
+  bool persistent_ = true;
+  bool user_stream_ = false;
   // plan
   bool planned_ = false;
   std::vector<Op> ops_;
@@ -214,6 +216,7 @@ class Net {
   void upload_params();
   void upload_dirty_inputs(int first_op);
   void run_op(Op& op);
+  void mark_written(int tensor);
   void ensure_device();
   void* dalloc(size_t bytes, bool zero);
   Tensor& T(int i) { return tensors_[i]; }

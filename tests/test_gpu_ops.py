@@ -48,12 +48,12 @@ def two_conv_net(shape, cmid, cout, k, s, p):
 PLAIN = {"gp", "gp_r", "fc"}  # blobs that are plain fp32 on the device
 
 
-def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True):
+def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True, persistent=True):
     ref = refnet.RefNet(txt).init_params(seed + 1)
     rng = np.random.default_rng(seed)
     x = rng.normal(size=shape).astype(np.float32)
     want = ref.forward(x, bf16=True)
-    net = make_net(txt, keep_all=keep_all, a_mode=a_mode)
+    net = make_net(txt, keep_all=keep_all, a_mode=a_mode, persistent=persistent)
     load_params(net, ref.params_dict())
     net.blobs["data"].data[...] = x
     net.forward()
@@ -104,6 +104,20 @@ CONV3D = [
 def test_conv3d(gpu, case, a_mode):
     shape, cmid, cout, k, s, p = case
     run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, a_mode, check=("a_bn", "c", "c_bn"))
+
+
+@pytest.mark.parametrize("case", [CONV2D[1], CONV2D[5]], ids=["c1", "c5"])
+def test_conv2d_im2col_one_tile_per_cta(gpu, case):
+    # the non-persistent kernel with the TMA im2col A path (the persistent one is the default)
+    shape, cmid, cout, k, s, p = case
+    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 1, check=("a_bn", "c", "c_bn"), persistent=False)
+
+
+def test_conv3d_many_tiles_persistent(gpu):
+    # more tiles than SMs and two N tiles: every CTA of the persistent kernel walks several tiles,
+    # both TMEM accumulator buffers and the per-tile constant reload are exercised
+    shape = (8, 8, 8, 14, 14)
+    run_case(two_conv_net(shape, 128, 512, [3, 3, 3], [1, 1, 1], [1, 1, 1]), shape, 1, check=("c", "c_bn"))
 
 
 @pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
