@@ -339,19 +339,23 @@ class RefNet:
         return self
 
     # ---- forward ---------------------------------------------------------------
-    def forward(self, inputs, bf16=False, keep=None, teacher=None):
+    def forward(self, inputs, bf16=False, keep=None, teacher=None, teacher_raw=None):
         """inputs: array for the single net input or {name: array}.  Returns {blob: array}
         for every blob (in-place layers overwrite, as in caffe).
 
         teacher: optional {blob: array} (e.g. the device's blobs).  After the last layer that
         writes a blob, the oracle's own value is recorded in the result and the teacher's value is
         substituted for all later consumers, so every layer is checked on the inputs the device
-        actually saw (no error amplification through the depth of the net)."""
+        actually saw (no error amplification through the depth of the net).
+        teacher_raw: optional {blob: array} of raw conv / eltwise sums as the device stored them
+        (bf16); used only as the *older* operand of an Eltwise, which is exactly what the device's
+        fused residual add reads back from memory."""
         if not isinstance(inputs, dict):
             inputs = {self.inputs[0]: inputs}
-        return self._walk(inputs, bf16=bf16, teacher=teacher)
+        return self._walk(inputs, bf16=bf16, teacher=teacher, teacher_raw=teacher_raw)
 
-    def _walk(self, inputs, shapes_only=False, out_param_shapes=None, bf16=False, bn_hook=None, teacher=None):
+    def _walk(self, inputs, shapes_only=False, out_param_shapes=None, bf16=False, bn_hook=None, teacher=None,
+              teacher_raw=None):
         blobs = {}
         shp = {}
         own = {}
@@ -453,10 +457,15 @@ class RefNet:
                         # add happens (fused into that conv's epilogue); the other one is read
                         # back from its bf16 copy in HBM.
                         last = max(range(2), key=lambda i: produced_order[l.bottoms[i]])
-                        if last == 0:
-                            b = round_bf16(b)
+                        older = l.bottoms[1 - last]
+                        if teacher_raw is not None and older in teacher_raw:
+                            old_val = _f32(teacher_raw[older]).reshape(a.shape)
                         else:
-                            a = round_bf16(a)
+                            old_val = round_bf16(b if last == 0 else a)
+                        if last == 0:
+                            b = old_val
+                        else:
+                            a = old_val
                     blobs[l.tops[0]] = eltwise_sum(a, b, co[0], co[1])
                 shp[l.tops[0]] = list(bs[0])
             elif t == "Reshape":

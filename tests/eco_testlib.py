@@ -80,6 +80,15 @@ def teacher_blobs(ref, dev):
     return {k: v for k, v in dev.items() if k not in raw}
 
 
+def teacher_raw_blobs(ref, dev):
+    """The raw sums as stored by the device: what its fused residual adds read back (older Eltwise operand)."""
+    raw = set()
+    for l in ref.layers:
+        if l.type in ("Convolution", "Eltwise"):
+            raw.update(l.tops)
+    return {k: v for k, v in dev.items() if k in raw}
+
+
 def check_f32_blob(got, want, name=""):
     assert rel_max(got, want) <= TOL_OP, describe_mismatch(got, want, name)
 

@@ -7,7 +7,7 @@ import pytest
 from oracle import refnet
 import gen_eco_prototxt as gen
 from eco_testlib import (TOL_LOGITS, TOL_NET, check_bf16_blob, check_f32_blob, describe_mismatch, load_params,
-                         make_net, rel_l2, rel_max, teacher_blobs)
+                         make_net, rel_l2, rel_max, teacher_blobs, teacher_raw_blobs)
 
 pytestmark = pytest.mark.gpu
 
@@ -38,7 +38,7 @@ def test_eco_lite_n4_every_blob(gpu, a_mode):
     blobs = net.blobs
     dev = {name: blobs[name].data.copy() for name in want if name not in FUSED_AWAY and name in blobs}
     # (1) teacher-forced: every blob of deploy.prototxt, each layer fed the device's own inputs
-    forced = ref.forward(x, bf16=True, teacher=teacher_blobs(ref, dev))
+    forced = ref.forward(x, bf16=True, teacher=teacher_blobs(ref, dev), teacher_raw=teacher_raw_blobs(ref, dev))
     worst_flip = ("", 0.0)
     for name, g in dev.items():
         assert g.shape == want[name].shape, (name, g.shape, want[name].shape)
@@ -85,7 +85,7 @@ def test_eco_full_n4(gpu):
     out = net.forward()
     blobs = net.blobs
     dev = {name: blobs[name].data.copy() for name in want if name not in FUSED_AWAY and name in blobs and name != "data"}
-    forced = ref.forward(x, bf16=True, teacher=teacher_blobs(ref, dev))
+    forced = ref.forward(x, bf16=True, teacher=teacher_blobs(ref, dev), teacher_raw=teacher_raw_blobs(ref, dev))
     for name, g in dev.items():
         if name in PLAIN_LITE:
             check_f32_blob(g, forced[name], name)

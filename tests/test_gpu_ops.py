@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import refnet
-from eco_testlib import check_bf16_blob, check_f32_blob, load_params, make_net, teacher_blobs
+from eco_testlib import check_bf16_blob, check_f32_blob, load_params, make_net, teacher_blobs, teacher_raw_blobs
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -61,7 +61,7 @@ def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True, persist
     dev = {name: got[name].data.copy() for name in check}
     # teacher forcing: every checked blob is recomputed by the oracle from the device's own upstream
     # blobs, so each fused op is judged on identical inputs
-    forced = ref.forward(x, bf16=True, teacher=teacher_blobs(ref, dev))
+    forced = ref.forward(x, bf16=True, teacher=teacher_blobs(ref, dev), teacher_raw=teacher_raw_blobs(ref, dev))
     for name in check:
         g = dev[name]
         assert g.shape == want[name].shape, (name, g.shape, want[name].shape)
