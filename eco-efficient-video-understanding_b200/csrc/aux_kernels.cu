@@ -140,6 +140,73 @@ __global__ void __launch_bounds__(256) pool_cl_kernel(const PoolParams p) {
   }
 }
 
+// 2-D 3x3 pooling (every pool of ECO's 2-D trunk): one thread produces a strip of T outputs along x
+// for 8 channels, sliding a 3-column window so each input column is loaded once per output row
+// (3*S+small loads per output instead of 9).  Same caffe semantics as pool_cl_kernel.
+template <bool IS_MAX, int S, int T>
+__global__ void __launch_bounds__(256) pool2d_k3_strip_kernel(const PoolParams p) {
+  constexpr int NCOLS = (T - 1) * S + 3;
+  const int cg = p.C >> 3;
+  const int strips = (p.OW + T - 1) / T;
+  const unsigned total = (unsigned)p.NB * p.OH * strips * cg;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    unsigned r = t / (unsigned)cg;
+    const int g = (int)(t - r * cg);
+    const int xs = (int)(r % (unsigned)strips); r /= (unsigned)strips;
+    const int oy = (int)(r % (unsigned)p.OH);
+    const int n = (int)(r / (unsigned)p.OH);
+    const int ox0 = xs * T;
+    const int iy0 = oy * S - p.pH;
+    const int ix0 = ox0 * S - p.pW;
+    const __nv_bfloat16* base = p.x + p.x_coff + g * 8 + (long long)n * p.IH * p.IW * p.x_cs;
+    bool rok[3];
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) rok[rr] = (unsigned)(iy0 + rr) < (unsigned)p.IH;
+    const int hcount = min(iy0 + 3, p.IH + p.pH) - iy0;  // pad-inclusive rows of the window (AVE divisor)
+    float c0[8], c1[8], c2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c0[j] = c1[j] = c2[j] = IS_MAX ? -FLT_MAX : 0.f;
+#pragma unroll
+    for (int col = 0; col < NCOLS; ++col) {
+      const int ix = ix0 + col;
+      float cv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cv[j] = IS_MAX ? -FLT_MAX : 0.f;
+      if ((unsigned)ix < (unsigned)p.IW) {
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+          if (rok[rr]) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + ((long long)(iy0 + rr) * p.IW + ix) * p.x_cs));
+            float f[8];
+            unpack8(v, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cv[j] = IS_MAX ? fmaxf(cv[j], f[j]) : cv[j] + f[j];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c0[j] = c1[j]; c1[j] = c2[j]; c2[j] = cv[j]; }
+      if (col >= 2 && (col - 2) % S == 0) {
+        const int ox = ox0 + (col - 2) / S;
+        if (ox < p.OW) {
+          float o[8];
+          if (IS_MAX) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaxf(c0[j], c1[j]), c2[j]);
+          } else {
+            const int ws = ox * S - p.pW;
+            const float div = (float)(hcount * (min(ws + 3, p.IW + p.pW) - ws));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = ((c0[j] + c1[j]) + c2[j]) / div;
+          }
+          const long long opix = ((long long)n * p.OH + oy) * p.OW + ox;
+          *reinterpret_cast<uint4*>(p.y + opix * p.y_cs + p.y_coff + g * 8) = pack8(o);
+        }
+      }
+    }
+  }
+}
+
 // global average: one thread per (outer, channel); consecutive threads read consecutive channels
 __global__ void global_avg_cl_kernel(ClView s, float* __restrict__ dst) {
   const long long total = s.outer * s.C;
@@ -270,6 +337,18 @@ cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {
   const long long n = (long long)p.NB * p.OD * p.OH * p.OW * (p.C / 8);
   if (n == 0) return cudaSuccess;
   if (n >= (1LL << 31)) return cudaErrorInvalidValue;  // 32-bit index math in the kernel
+  if (p.ID == 1 && p.KD == 1 && p.KH == 3 && p.KW == 3 && p.sH == p.sW && (p.sH == 1 || p.sH == 2) && p.pH == p.pW &&
+      p.pH <= 1) {
+    constexpr int T = 4;
+    const long long nt = (long long)p.NB * p.OH * ((p.OW + T - 1) / T) * (p.C / 8);
+    const long long b = (nt + kThreads - 1) / kThreads;
+    const unsigned grid = (unsigned)(b > 148LL * 64 ? 148LL * 64 : b);
+    if (p.is_max && p.sH == 2) pool2d_k3_strip_kernel<true, 2, T><<<grid, kThreads, 0, st>>>(p);
+    else if (p.is_max) pool2d_k3_strip_kernel<true, 1, T><<<grid, kThreads, 0, st>>>(p);
+    else if (p.sH == 2) pool2d_k3_strip_kernel<false, 2, T><<<grid, kThreads, 0, st>>>(p);
+    else pool2d_k3_strip_kernel<false, 1, T><<<grid, kThreads, 0, st>>>(p);
+    return cudaGetLastError();
+  }
   const long long blocks = (n + kThreads - 1) / kThreads;
   pool_cl_kernel<<<(unsigned)(blocks > 148LL * 64 ? 148LL * 64 : blocks), kThreads, 0, st>>>(p);
   return cudaGetLastError();

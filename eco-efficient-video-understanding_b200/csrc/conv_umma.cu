@@ -367,10 +367,66 @@ conv_umma_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap t
 
 
 // ------------------------------------------------------------------------------------------------
-// Persistent variant (A via TMA im2col only): one CTA per SM walks the tile list; the TMEM
-// accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1, and the
-// smem ring keeps streaming across tile boundaries.
-__global__ void __launch_bounds__(kConvThreads, 1)
+// Persistent variant (A via TMA im2col only).  One CTA per SM walks the tile list.
+//   * tile = (MT x 128) output positions x block_n channels; with MT = 2 the two 128-row halves share
+//     every weight tile in shared memory (half the B traffic per FLOP, for block_n <= 128)
+//   * TMEM accumulators are double-buffered (2 x MT x block_n fp32 columns <= 512): the epilogue of
+//     tile i overlaps the MMAs of tile i+1; the smem ring streams across tile boundaries
+//   * 10 warps: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = epilogue; two epilogue warps
+//     per TMEM lane quarter split the 16-column chunks between them
+constexpr int kPersistThreads = 320;
+
+__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32_t taddr, int m, bool row_ok, int cg,
+                                               int c0, const float* s_bias, const float* s_scale,
+                                               const float* s_shift, bool simple) {
+  uint32_t v[16];
+  tmem_ld16(taddr, v);
+  const int nvalid = p.Cout - cg;
+  if (!(row_ok && nvalid > 0)) return;
+  float f[16];
+  const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
+  const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
+  if (simple) {
+    // no raw / residual consumer: bias is pre-folded into the shift, y = relu?(acc * scale + shift')
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = sc4[j], b = sh4[j];
+      f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), a.x, b.x);
+      f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y);
+      f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z);
+      f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w);
+    }
+  } else {
+    const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b = bi4[j];
+      f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+      f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+      f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+      f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+    }
+    if (p.res) load16_bf16_add(p.res + (long long)m * p.res_cs + p.res_coff + cg, f, nvalid);
+    if (p.raw) store16_bf16(p.raw + (long long)m * p.raw_cs + p.raw_coff + cg, f, nvalid);
+    if (!p.out) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = sc4[j], b = sh4[j];
+      f[4 * j + 0] = fmaf(f[4 * j + 0], a.x, b.x);
+      f[4 * j + 1] = fmaf(f[4 * j + 1], a.y, b.y);
+      f[4 * j + 2] = fmaf(f[4 * j + 2], a.z, b.z);
+      f[4 * j + 3] = fmaf(f[4 * j + 3], a.w, b.w);
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  store16_bf16(p.out + (long long)m * p.out_cs + p.out_coff + cg, f, nvalid);
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kPersistThreads, 1)
 conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap tmA,
                             const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ uint8_t smem_raw[];
@@ -378,9 +434,11 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
 
+  constexpr int TILE_M = MT * kBlockM;
   const int S = p.stages;
   const int BN = p.block_n;
-  const uint32_t a_stage_bytes = kBlockM * 128;
+  const uint32_t a_half_bytes = kBlockM * 128;
+  const uint32_t a_stage_bytes = MT * a_half_bytes;
   const uint32_t b_stage_bytes = (uint32_t)BN * 128;
   const uint32_t sA = base;
   const uint32_t sB = sA + S * a_stage_bytes;
@@ -397,8 +455,9 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles_n = (p.Cout + BN - 1) / BN;
-  const int n_tiles_m = (p.M + kBlockM - 1) / kBlockM;
+  const int n_tiles_m = (p.M + TILE_M - 1) / TILE_M;
   const int total_tiles = n_tiles_n * n_tiles_m;
+  const uint32_t acc_cols = (uint32_t)(MT * BN);  // TMEM columns of one accumulator buffer
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -407,7 +466,7 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tmem_full + 8 * b, 1);
-      mbar_init(bar_tmem_empty + 8 * b, 4);  // one arrival per epilogue warp
+      mbar_init(bar_tmem_empty + 8 * b, 8);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -430,12 +489,16 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
       uint32_t it = 0;  // running K-block counter across tiles
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n0 = (t % n_tiles_n) * BN;
-        int r = (t / n_tiles_n) * kBlockM;
-        const int q = r % p.OW; r /= p.OW;
-        const int pp = r % p.OH; r /= p.OH;
-        const int z = r % p.OD;
-        const int n = r / p.OD;
-        const int cw = q * p.sW - p.pW, chh = pp * p.sH - p.pH, cd = z * p.sD - p.pD;
+        int cw[MT], chh[MT], cd[MT], cn[MT];
+#pragma unroll
+        for (int h = 0; h < MT; ++h) {
+          int r = (t / n_tiles_n) * TILE_M + h * kBlockM;
+          const int q = r % p.OW; r /= p.OW;
+          const int pp = r % p.OH; r /= p.OH;
+          const int z = r % p.OD;
+          cn[h] = r / p.OD;
+          cw[h] = q * p.sW - p.pW; chh[h] = pp * p.sH - p.pH; cd[h] = z * p.sD - p.pD;
+        }
         int cb = 0, kx = 0, ky = 0, kz = 0;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % (uint32_t)S;
@@ -443,12 +506,16 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
           mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
           tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
-          if (p.nsp == 3)
-            tma_im2col_5d(sA + s * a_stage_bytes, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, cd, n,
-                          (uint16_t)kx, (uint16_t)ky, (uint16_t)kz);
-          else
-            tma_im2col_4d(sA + s * a_stage_bytes, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, n,
-                          (uint16_t)kx, (uint16_t)ky);
+#pragma unroll
+          for (int h = 0; h < MT; ++h) {
+            const uint32_t dst = sA + s * a_stage_bytes + h * a_half_bytes;
+            if (p.nsp == 3)
+              tma_im2col_5d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cd[h], cn[h], (uint16_t)kx,
+                            (uint16_t)ky, (uint16_t)kz);
+            else
+              tma_im2col_4d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cn[h], (uint16_t)kx,
+                            (uint16_t)ky);
+          }
           if (++cb == p.cblocks) {
             cb = 0;
             if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++kz; } }
@@ -466,50 +533,63 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
         const uint32_t use = tile_iter >> 1;
         mbar_wait(bar_tmem_empty + 8 * buf, (use & 1u) ^ 1u, p.error_flag, 5);  // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * (uint32_t)BN;
+        const uint32_t acc = tmem_base + buf * acc_cols;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % (uint32_t)S;
           const uint32_t ph = (it / (uint32_t)S) & 1u;
           mbar_wait(bar_full + 8 * s, ph, p.error_flag, 2);
           tc_fence_after();
-          const uint64_t adesc = make_sw128_desc(sA + s * a_stage_bytes);
           const uint64_t bdesc = make_sw128_desc(sB + s * b_stage_bytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          for (int h = 0; h < MT; ++h) {
+            const uint64_t adesc = make_sw128_desc(sA + s * a_stage_bytes + h * a_half_bytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16(acc + (uint32_t)(h * BN), adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          }
           umma_commit(bar_empty + 8 * s);
         }
         umma_commit(bar_tmem_full + 8 * buf);
       }
     }
   } else {
-    // ===================== epilogue warps =====================
-    const int wq = warp & 3;
-    const int row = wq * 32 + lane;
+    // ===================== epilogue warps (8) =====================
+    const int wq = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;   // which of the two warps of that quarter
+    const int chunks = BN >> 4;
+    const bool simple = (p.res == nullptr) && (p.raw == nullptr) && (p.out != nullptr);
     uint32_t tile_iter = 0;
     int loaded_n0 = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
       const int n0 = (t % n_tiles_n) * BN;
-      const int m0 = (t / n_tiles_n) * kBlockM;
-      if (n0 != loaded_n0) {  // uniform across the four epilogue warps
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      const int m0 = (t / n_tiles_n) * TILE_M;
+      if (n0 != loaded_n0) {  // uniform across the eight epilogue warps
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = threadIdx.x - 64; i < BN; i += 256) {
           const int c = n0 + i;
           const bool ok = c < p.Cout;
-          s_bias[i] = (ok && p.bias) ? p.bias[c] : 0.f;
-          s_scale[i] = (ok && p.scale) ? p.scale[c] : 1.f;
-          s_shift[i] = (ok && p.scale) ? p.shift[c] : 0.f;
+          const float bi = (ok && p.bias) ? p.bias[c] : 0.f;
+          const float sc = (ok && p.scale) ? p.scale[c] : 1.f;
+          const float sh = (ok && p.scale) ? p.shift[c] : 0.f;
+          s_bias[i] = bi;
+          s_scale[i] = sc;
+          s_shift[i] = simple ? fmaf(bi, sc, sh) : sh;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         loaded_n0 = n0;
       }
       const uint32_t buf = tile_iter & 1u;
       const uint32_t use = tile_iter >> 1;
       mbar_wait(bar_tmem_full + 8 * buf, use & 1u, p.error_flag, 4);
       tc_fence_after();
-      const int m = m0 + row;
-      epilogue_rows(p, tmem_base + ((uint32_t)(wq * 32) << 16) + buf * (uint32_t)BN, m, m < p.M, n0, BN, s_bias,
-                    s_scale, s_shift);
+#pragma unroll
+      for (int h = 0; h < MT; ++h) {
+        const int m = m0 + h * kBlockM + wq * 32 + lane;
+        const bool row_ok = m < p.M;
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols + (uint32_t)(h * BN);
+        for (int c = half; c < chunks; c += 2)
+          epilogue_chunk(p, taddr + (uint32_t)(c * 16), m, row_ok, n0 + c * 16, c * 16, s_bias, s_scale, s_shift, simple);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -529,18 +609,24 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
 }  // namespace
 
 cudaError_t conv_umma_configure() {
-  cudaError_t e = cudaFuncSetAttribute(conv_umma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_umma_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 cudaError_t launch_conv_umma(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                              cudaStream_t stream) {
-  const size_t smem = conv_smem_bytes(p.block_n, p.stages);
+  const size_t smem = conv_smem_bytes(p.block_n, p.stages, p.persistent ? p.m_halves : 1);
   if (p.persistent) {
-    const int tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.Cout + p.block_n - 1) / p.block_n);
+    const int tile_m = kBlockM * p.m_halves;
+    const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.Cout + p.block_n - 1) / p.block_n);
     const int grid = tiles < p.num_sms ? tiles : p.num_sms;
-    conv_umma_persistent_kernel<<<grid, kConvThreads, smem, stream>>>(p, tmA, tmB);
+    if (p.m_halves == 2)
+      conv_umma_persistent_kernel<2><<<grid, kPersistThreads, smem, stream>>>(p, tmA, tmB);
+    else
+      conv_umma_persistent_kernel<1><<<grid, kPersistThreads, smem, stream>>>(p, tmA, tmB);
     return cudaGetLastError();
   }
   dim3 grid((p.M + kBlockM - 1) / kBlockM, (p.Cout + p.block_n - 1) / p.block_n, 1);

@@ -44,6 +44,7 @@ struct ConvKernelParams {
   int stages;
   int tmem_cols;                     // power of two >= block_n (x2 when persistent: double-buffered accumulator)
   int persistent;                    // 1: conv_umma_persistent_kernel (needs a_mode == A_TMA_IM2COL)
+  int m_halves;                      // persistent only: 1 or 2 128-row halves per tile sharing the weight tile
   int num_sms;
   // ---- epilogue:  raw = acc + bias (+ res);  y = relu?(raw * scale + shift) ----
   int Cout;
@@ -58,8 +59,8 @@ struct ConvKernelParams {
 };
 
 // dynamic shared memory needed for (block_n, stages)
-inline size_t conv_smem_bytes(int block_n, int stages) {
-  size_t a = (size_t)stages * kBlockM * 128;
+inline size_t conv_smem_bytes(int block_n, int stages, int m_halves = 1) {
+  size_t a = (size_t)stages * kBlockM * 128 * m_halves;
   size_t b = (size_t)stages * block_n * 128;
   size_t epi = 3 * 256 * sizeof(float);
   size_t bars = 64 * 8;

@@ -525,6 +525,7 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "a_mode") a_mode_ = v;
   else if (key == "use_graph") use_graph_ = v != 0;
   else if (key == "persistent") persistent_ = v != 0;
+  else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
   else ECO_CHECK(false, "unknown option '" << key << "'");
   free_plan();
 }
@@ -1259,10 +1260,16 @@ void Net::plan() {
         {
           const size_t per_stage = (size_t)kBlockM * 128 + (size_t)kp.block_n * 128;
           kp.persistent = (persistent_ && kp.a_mode == A_TMA_IM2COL) ? 1 : 0;
+          kp.m_halves = 1;
           if (kp.persistent) {
-            // one CTA per SM: deep ring, double-buffered accumulator (2 x block_n TMEM columns)
-            kp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (size_t)(200 * 1024) / per_stage));
-            kp.tmem_cols = pow2_at_least(2 * kp.block_n);
+            // one CTA per SM: deep ring, double-buffered accumulator (2 x m_halves x block_n TMEM columns).
+            // Two 128-row halves share each weight tile when the accumulators fit (block_n <= 128) and
+            // there is enough work to keep every SM busy with the larger tiles.
+            const long long tiles256 = ((long long)kp.M + 255) / 256 * ((c.Cout + kp.block_n - 1) / kp.block_n);
+            if (kp.block_n <= 128 && (dual_m_ == 2 || (dual_m_ == 1 && tiles256 >= 2LL * g_num_sms))) kp.m_halves = 2;
+            const size_t stage_bytes = (size_t)kBlockM * 128 * kp.m_halves + (size_t)kp.block_n * 128;
+            kp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (size_t)(200 * 1024) / stage_bytes));
+            kp.tmem_cols = pow2_at_least(2 * kp.m_halves * kp.block_n);
           } else {
             const size_t budget = kp.block_n <= 128 ? 100 * 1024 : 200 * 1024;
             kp.stages = (int)std::max<size_t>(2, std::min<size_t>(6, budget / per_stage));

@@ -194,6 +194,7 @@ class Net {
   int a_mode_ = -1;
   bool use_graph_ = false;
   bool persistent_ = true;
+  int dual_m_ = 1;
   bool user_stream_ = false;
   // plan
   bool planned_ = false;

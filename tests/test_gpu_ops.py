@@ -48,12 +48,12 @@ def two_conv_net(shape, cmid, cout, k, s, p):
 PLAIN = {"gp", "gp_r", "fc"}  # blobs that are plain fp32 on the device
 
 
-def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True, persistent=True):
+def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True, persistent=True, dual_m=1):
     ref = refnet.RefNet(txt).init_params(seed + 1)
     rng = np.random.default_rng(seed)
     x = rng.normal(size=shape).astype(np.float32)
     want = ref.forward(x, bf16=True)
-    net = make_net(txt, keep_all=keep_all, a_mode=a_mode, persistent=persistent)
+    net = make_net(txt, keep_all=keep_all, a_mode=a_mode, persistent=persistent, dual_m=dual_m)
     load_params(net, ref.params_dict())
     net.blobs["data"].data[...] = x
     net.forward()
@@ -111,6 +111,17 @@ def test_conv2d_im2col_one_tile_per_cta(gpu, case):
     # the non-persistent kernel with the TMA im2col A path (the persistent one is the default)
     shape, cmid, cout, k, s, p = case
     run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 1, check=("a_bn", "c", "c_bn"), persistent=False)
+
+
+@pytest.mark.parametrize("case", [CONV2D[0], CONV2D[1], CONV2D[3]], ids=["c0", "c1", "c3"])
+def test_conv2d_dual_m_tiles(gpu, case):
+    # 256-row tiles: two 128-row halves share each weight tile (forced; auto needs >= 2 tiles per SM)
+    shape, cmid, cout, k, s, p = case
+    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 1, check=("a_bn", "c", "c_bn"), dual_m=2)
+
+
+def test_conv3d_dual_m_residual(gpu):
+    run_case(RES_NET, (2, 8, 4, 6, 6), 1, check=("ra", "ra_bn", "rb_bn", "rc_bn", "fc"), dual_m=2)
 
 
 def test_conv3d_many_tiles_persistent(gpu):
@@ -213,6 +224,29 @@ layer { name: "nx_bn" type: "BN" bottom: "nx" top: "nx_bn" }
 def test_inception_block_concat_alias(gpu, a_mode):
     # concat is zero-copy: branch epilogues / pools write channel slices of `out`
     run_case(INCEPTION, (2, 8, 14, 14), a_mode, check=("b1_bn", "b2_bn", "pl", "pp_bn", "mp", "out", "down", "nx_bn"))
+
+
+POOLS = """name: "pools"
+input: "data" input_dim: 3 input_dim: 8 input_dim: %d input_dim: %d
+layer { name: "f" type: "Convolution" bottom: "data" top: "f" convolution_param { num_output: 24 kernel_size: 1 } }
+layer { name: "f_bn" type: "BN" bottom: "f" top: "f_bn" }
+layer { name: "p_max_s2" type: "Pooling" bottom: "f_bn" top: "p_max_s2" pooling_param { pool: MAX kernel_size: 3 stride: 2 } }
+layer { name: "p_max_s2p" type: "Pooling" bottom: "f_bn" top: "p_max_s2p" pooling_param { pool: MAX kernel_size: 3 stride: 2 pad: 1 } }
+layer { name: "p_max_s1p" type: "Pooling" bottom: "f_bn" top: "p_max_s1p" pooling_param { pool: MAX kernel_size: 3 stride: 1 pad: 1 } }
+layer { name: "p_ave_s1p" type: "Pooling" bottom: "f_bn" top: "p_ave_s1p" pooling_param { pool: AVE kernel_size: 3 stride: 1 pad: 1 } }
+layer { name: "p_ave_s2p" type: "Pooling" bottom: "f_bn" top: "p_ave_s2p" pooling_param { pool: AVE kernel_size: 3 stride: 2 pad: 1 } }
+layer { name: "p_ave_s2" type: "Pooling" bottom: "f_bn" top: "p_ave_s2" pooling_param { pool: AVE kernel_size: 3 stride: 2 } }
+layer { name: "p_ave_5" type: "Pooling" bottom: "f_bn" top: "p_ave_5" pooling_param { pool: AVE kernel_size: 5 stride: 3 pad: 2 } }
+layer { name: "p_max_hw" type: "Pooling" bottom: "f_bn" top: "p_max_hw" pooling_param { pool: MAX kernel_h: 2 kernel_w: 3 stride: 1 } }
+"""
+
+
+@pytest.mark.parametrize("hw", [(15, 13), (28, 28), (7, 9), (112, 112)])
+def test_pool_variants(gpu, hw):
+    # the 3x3 strip kernel (stride 1/2, pad 0/1, ragged strips, ceil-mode last window) and the generic kernel
+    shape = (3, 8) + hw
+    run_case(POOLS % hw, shape, 1, check=("p_max_s2", "p_max_s2p", "p_max_s1p", "p_ave_s1p", "p_ave_s2p", "p_ave_s2",
+                                          "p_ave_5", "p_max_hw"))
 
 
 GOLD = json.load(open(os.path.join(HERE, "golden", "reference_known_answers.json")))
