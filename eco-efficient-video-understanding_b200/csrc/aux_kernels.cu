@@ -207,6 +207,93 @@ __global__ void __launch_bounds__(256) pool2d_k3_strip_kernel(const PoolParams p
   }
 }
 
+// 2-D pooling with the input rows staged through shared memory by bulk async copies
+// (cp.async.bulk -> mbarrier): one CTA = one band of output rows of one image.  The rows it needs are
+// contiguous in a dense channels-last map, so a handful of 10-20 KB bulk copies put >= 64 KB per SM in
+// flight (three CTAs per SM), which plain 16-byte loads could not; every input row is fetched once per
+// band.  Same caffe semantics as pool_cl_kernel (pooling_layer.cpp:199-262).
+__global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, int rows_out) {
+  extern __shared__ __align__(128) uint8_t pool_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int n = blockIdx.y;
+  const int oy0 = blockIdx.x * rows_out;
+  const int oy1 = min(oy0 + rows_out, p.OH);
+  const int iy_lo = oy0 * p.sH - p.pH;
+  const int iy_hi = (oy1 - 1) * p.sH - p.pH + p.KH;
+  const int vy_lo = max(iy_lo, 0), vy_hi = min(iy_hi, p.IH);
+  const uint32_t row_bytes = (uint32_t)p.IW * p.C * 2;
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+  const uint32_t smem_addr = (uint32_t)__cvta_generic_to_shared(pool_smem);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t total = (uint32_t)(vy_hi - vy_lo) * row_bytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(total) : "memory");
+    const __nv_bfloat16* src = p.x + ((long long)n * p.IH + vy_lo) * p.IW * p.C;
+    for (int r = 0; r < vy_hi - vy_lo; ++r) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_addr + (uint32_t)r * row_bytes),
+                   "l"(src + (long long)r * p.IW * p.C), "r"(row_bytes), "r"(bar_addr)
+                   : "memory");
+    }
+  }
+  {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (!ok) {
+      asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0; selp.u32 %0,1,0,q; }"
+                   : "=r"(ok) : "r"(bar_addr) : "memory");
+      if (!ok && clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+  const int cg = p.C >> 3;
+  const int items = (oy1 - oy0) * p.OW * cg;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int g = i % cg;
+    const int r1 = i / cg;
+    const int ox = r1 % p.OW;
+    const int oy = oy0 + r1 / p.OW;
+    int y0 = oy * p.sH - p.pH, x0 = ox * p.sW - p.pW;
+    int y1, x1;
+    float div = 1.f;
+    if (p.is_max) {
+      y1 = min(y0 + p.KH, p.IH); x1 = min(x0 + p.KW, p.IW);
+    } else {
+      y1 = min(y0 + p.KH, p.IH + p.pH); x1 = min(x0 + p.KW, p.IW + p.pW);
+      div = (float)((y1 - y0) * (x1 - x0));
+      y1 = min(y1, p.IH); x1 = min(x1, p.IW);
+    }
+    y0 = max(y0, 0); x0 = max(x0, 0);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = p.is_max ? -FLT_MAX : 0.f;
+    for (int y = y0; y < y1; ++y) {
+      const uint8_t* row = pool_smem + (size_t)(y - vy_lo) * row_bytes + (size_t)g * 16;
+      for (int x = x0; x < x1; ++x) {
+        const uint4 v = *reinterpret_cast<const uint4*>(row + (size_t)x * p.C * 2);
+        float f[8];
+        unpack8(v, f);
+        if (p.is_max) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], f[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+      }
+    }
+    if (!p.is_max) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] / div;
+    }
+    const long long opix = ((long long)n * p.OH + oy) * p.OW + ox;
+    *reinterpret_cast<uint4*>(p.y + opix * p.y_cs + p.y_coff + g * 8) = pack8(acc);
+  }
+}
+
 // global average: one thread per (outer, channel); consecutive threads read consecutive channels
 __global__ void global_avg_cl_kernel(ClView s, float* __restrict__ dst) {
   const long long total = s.outer * s.C;
@@ -337,6 +424,24 @@ cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {
   const long long n = (long long)p.NB * p.OD * p.OH * p.OW * (p.C / 8);
   if (n == 0) return cudaSuccess;
   if (n >= (1LL << 31)) return cudaErrorInvalidValue;  // 32-bit index math in the kernel
+  if (p.ID == 1 && p.KD == 1 && p.OD == 1 && p.x_cs == p.C && p.x_coff == 0) {
+    // rows staged through shared memory by bulk copies
+    const size_t row_bytes = (size_t)p.IW * p.C * 2;
+    int rows_out = 1;
+    while (rows_out < p.OH && ((size_t)(rows_out * p.sH + p.KH) * row_bytes) <= 72 * 1024) ++rows_out;
+    const size_t rows_in = (size_t)(rows_out - 1) * p.sH + p.KH;
+    const size_t smem = rows_in * row_bytes;
+    if (smem <= 200 * 1024 && row_bytes % 16 == 0 && p.NB <= 65535) {
+      static bool configured = false;
+      if (!configured) {
+        cudaFuncSetAttribute(pool2d_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+      }
+      dim3 grid((p.OH + rows_out - 1) / rows_out, p.NB, 1);
+      pool2d_rows_kernel<<<grid, 256, smem, st>>>(p, rows_out);
+      return cudaGetLastError();
+    }
+  }
   if (p.ID == 1 && p.KD == 1 && p.KH == 3 && p.KW == 3 && p.sH == p.sW && (p.sH == 1 || p.sH == 2) && p.pH == p.pW &&
       p.pH <= 1) {
     constexpr int T = 4;

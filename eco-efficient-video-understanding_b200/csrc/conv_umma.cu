@@ -485,14 +485,17 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t tx_bytes = b_stage_bytes + a_stage_bytes;
       uint32_t it = 0;  // running K-block counter across tiles
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n0 = (t % n_tiles_n) * BN;
         int cw[MT], chh[MT], cd[MT], cn[MT];
+        bool live[MT];  // a half that starts beyond the last output position is never loaded
+        uint32_t tile_tx = b_stage_bytes;
 #pragma unroll
         for (int h = 0; h < MT; ++h) {
           int r = (t / n_tiles_n) * TILE_M + h * kBlockM;
+          live[h] = r < p.M;
+          if (live[h]) tile_tx += a_half_bytes;
           const int q = r % p.OW; r /= p.OW;
           const int pp = r % p.OH; r /= p.OH;
           const int z = r % p.OD;
@@ -504,10 +507,11 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
           const uint32_t s = it % (uint32_t)S;
           const uint32_t ph = (it / (uint32_t)S) & 1u;
           mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
-          mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
+          mbar_arrive_expect_tx(bar_full + 8 * s, tile_tx);
           tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
 #pragma unroll
           for (int h = 0; h < MT; ++h) {
+            if (!live[h]) continue;
             const uint32_t dst = sA + s * a_stage_bytes + h * a_half_bytes;
             if (p.nsp == 3)
               tma_im2col_5d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cd[h], cn[h], (uint16_t)kx,
@@ -542,6 +546,7 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
           const uint64_t bdesc = make_sw128_desc(sB + s * b_stage_bytes);
 #pragma unroll
           for (int h = 0; h < MT; ++h) {
+            if ((t / n_tiles_n) * TILE_M + h * kBlockM >= p.M) continue;  // half beyond the last output position
             const uint64_t adesc = make_sw128_desc(sA + s * a_stage_bytes + h * a_half_bytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)

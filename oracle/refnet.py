@@ -359,6 +359,7 @@ class RefNet:
         blobs = {}
         shp = {}
         own = {}
+        plain = set()  # blobs the device keeps as plain fp32 vectors (downstream of a collapsing pool / fc)
         last_writer = {}
         for li, l in enumerate(self.layers):
             for top in l.tops:
@@ -436,7 +437,9 @@ class RefNet:
                     # bf16 mirror: pooled maps stay bf16 feature maps; pools that collapse the
                     # whole map (global pools / segment consensus) feed fp32 vectors to the fc.
                     collapses = all(o == 1 for o in osh[2:])
-                    blobs[l.tops[0]] = y if collapses else R(y)
+                    if collapses or l.bottoms[0] in plain:
+                        plain.add(l.tops[0])
+                    blobs[l.tops[0]] = y if l.tops[0] in plain else R(y)
                 shp[l.tops[0]] = osh
             elif t == "Concat":
                 axis = int((l.msg.get1("concat_param") or _pt.Msg()).get1("axis", 1))
@@ -528,6 +531,9 @@ class RefNet:
                     shp[top] = []
             else:
                 raise NotImplementedError("oracle: layer type %s (%s)" % (t, l.name))
+            if t in ("InnerProduct", "Softmax") or (l.bottoms and l.bottoms[0] in plain and t in
+                                                     ("Reshape", "Dropout", "Concat", "Permute", "Split")):
+                plain.update(l.tops)
             for top in l.tops:
                 produced_order[top] = li
                 if teacher is not None and not shapes_only and last_writer[top] == li and top in blobs:

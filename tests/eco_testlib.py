@@ -65,7 +65,12 @@ def check_bf16_blob(got, want, name=""):
     lim = 1.001 * bf16_ulp(wr) + atol
     ok = d <= lim
     flips = float((d > atol).mean())
-    assert ok.all(), "%s: %d elements differ by more than one bf16 ulp; %s" % (name, (~ok).sum(), describe_mismatch(got, want, name))
+    if not ok.all():
+        excess = np.where(ok, 0.0, d / lim)
+        idx = np.unravel_index(np.argmax(excess), excess.shape)
+        raise AssertionError("%s: %d elements differ by more than one bf16 ulp; worst violation @%s got=%.9g want_bf16=%.9g "
+                             "want_f32=%.9g ulp=%.3g atol=%.3g; %s" % (name, (~ok).sum(), idx, got[idx], wr[idx], want[idx],
+                                                                      bf16_ulp(wr)[idx], atol, describe_mismatch(got, want, name)))
     assert flips <= FLIP_FRAC, "%s: %.4f of the elements differ from the oracle (limit %.2f)" % (name, flips, FLIP_FRAC)
     return flips
 
