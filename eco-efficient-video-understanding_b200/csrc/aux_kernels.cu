@@ -250,10 +250,109 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
     }
   }
   const int cg = p.C >> 3;
+  const uint32_t magic_cg = 0xFFFFFFFFu / (uint32_t)cg + 1u;  // i / cg == umulhi(i, magic) for i < 2^16
+  if (p.KH == 3 && p.KW == 3 && p.sH == p.sW && (p.sW == 1 || p.sW == 2)) {
+    // 3x3 windows: a thread owns a strip of T outputs along x and slides over the input columns once
+    constexpr int T = 4;
+    const int S = p.sW;
+    const int strips = (p.OW + T - 1) / T;
+    const int items = (oy1 - oy0) * strips * cg;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      const int r1 = (int)__umulhi((uint32_t)i, magic_cg);
+      const int g = i - r1 * cg;
+      const int rowi = r1 / strips;
+      const int xs = r1 - rowi * strips;
+      const int oy = oy0 + rowi;
+      const int ox0 = xs * T;
+      const int iy0 = oy * S - p.pH;
+      const int ix0 = ox0 * S - p.pW;
+      const uint8_t* rows[3];
+      bool rok[3];
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        const int y = iy0 + rr;
+        rok[rr] = y >= vy_lo && y < vy_hi;
+        rows[rr] = pool_smem + (size_t)(rok[rr] ? y - vy_lo : 0) * row_bytes + (size_t)g * 16;
+      }
+      const long long opix0 = ((long long)n * p.OH + oy) * p.OW;
+      const int ncols = (T - 1) * S + 3;
+      if (p.is_max) {
+        // max of bf16 values is exact in packed bf16 arithmetic: no fp32 unpacking
+        const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+        __nv_bfloat162 c0[4], c1[4], c2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c0[j] = c1[j] = c2[j] = ninf;
+        for (int col = 0; col < ncols; ++col) {
+          const int ix = ix0 + col;
+          __nv_bfloat162 cv[4] = {ninf, ninf, ninf, ninf};
+          if ((unsigned)ix < (unsigned)p.IW) {
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr)
+              if (rok[rr]) {
+                const uint4 v = *reinterpret_cast<const uint4*>(rows[rr] + (size_t)ix * p.C * 2);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cv[j] = __hmax2(cv[j], h[j]);
+              }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { c0[j] = c1[j]; c1[j] = c2[j]; c2[j] = cv[j]; }
+          const int d = col - 2;
+          if (d >= 0 && (S == 1 || (d & 1) == 0)) {
+            const int ox = ox0 + (S == 1 ? d : d >> 1);
+            if (ox < p.OW) {
+              uint4 o;
+              __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) oh[j] = __hmax2(__hmax2(c0[j], c1[j]), c2[j]);
+              *reinterpret_cast<uint4*>(p.y + (opix0 + ox) * p.y_cs + p.y_coff + g * 8) = o;
+            }
+          }
+        }
+      } else {
+        const int hcount = min(iy0 + 3, p.IH + p.pH) - iy0;  // pad-inclusive window rows (AVE divisor)
+        float c0[8], c1[8], c2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c0[j] = c1[j] = c2[j] = 0.f;
+        for (int col = 0; col < ncols; ++col) {
+          const int ix = ix0 + col;
+          float cv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cv[j] = 0.f;
+          if ((unsigned)ix < (unsigned)p.IW) {
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr)
+              if (rok[rr]) {
+                const uint4 v = *reinterpret_cast<const uint4*>(rows[rr] + (size_t)ix * p.C * 2);
+                float f[8];
+                unpack8(v, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cv[j] += f[j];
+              }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { c0[j] = c1[j]; c1[j] = c2[j]; c2[j] = cv[j]; }
+          const int d = col - 2;
+          if (d >= 0 && (S == 1 || (d & 1) == 0)) {
+            const int ox = ox0 + (S == 1 ? d : d >> 1);
+            if (ox < p.OW) {
+              const int ws = ox * S - p.pW;
+              const float inv = __frcp_rn((float)(hcount * (min(ws + 3, p.IW + p.pW) - ws)));
+              float o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = ((c0[j] + c1[j]) + c2[j]) * inv;
+              *reinterpret_cast<uint4*>(p.y + (opix0 + ox) * p.y_cs + p.y_coff + g * 8) = pack8(o);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
   const int items = (oy1 - oy0) * p.OW * cg;
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int g = i % cg;
-    const int r1 = i / cg;
+    const int r1 = (int)__umulhi((uint32_t)i, magic_cg);
+    const int g = i - r1 * cg;
     const int ox = r1 % p.OW;
     const int oy = oy0 + r1 / p.OW;
     int y0 = oy * p.sH - p.pH, x0 = ox * p.sW - p.pW;

@@ -376,13 +376,16 @@ conv_umma_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap t
 //     per TMEM lane quarter split the 16-column chunks between them
 constexpr int kPersistThreads = 320;
 
+// Computes one 16-column chunk of the epilogue for this thread's row.  `raw` (if any) is stored
+// directly; the final value y is written as 32 bytes of bf16 into the warp's staging row at
+// `stage_dst` (shared memory) -- the caller copies staged rows out with row-contiguous 16-byte
+// stores so that every global store instruction covers whole 32-byte sectors.
 __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32_t taddr, int m, bool row_ok, int cg,
                                                int c0, const float* s_bias, const float* s_scale,
-                                               const float* s_shift, bool simple) {
+                                               const float* s_shift, bool simple, uint32_t stage_dst) {
   uint32_t v[16];
   tmem_ld16(taddr, v);
   const int nvalid = p.Cout - cg;
-  if (!(row_ok && nvalid > 0)) return;
   float f[16];
   const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
   const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
@@ -406,8 +409,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32
       f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
       f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
     }
-    if (p.res) load16_bf16_add(p.res + (long long)m * p.res_cs + p.res_coff + cg, f, nvalid);
-    if (p.raw) store16_bf16(p.raw + (long long)m * p.raw_cs + p.raw_coff + cg, f, nvalid);
+    if (row_ok && nvalid > 0) {
+      if (p.res) load16_bf16_add(p.res + (long long)m * p.res_cs + p.res_coff + cg, f, nvalid);
+      if (p.raw) store16_bf16(p.raw + (long long)m * p.raw_cs + p.raw_coff + cg, f, nvalid);
+    }
     if (!p.out) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -422,7 +427,12 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
   }
-  store16_bf16(p.out + (long long)m * p.out_cs + p.out_coff + cg, f, nvalid);
+  const uint32_t w0 = pack_bf16x2(f[0], f[1]), w1 = pack_bf16x2(f[2], f[3]), w2 = pack_bf16x2(f[4], f[5]),
+                 w3 = pack_bf16x2(f[6], f[7]), w4 = pack_bf16x2(f[8], f[9]), w5 = pack_bf16x2(f[10], f[11]),
+                 w6 = pack_bf16x2(f[12], f[13]), w7 = pack_bf16x2(f[14], f[15]);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_dst + 16), "r"(w4), "r"(w5), "r"(w6), "r"(w7)
+               : "memory");
 }
 
 template <int MT>
@@ -451,6 +461,9 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   const uint32_t bar_tmem_full = bar_empty + 8 * S;      // [2]
   const uint32_t bar_tmem_empty = bar_tmem_full + 16;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  // epilogue staging: 8 warps x 32 rows x (epi_group chunks x 32 B + 16 B pad)
+  const uint32_t stage_pitch = (uint32_t)p.epi_group * 32u + 16u;
+  const uint32_t stage_base = smem_u32(bars) + 512u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -589,11 +602,42 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
       tc_fence_after();
 #pragma unroll
       for (int h = 0; h < MT; ++h) {
-        const int m = m0 + h * kBlockM + wq * 32 + lane;
+        const int mrow0 = m0 + h * kBlockM + wq * 32;  // first output position of this warp's 32 rows
+        const int m = mrow0 + lane;
         const bool row_ok = m < p.M;
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols + (uint32_t)(h * BN);
-        for (int c = half; c < chunks; c += 2)
-          epilogue_chunk(p, taddr + (uint32_t)(c * 16), m, row_ok, n0 + c * 16, c * 16, s_bias, s_scale, s_shift, simple);
+        // this warp's contiguous chunk range: the two warps of a lane quarter split the columns in half
+        const int c_begin = half ? (chunks + 1) / 2 : 0;
+        const int c_end = half ? chunks : (chunks + 1) / 2;
+        const uint32_t my_stage = stage_base + (uint32_t)(warp - 2) * 32u * stage_pitch;
+        for (int cgrp = c_begin; cgrp < c_end; cgrp += p.epi_group) {
+          const int gcount = min(p.epi_group, c_end - cgrp);
+          for (int k = 0; k < gcount; ++k) {
+            const int c = cgrp + k;
+            epilogue_chunk(p, taddr + (uint32_t)(c * 16), m, row_ok, n0 + c * 16, c * 16, s_bias, s_scale, s_shift,
+                           simple, my_stage + (uint32_t)lane * stage_pitch + (uint32_t)k * 32u);
+          }
+          if (p.out) {
+            __syncwarp();
+            // copy out: consecutive lanes take consecutive 16-byte pieces of a row -> whole sectors / lines
+            const int ppr = gcount * 2;  // 16-byte pieces per row in this group
+            const int col0 = n0 + cgrp * 16;
+            for (int idx = lane; idx < 32 * ppr; idx += 32) {
+              const int r = idx / ppr;
+              const int piece = idx - r * ppr;
+              const int mm = mrow0 + r;
+              const int col = col0 + piece * 8;
+              if (mm < p.M && col < p.Cout) {
+                uint4 val;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                             : "r"(my_stage + (uint32_t)r * stage_pitch + (uint32_t)piece * 16u));
+                *reinterpret_cast<uint4*>(p.out + (long long)mm * p.out_cs + p.out_coff + col) = val;
+              }
+            }
+            __syncwarp();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -623,7 +667,8 @@ cudaError_t conv_umma_configure() {
 
 cudaError_t launch_conv_umma(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                              cudaStream_t stream) {
-  const size_t smem = conv_smem_bytes(p.block_n, p.stages, p.persistent ? p.m_halves : 1);
+  const size_t smem = conv_smem_bytes(p.block_n, p.stages, p.persistent ? p.m_halves : 1,
+                                      p.persistent ? conv_epi_stage_bytes(p.epi_group) : 0);
   if (p.persistent) {
     const int tile_m = kBlockM * p.m_halves;
     const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.Cout + p.block_n - 1) / p.block_n);

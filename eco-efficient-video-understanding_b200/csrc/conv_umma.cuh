@@ -45,6 +45,7 @@ struct ConvKernelParams {
   int tmem_cols;                     // power of two >= block_n (x2 when persistent: double-buffered accumulator)
   int persistent;                    // 1: conv_umma_persistent_kernel (needs a_mode == A_TMA_IM2COL)
   int m_halves;                      // persistent only: 1 or 2 128-row halves per tile sharing the weight tile
+  int epi_group;                     // persistent only: 16-column chunks staged per copy-out (2 or 4)
   int num_sms;
   // ---- epilogue:  raw = acc + bias (+ res);  y = relu?(raw * scale + shift) ----
   int Cout;
@@ -59,12 +60,13 @@ struct ConvKernelParams {
 };
 
 // dynamic shared memory needed for (block_n, stages)
-inline size_t conv_smem_bytes(int block_n, int stages, int m_halves = 1) {
+inline size_t conv_epi_stage_bytes(int epi_group) { return (size_t)8 * 32 * ((size_t)epi_group * 32 + 16); }
+inline size_t conv_smem_bytes(int block_n, int stages, int m_halves = 1, size_t epi_stage = 0) {
   size_t a = (size_t)stages * kBlockM * 128 * m_halves;
   size_t b = (size_t)stages * block_n * 128;
   size_t epi = 3 * 256 * sizeof(float);
   size_t bars = 64 * 8;
-  return 1024 /*alignment slack*/ + a + b + epi + bars;
+  return 1024 /*alignment slack*/ + a + b + epi + bars + epi_stage;
 }
 
 cudaError_t launch_conv_umma(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,

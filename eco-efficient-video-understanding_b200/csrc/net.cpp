@@ -1228,6 +1228,15 @@ void Net::plan() {
         kp.Cout = c.Cout;
         const int ntiles = (c.Cout + 255) / 256;
         kp.block_n = round_up((c.Cout + ntiles - 1) / ntiles, 16);
+        if (kp.block_n >= 192 && (kp.block_n / 2) % 16 == 0) {
+          // wave quantisation on the persistent grid: halve the N tile when that lowers
+          // ceil(tiles / SMs) * tile_cost (e.g. res5 at batch 64: 196 tiles of 256 -> 392 tiles of 128)
+          auto cost = [&](int bn) {
+            const long long tiles = ((long long)kp.M + kBlockM - 1) / kBlockM * ((c.Cout + bn - 1) / bn);
+            return ((tiles + g_num_sms - 1) / g_num_sms) * (long long)bn;
+          };
+          if (cost(kp.block_n / 2) < cost(kp.block_n)) kp.block_n /= 2;
+        }
         c.Cout_pad = round_up(c.Cout, kp.block_n);
         kp.a_mode = a_mode_ < 0 ? A_TMA_IM2COL : a_mode_;
         kp.num_sms = g_num_sms;
@@ -1268,7 +1277,13 @@ void Net::plan() {
             const long long tiles256 = ((long long)kp.M + 255) / 256 * ((c.Cout + kp.block_n - 1) / kp.block_n);
             if (kp.block_n <= 128 && (dual_m_ == 2 || (dual_m_ == 1 && tiles256 >= 2LL * g_num_sms))) kp.m_halves = 2;
             const size_t stage_bytes = (size_t)kBlockM * 128 * kp.m_halves + (size_t)kp.block_n * 128;
-            kp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (size_t)(200 * 1024) / stage_bytes));
+            // shared memory: 227 KB - alignment slack - constants - barriers; the epilogue staging takes
+            // 4 chunks per copy-out (128-byte row pieces) unless that would cost a pipeline stage
+            const size_t avail = (size_t)227 * 1024 - 1024 - 3 * 1024 - 512;
+            kp.epi_group = 4;
+            size_t st4 = (avail - conv_epi_stage_bytes(4)) / stage_bytes, st2 = (avail - conv_epi_stage_bytes(2)) / stage_bytes;
+            if (st4 < st2 && st4 < 6) kp.epi_group = 2;
+            kp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (avail - conv_epi_stage_bytes(kp.epi_group)) / stage_bytes));
             kp.tmem_cols = pow2_at_least(2 * kp.m_halves * kp.block_n);
           } else {
             const size_t budget = kp.block_n <= 128 ? 100 * 1024 : 200 * 1024;

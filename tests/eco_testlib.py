@@ -17,6 +17,7 @@ TOL_NET = 4e-2    # free-running whole net, per-blob rel-L2.  Calibrated on the 
                   # from itself by rel-L2 4e-4 (inception_3a) .. 1.6e-2 (res5b_bn), 4.4e-3 on fc8, because
                   # rounding-boundary flips of the bf16-stored maps are amplified through 32 conv layers
                   # (DESIGN.md section 4).  The tight statement is the teacher-forced per-layer check.
+TOL_NET_FULL = 1e-1  # ECO-Full is 69 convs deep on the 2-D stream: oracle self-noise reaches 4.2e-2 at inception_5b_output
 TOL_LOGITS = 2e-2 # free-running whole net, logits max|a-b| / max|b| (oracle self-noise: 4.2e-3)
 
 

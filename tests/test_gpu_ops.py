@@ -245,7 +245,7 @@ layer { name: "p_max_hw" type: "Pooling" bottom: "f_bn" top: "p_max_hw" pooling_
 def test_pool_variants(gpu, hw):
     # the 3x3 strip kernel (stride 1/2, pad 0/1, ragged strips, ceil-mode last window) and the generic kernel
     shape = (3, 8) + hw
-    run_case(POOLS % hw, shape, 1, check=("p_max_s2", "p_max_s2p", "p_max_s1p", "p_ave_s1p", "p_ave_s2p", "p_ave_s2",
+    run_case(POOLS % hw, shape, 1, check=("f_bn", "p_max_s2", "p_max_s2p", "p_max_s1p", "p_ave_s1p", "p_ave_s2p", "p_ave_s2",
                                           "p_ave_5", "p_max_hw"))
 
 
