@@ -158,11 +158,8 @@ def main():
     torch.cuda.set_device(local_rank)
     caffe.set_device(local_rank)
     caffe.set_mode_gpu()
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    else:
-        dist = None
+    from dist_util import Group
+    grp = Group("nccl", torch.device("cuda", local_rank))
 
     B, N = a.batch, a.segments
     classes = CLASSES if a.model == "lite" else 400
@@ -183,18 +180,8 @@ def main():
     count = frames.numel()
     torch.cuda.synchronize()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if dist is None:
-            return ms
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    barrier = grp.barrier
+    max_over_ranks = grp.max_over_ranks
 
     # ---------------- value: inputs resident in HBM ----------------
     net.set_input_device("data", frames.data_ptr(), count)
@@ -259,6 +246,7 @@ def main():
                 "share_of_step": conv_ms / max(conv_ms + other_ms, 1e-9)}
 
     if rank != 0:
+        grp.close()
         return
     cpu_baseline = None
     if not a.no_cpu_baseline and world == 1:
@@ -278,6 +266,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "gflop_per_video": GFLOP_PER_VIDEO.get((a.model, N))}
     print(json.dumps(line))
+    grp.close()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,51 @@
+"""The N>1 path on CPU: world_size-2 gloo runs of the helpers bench.py uses under torchrun, and the
+reference arm's contract under torchrun (rank 0 prints one JSON line, the other ranks exit 0 silently)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, os.path.join(%r, "tools"))
+import torch
+from dist_util import Group, shard
+g = Group("gloo")
+lo, hi = shard(7, g.world, g.rank)
+g.barrier()
+mx = g.max_over_ranks(10.0 + g.rank)       # device time per rank -> the slowest rank defines the step
+tot = g.sum_over_ranks(hi - lo)
+print(json.dumps({"rank": g.rank, "world": g.world, "shard": [lo, hi], "max": mx, "total": tot}))
+g.close()
+''' % ROOT
+
+
+def _torchrun(args, timeout=240):
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = "2"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29611"] + args
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+
+
+def test_gloo_world2_shard_barrier_max(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    r = _torchrun([str(script)])
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert sorted(x["rank"] for x in rows) == [0, 1]
+    assert all(x["world"] == 2 and x["max"] == 11.0 and x["total"] == 7.0 for x in rows)
+    assert sorted(tuple(x["shard"]) for x in rows) == [(0, 4), (4, 7)]
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    r = _torchrun(["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--segments", "4"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = lines[0]
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

@@ -1,0 +1,6 @@
+export PYTHONPATH="$PWD:$PWD/tools:$PWD/eco-efficient-video-understanding_b200:$PWD/tests"
+mkdir -p gpurun_out
+timeout 700 bash tools/run_gpu_suite.sh "ops eco" > gpurun_out/trip7_suite.log 2>&1
+grep rc= gpurun_out/trip7_suite.log | tr '\n' ' '
+for b in 32 64; do timeout 300 python bench.py --steps 10 --warmup 3 --batch $b --no-cpu-baseline > gpurun_out/bench7_b$b.log 2>&1; echo "bench b$b rc=$?"; tail -c 900 gpurun_out/bench7_b$b.log; done
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_r01e.csv python bench.py --steps 1 --warmup 1 --batch 32 --no-cpu-baseline --no-graph > gpurun_out/ncu_launches7.log 2>&1; echo "ncu launches rc=$?"
