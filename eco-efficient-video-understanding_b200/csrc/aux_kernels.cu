@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
     }
   }
   const int cg = p.C >> 3;
-  const uint32_t magic_cg = 0xFFFFFFFFu / (uint32_t)cg + 1u;  // i / cg == umulhi(i, magic) for i < 2^16
+  const unsigned long long magic_cg = (1ULL << 32) / (unsigned)cg + 1ULL;  // i / cg == (i * magic) >> 32 for i < 2^16
   if (p.KH == 3 && p.KW == 3 && p.sH == p.sW && (p.sW == 1 || p.sW == 2)) {
     // 3x3 windows: a thread owns a strip of T outputs along x and slides over the input columns once
     constexpr int T = 4;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
     const int strips = (p.OW + T - 1) / T;
     const int items = (oy1 - oy0) * strips * cg;
     for (int i = threadIdx.x; i < items; i += blockDim.x) {
-      const int r1 = (int)__umulhi((uint32_t)i, magic_cg);
+      const int r1 = (int)(((unsigned long long)(unsigned)i * magic_cg) >> 32);
       const int g = i - r1 * cg;
       const int rowi = r1 / strips;
       const int xs = r1 - rowi * strips;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
   }
   const int items = (oy1 - oy0) * p.OW * cg;
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int r1 = (int)__umulhi((uint32_t)i, magic_cg);
+    const int r1 = (int)(((unsigned long long)(unsigned)i * magic_cg) >> 32);
     const int g = i - r1 * cg;
     const int ox = r1 % p.OW;
     const int oy = oy0 + r1 / p.OW;

@@ -427,6 +427,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
   }
+  if (!p.epi_staged) {
+    if (row_ok && nvalid > 0) store16_bf16(p.out + (long long)m * p.out_cs + p.out_coff + cg, f, nvalid);
+    return;
+  }
   const uint32_t w0 = pack_bf16x2(f[0], f[1]), w1 = pack_bf16x2(f[2], f[3]), w2 = pack_bf16x2(f[4], f[5]),
                  w3 = pack_bf16x2(f[6], f[7]), w4 = pack_bf16x2(f[8], f[9]), w5 = pack_bf16x2(f[10], f[11]),
                  w6 = pack_bf16x2(f[12], f[13]), w7 = pack_bf16x2(f[14], f[15]);
@@ -617,7 +621,7 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
             epilogue_chunk(p, taddr + (uint32_t)(c * 16), m, row_ok, n0 + c * 16, c * 16, s_bias, s_scale, s_shift,
                            simple, my_stage + (uint32_t)lane * stage_pitch + (uint32_t)k * 32u);
           }
-          if (p.out) {
+          if (p.out && p.epi_staged) {
             __syncwarp();
             // copy out: consecutive lanes take consecutive 16-byte pieces of a row -> whole sectors / lines
             const int ppr = gcount * 2;  // 16-byte pieces per row in this group

@@ -525,6 +525,7 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "a_mode") a_mode_ = v;
   else if (key == "use_graph") use_graph_ = v != 0;
   else if (key == "persistent") persistent_ = v != 0;
+  else if (key == "epi_staged") epi_staged_ = v != 0;
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
   else ECO_CHECK(false, "unknown option '" << key << "'");
   free_plan();
@@ -1281,6 +1282,7 @@ void Net::plan() {
             // 4 chunks per copy-out (128-byte row pieces) unless that would cost a pipeline stage
             const size_t avail = (size_t)227 * 1024 - 1024 - 3 * 1024 - 512;
             kp.epi_group = 4;
+            kp.epi_staged = epi_staged_ ? 1 : 0;
             size_t st4 = (avail - conv_epi_stage_bytes(4)) / stage_bytes, st2 = (avail - conv_epi_stage_bytes(2)) / stage_bytes;
             if (st4 < st2 && st4 < 6) kp.epi_group = 2;
             kp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (avail - conv_epi_stage_bytes(kp.epi_group)) / stage_bytes));

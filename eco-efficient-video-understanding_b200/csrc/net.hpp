@@ -195,6 +195,7 @@ class Net {
   bool use_graph_ = false;
   bool persistent_ = true;
   int dual_m_ = 1;
+  bool epi_staged_ = true;
   bool user_stream_ = false;
   // plan
   bool planned_ = false;
