@@ -66,6 +66,10 @@ def lib():
     L.eco_blob_host_diff.argtypes = L.eco_blob_host_data.argtypes
     L.eco_net_set_input_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.eco_blob_device_f32.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.eco_net_forward_pipelined.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+    L.eco_net_wait.argtypes = [C.c_void_p, C.c_int]
+    L.eco_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.eco_host_free.argtypes = [C.c_void_p]
     L.eco_net_last_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.eco_net_profile_forward.argtypes = [C.c_void_p, C.POINTER(OpTime), C.c_int, C.POINTER(C.c_int)]
     L.eco_device_count.argtypes = [C.POINTER(C.c_int)]

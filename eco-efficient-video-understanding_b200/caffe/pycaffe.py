@@ -195,6 +195,17 @@ class Net(object):
         check(lib().eco_blob_device_f32(self._h, self._blob_names.index(blob_name), C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def forward_pipelined(self, host_in_ptr, count, host_out_ptr, out_count):
+        """Serving extension: enqueue a forward fed from (pinned) host memory, results to host memory;
+        returns a ticket for wait().  The H2D copy of call k+1 overlaps the compute of call k."""
+        t = C.c_int()
+        check(lib().eco_net_forward_pipelined(self._h, C.c_void_p(int(host_in_ptr)), int(count),
+                                              C.c_void_p(int(host_out_ptr)), int(out_count), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        check(lib().eco_net_wait(self._h, int(ticket)))
+
     def last_launch_count(self):
         n = C.c_int()
         check(lib().eco_net_last_launch_count(self._h, C.byref(n)))

@@ -272,6 +272,31 @@ int eco_blob_device_f32(eco_net* net, int blob, const float** dev, size_t* count
   *dev = N(net).device_f32(blob, count);
   ECO_API_END
 }
+int eco_net_forward_pipelined(eco_net* net, const float* host_in, size_t count, float* host_out, size_t out_count,
+                              int* ticket) {
+  ECO_API_BEGIN
+  if (!g_mode_gpu) throw std::runtime_error("set_mode_cpu() was requested: libeco_b200 has no CPU execution path");
+  const int t = N(net).forward_pipelined(host_in, count, host_out, out_count);
+  if (ticket) *ticket = t;
+  ECO_API_END
+}
+int eco_net_wait(eco_net* net, int ticket) {
+  ECO_API_BEGIN
+  N(net).wait_ticket(ticket);
+  ECO_API_END
+}
+int eco_host_alloc(void** ptr, size_t bytes) {
+  ECO_API_BEGIN
+  if (!ptr) throw std::runtime_error("null argument");
+  cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 16);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("cudaMallocHost failed: ") + cudaGetErrorString(e));
+  ECO_API_END
+}
+int eco_host_free(void* ptr) {
+  ECO_API_BEGIN
+  if (ptr) cudaFreeHost(ptr);
+  ECO_API_END
+}
 int eco_net_last_launch_count(const eco_net* net, int* launches) {
   ECO_API_BEGIN
   *launches = N(net).last_launches();

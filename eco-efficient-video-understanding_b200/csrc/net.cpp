@@ -614,6 +614,19 @@ void Net::free_plan() {
     graph_exec_ = nullptr;
   }
   graph_valid_ = false;
+  if (copy_stream_) {
+    cudaStreamSynchronize(copy_stream_);
+    cudaStreamDestroy(copy_stream_);
+    copy_stream_ = nullptr;
+    for (int i = 0; i < 2; ++i) {
+      if (ev_h2d_[i]) cudaEventDestroy(ev_h2d_[i]);
+      if (ev_slot_free_[i]) cudaEventDestroy(ev_slot_free_[i]);
+      if (ev_done_[i]) cudaEventDestroy(ev_done_[i]);
+      ev_h2d_[i] = ev_slot_free_[i] = ev_done_[i] = nullptr;
+      pipe_slot_[i] = nullptr;
+    }
+    pipe_iter_ = 0;
+  }
   if (!allocs_.empty()) {
     if (stream_) cudaStreamSynchronize(stream_);
     for (void* p : allocs_) cudaFree(p);
@@ -1586,26 +1599,31 @@ void Net::sync() {
 }
 
 // =====================================================================================
-void Net::run_op(Op& op) {
+// fp32 NCHW net input -> bf16 operand of the first convolution (space-to-depth cells for the 7x7 stem,
+// channel-padded channels-last otherwise).  `src` overrides the input blob's device buffer (pipelined
+// forward reads straight from a staging slot).
+void Net::run_input_xform(ConvOp& c, const float* src) {
+  Tensor& x = tensors_[c.in_tensor];
+  const float* in = src ? src : static_cast<const float*>(x.dev);
+  if (c.stem) {
+    CUDA_OK(launch_stem_s2d(in, c.stem_in, c.NB, c.I[1], c.I[2], c.stem_CH, c.stem_CW, stream_));
+  } else {
+    ClView v;
+    v.ptr = c.stem_in;
+    v.outer = c.NB;
+    v.inner = (long long)c.I[0] * c.I[1] * c.I[2];
+    v.C = c.Cin;
+    v.cs = c.Cin_k;
+    v.coff = 0;
+    CUDA_OK(launch_f32_to_cl(in, v, stream_));
+  }
+}
+
+void Net::run_op(Op& op, bool with_xform) {
   switch (op.type) {
     case Op::CONV: {
       ConvOp& c = convs_[op.conv];
-      if (c.stem_in) {
-        Tensor& x = tensors_[c.in_tensor];
-        if (c.stem) {
-          CUDA_OK(launch_stem_s2d(static_cast<const float*>(x.dev), c.stem_in, c.NB, c.I[1], c.I[2], c.stem_CH,
-                                  c.stem_CW, stream_));
-        } else {
-          ClView v;
-          v.ptr = c.stem_in;
-          v.outer = c.NB;
-          v.inner = (long long)c.I[0] * c.I[1] * c.I[2];
-          v.C = c.Cin;
-          v.cs = c.Cin_k;
-          v.coff = 0;
-          CUDA_OK(launch_f32_to_cl(static_cast<const float*>(x.dev), v, stream_));
-        }
-      }
+      if (c.stem_in && with_xform) run_input_xform(c, nullptr);
       CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.tmB, stream_));
       if (c.out_tensor >= 0) mark_written(c.out_tensor);
       if (c.raw_tensor >= 0) mark_written(c.raw_tensor);
@@ -1660,6 +1678,95 @@ void Net::mark_written(int tid) {
     if (t.root == root && t.materialized) t.dev_newer = true;
 }
 
+// Runs the planned ops on stream_.  Full forwards may replay a CUDA graph; the input transforms stay
+// outside the graph so their source pointer can change from call to call.
+void Net::run_ops(bool full, int lo, int hi, const float* input_override, int* launches) {
+  int n = 0;
+  if (full && use_graph_) {
+    for (auto& op : ops_)
+      if (op.type == Op::CONV && convs_[op.conv].stem_in) run_input_xform(convs_[op.conv], input_override);
+    if (!graph_valid_) {
+      cudaGraph_t g = nullptr;
+      CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+      for (auto& op : ops_) run_op(op, false);
+      CUDA_OK(cudaStreamEndCapture(stream_, &g));
+      if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+      CUDA_OK(cudaGraphInstantiate(&graph_exec_, g, 0));
+      cudaGraphDestroy(g);
+      graph_valid_ = true;
+    } else {
+      std::vector<char> is_input(tensors_.size(), 0);
+      for (int vb : inputs_) is_input[vis_blobs_[vb].tensor] = 1;
+      for (size_t i = 0; i < tensors_.size(); ++i)
+        if (tensors_[i].materialized && !is_input[i]) tensors_[i].dev_newer = true;
+    }
+    for (auto& op : ops_) n += op.launches;
+    CUDA_OK(cudaGraphLaunch(graph_exec_, stream_));
+  } else {
+    for (auto& op : ops_) {
+      if (!full && (op.last_layer < lo || op.first_layer > hi)) continue;
+      if (op.type == Op::CONV && convs_[op.conv].stem_in) {
+        run_input_xform(convs_[op.conv], input_override);
+        run_op(op, false);
+      } else {
+        run_op(op, true);
+      }
+      n += op.launches;
+    }
+  }
+  if (launches) *launches = n;
+}
+
+// Serving extension (not in caffe): overlap the host->device copy of clip k+1 with the compute of clip k.
+// The caller owns two (pinned) input buffers and alternates them; results are copied to `host_out`
+// asynchronously and are valid after wait_ticket().
+int Net::forward_pipelined(const float* host_in, size_t count, float* host_out, size_t out_count) {
+  if (!planned_) plan();
+  upload_params();
+  ECO_CHECK(inputs_.size() >= 1 && outputs_.size() >= 1, "forward_pipelined needs one input and one output blob");
+  Tensor& tin = tensors_[vis_blobs_[inputs_[0]].tensor];
+  Tensor& tout = tensors_[vis_blobs_[outputs_[0]].tensor];
+  ECO_CHECK(tin.kind == Kind::F32 && count == (size_t)tin.count(), "forward_pipelined: input size mismatch");
+  ECO_CHECK(tout.kind == Kind::F32 && tout.dev && out_count == (size_t)tout.count(), "forward_pipelined: output size mismatch");
+  if (!copy_stream_) {
+    CUDA_OK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      pipe_slot_[i] = static_cast<float*>(dalloc(count * 4, false));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_h2d_[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_slot_free_[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_done_[i], cudaEventDisableTiming));
+    }
+  }
+  const int slot = (int)(pipe_iter_ & 1);
+  if (pipe_iter_ >= 2) CUDA_OK(cudaStreamWaitEvent(copy_stream_, ev_slot_free_[slot], 0));
+  CUDA_OK(cudaMemcpyAsync(pipe_slot_[slot], host_in, count * 4, cudaMemcpyHostToDevice, copy_stream_));
+  CUDA_OK(cudaEventRecord(ev_h2d_[slot], copy_stream_));
+  CUDA_OK(cudaStreamWaitEvent(stream_, ev_h2d_[slot], 0));
+  bool xform_only_input = false;
+  for (auto& op : ops_)
+    if (op.type == Op::CONV && convs_[op.conv].stem_in && convs_[op.conv].in_tensor == vis_blobs_[inputs_[0]].tensor)
+      xform_only_input = true;
+  ECO_CHECK(xform_only_input, "forward_pipelined: the net input must feed a convolution directly");
+  int launches = 0;
+  if (use_graph_) {
+    run_ops(true, 0, 0, pipe_slot_[slot], &launches);  // transforms read the slot, graph covers the rest
+  } else {
+    run_ops(true, 0, 0, pipe_slot_[slot], &launches);
+  }
+  // the slot is free once the transform has consumed it; conservatively: once this forward is enqueued
+  // up to here the transform is the first kernel, so record right after the whole enqueue is cheap too
+  CUDA_OK(cudaEventRecord(ev_slot_free_[slot], stream_));
+  CUDA_OK(cudaMemcpyAsync(host_out, tout.dev, out_count * 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaEventRecord(ev_done_[slot], stream_));
+  last_launches_ = launches;
+  return (int)(pipe_iter_++ & 0x7fffffff);
+}
+
+void Net::wait_ticket(int ticket) {
+  ECO_CHECK(copy_stream_ != nullptr, "wait_ticket without forward_pipelined");
+  CUDA_OK(cudaEventSynchronize(ev_done_[ticket & 1]));
+}
+
 float Net::forward(int start, int end) {
   if (!planned_) plan();
   upload_params();
@@ -1684,34 +1791,7 @@ float Net::forward(int start, int end) {
   for (int vb : inputs_) tensors_[vis_blobs_[vb].tensor].dev_newer = false;
 
   int launches = 0;
-  auto run_range = [&]() {
-    for (auto& op : ops_) {
-      if (!full && (op.last_layer < lo || op.first_layer > hi)) continue;
-      run_op(op);
-      launches += op.launches;
-    }
-  };
-  if (full && use_graph_) {
-    if (!graph_valid_) {
-      cudaGraph_t g = nullptr;
-      CUDA_OK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
-      run_range();
-      CUDA_OK(cudaStreamEndCapture(stream_, &g));
-      if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
-      CUDA_OK(cudaGraphInstantiate(&graph_exec_, g, 0));
-      cudaGraphDestroy(g);
-      graph_valid_ = true;
-    } else {
-      for (auto& op : ops_) launches += op.launches;
-      std::vector<char> is_input(tensors_.size(), 0);
-      for (int vb : inputs_) is_input[vis_blobs_[vb].tensor] = 1;
-      for (size_t i = 0; i < tensors_.size(); ++i)
-        if (tensors_[i].materialized && !is_input[i]) tensors_[i].dev_newer = true;
-    }
-    CUDA_OK(cudaGraphLaunch(graph_exec_, stream_));
-  } else {
-    run_range();
-  }
+  run_ops(full, lo, hi, nullptr, &launches);
   last_launches_ = launches;
   return 0.f;
 }

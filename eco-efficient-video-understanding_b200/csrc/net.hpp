@@ -171,6 +171,8 @@ class Net {
   void reshape_blob(int vis_blob, const std::vector<int>& dims);
   void reshape();
   float forward(int start, int end);
+  int forward_pipelined(const float* host_in, size_t count, float* host_out, size_t out_count);
+  void wait_ticket(int ticket);
   void sync();
   float* host_data(int vis_blob, bool for_write, size_t* count);
   float* host_diff(int vis_blob, bool for_write, size_t* count);
@@ -209,6 +211,11 @@ class Net {
   cudaGraphExec_t graph_exec_ = nullptr;
   bool graph_valid_ = false;
   std::vector<std::string> op_names_;
+  // pipelined serving path
+  cudaStream_t copy_stream_ = nullptr;
+  float* pipe_slot_[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d_[2] = {nullptr, nullptr}, ev_slot_free_[2] = {nullptr, nullptr}, ev_done_[2] = {nullptr, nullptr};
+  unsigned long long pipe_iter_ = 0;
 
   void build_graph();
   void init_params();
@@ -217,7 +224,9 @@ class Net {
   void free_plan();
   void upload_params();
   void upload_dirty_inputs(int first_op);
-  void run_op(Op& op);
+  void run_op(Op& op, bool with_xform = true);
+  void run_input_xform(ConvOp& c, const float* src);
+  void run_ops(bool full, int lo, int hi, const float* input_override, int* launches);
   void mark_written(int tensor);
   void ensure_device();
   void* dalloc(size_t bytes, bool zero);

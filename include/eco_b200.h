@@ -107,6 +107,17 @@ int eco_net_set_input_device(eco_net* net, int blob, const void* dev_f32, size_t
 /* device pointer of a plain fp32 blob (e.g. fc8) valid until reshape; NULL/err for fused-away blobs */
 int eco_blob_device_f32(eco_net* net, int blob, const float** dev, size_t* count);
 
+/* pipelined serving: enqueue one forward whose input comes from `host_in` (fp32, caffe layout; use pinned
+ * memory, e.g. eco_host_alloc, for a truly asynchronous copy) and whose first output blob is copied to
+ * `host_out`; returns at once with a ticket.  The copy of call k+1 overlaps the compute of call k; the
+ * caller must not touch host_in/host_out of a call until eco_net_wait(ticket) returned, and alternates
+ * two buffer pairs. */
+int eco_net_forward_pipelined(eco_net* net, const float* host_in, size_t count, float* host_out, size_t out_count,
+                              int* ticket);
+int eco_net_wait(eco_net* net, int ticket);
+int eco_host_alloc(void** ptr, size_t bytes);   /* page-locked host memory */
+int eco_host_free(void* ptr);
+
 /* ---- measurement hooks used by bench.py ---- */
 /* number of kernels this library launched for the last eco_net_forward on this net */
 int eco_net_last_launch_count(const eco_net* net, int* launches);

@@ -129,3 +129,49 @@ def test_eco_lite_n16_properties(gpu):
     assert d.shape == (1, 101)
     assert np.array_equal(d[0], a[0])
     assert np.isfinite(a).all() and a.std() > 1e-3
+
+
+def test_pipelined_forward_matches_blocking_forward(gpu):
+    """eco_net_forward_pipelined (copy of clip k+1 overlapping compute of clip k, two buffer pairs)
+    returns exactly what the caffe-style blocking forward returns, for a stream of different clips."""
+    import ctypes
+    import caffe
+    from caffe import _caffe
+    segments, batch = 4, 2
+    txt, ref, x = oracle_lite(segments, batch)
+    for graph in (False, True):
+        net = make_net(txt, keep_all=False, graph=graph)
+        load_params(net, ref.params_dict())
+        clips = [np.roll(x, k, axis=0) * (1.0 + 0.1 * k) for k in range(5)]
+        want = []
+        for c in clips:
+            net.blobs["data"].data[...] = c
+            want.append(net.forward()["fc8"].copy())
+        count, ocount = x.size, batch * 101
+        bufs = []
+        for _ in range(2):
+            pi, po = ctypes.c_void_p(), ctypes.c_void_p()
+            _caffe.check(_caffe.lib().eco_host_alloc(ctypes.byref(pi), count * 4))
+            _caffe.check(_caffe.lib().eco_host_alloc(ctypes.byref(po), ocount * 4))
+            bufs.append((pi, po,
+                         np.ctypeslib.as_array(ctypes.cast(pi, ctypes.POINTER(ctypes.c_float)), (count,)),
+                         np.ctypeslib.as_array(ctypes.cast(po, ctypes.POINTER(ctypes.c_float)), (ocount,))))
+        tickets, got = [None, None], [None] * len(clips)
+        owner = [None, None]
+        for k, c in enumerate(clips):
+            s_ = k & 1
+            if tickets[s_] is not None:
+                net.wait(tickets[s_])
+                got[owner[s_]] = bufs[s_][3].copy().reshape(batch, 101)
+            bufs[s_][2][:] = c.ravel()
+            tickets[s_] = net.forward_pipelined(bufs[s_][0].value, count, bufs[s_][1].value, ocount)
+            owner[s_] = k
+        for s_ in (0, 1):
+            if tickets[s_] is not None:
+                net.wait(tickets[s_])
+                got[owner[s_]] = bufs[s_][3].copy().reshape(batch, 101)
+        for k in range(len(clips)):
+            assert np.array_equal(got[k], want[k]), "clip %d (graph=%s)" % (k, graph)
+        for pi, po, _, _ in bufs:
+            _caffe.lib().eco_host_free(pi)
+            _caffe.lib().eco_host_free(po)
