@@ -524,7 +524,7 @@ void Net::set_option(const std::string& key, int v) {
   if (key == "keep_all_blobs") keep_all_ = v != 0;
   else if (key == "a_mode") a_mode_ = v;
   else if (key == "use_graph") use_graph_ = v != 0;
-  else if (key == "persistent") persistent_ = v != 0;
+  else if (key == "persistent") persistent_ = v;  // 0 never, 1 auto (per layer), 2 always
   else if (key == "epi_staged") epi_staged_ = v != 0;
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
   else ECO_CHECK(false, "unknown option '" << key << "'");
@@ -1048,7 +1048,14 @@ void Net::plan() {
     for (size_t j = 0; j < L.bottoms.size(); ++j) {
       Tensor& b = tensors_[L.bottoms[j]];
       const int width = top.kind == Kind::CL ? b.C() : 0;
-      bool can_alias = top.kind == Kind::CL && b.consumers.size() == 1 && b.materialized && view_of[L.bottoms[j]] < 0 &&
+      // readers other than layers that rewrite the blob in place (the fused ReLU after a BN)
+      int readers = 0;
+      for (int ci : b.consumers) {
+        const OrigLayer& Lc = layers_[ci];
+        const bool inplace = Lc.tops.size() == 1 && Lc.bottoms.size() == 1 && Lc.tops[0] == L.bottoms[j];
+        if (!inplace) ++readers;
+      }
+      bool can_alias = top.kind == Kind::CL && readers == 1 && b.materialized && view_of[L.bottoms[j]] < 0 &&
                        !aliased[L.bottoms[j]] && b.producer >= 0 && !is_data_layer(layers_[b.producer].type) &&
                        layers_[b.producer].type != "Concat" && (off % 8 == 0);
       // a tensor that other tensors view must keep its own buffer
@@ -1283,6 +1290,9 @@ void Net::plan() {
         {
           const size_t per_stage = (size_t)kBlockM * 128 + (size_t)kp.block_n * 128;
           kp.persistent = (persistent_ && kp.a_mode == A_TMA_IM2COL) ? 1 : 0;
+          // measured A/B (tools/ab_bench.py, B=32): long-K layers with >= 128-wide tiles (the 3-D head) run
+          // 5-15% faster as one-tile CTAs, two per SM, than as a single persistent CTA per SM
+          if (persistent_ == 1 && kp.persistent && kp.num_kb >= 48 && kp.block_n >= 128) kp.persistent = 0;
           kp.m_halves = 1;
           if (kp.persistent) {
             // one CTA per SM: deep ring, double-buffered accumulator (2 x m_halves x block_n TMEM columns).

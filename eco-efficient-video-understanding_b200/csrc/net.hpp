@@ -195,7 +195,7 @@ class Net {
   bool keep_all_ = false;
   int a_mode_ = -1;
   bool use_graph_ = false;
-  bool persistent_ = true;
+  int persistent_ = 1;
   int dual_m_ = 1;
   bool epi_staged_ = true;
   bool user_stream_ = false;

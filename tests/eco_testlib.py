@@ -24,7 +24,7 @@ TOL_LOGITS = 2e-2 # free-running whole net, logits max|a-b| / max|b| (oracle sel
 def make_net(text, keep_all=True, a_mode=None, graph=False, persistent=True, dual_m=1):
     import caffe
     opts = {"keep_all_blobs": 1 if keep_all else 0, "use_graph": 1 if graph else 0,
-            "persistent": 1 if persistent else 0, "dual_m": dual_m}
+            "persistent": 2 if persistent else 0, "dual_m": dual_m}
     if a_mode is not None:
         opts["a_mode"] = a_mode
     return caffe.Net.from_string(text, caffe.TEST, **opts)

@@ -67,6 +67,7 @@ def test_eco_lite_n4_fast_plan_matches(gpu, graph):
     txt, ref, x = oracle_lite(4, 2)
     want = ref.forward(x, bf16=True)["fc8"]
     net = make_net(txt, keep_all=False, graph=graph)
+    net.set_option("persistent", 1)   # production default: per-layer choice between the two conv kernels
     load_params(net, ref.params_dict())
     for _ in range(3):
         net.blobs["data"].data[...] = x
