@@ -659,6 +659,196 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Halo-resident 2-D convolution, stride 1 (3x3 / 4x4 / ... filters).
+//   tile   = R output rows x OW columns of one image, enumerated on the padded-width grid
+//            (position i = r*pw + c, pw = OW + KW - 1; columns c >= OW are discarded in the epilogue),
+//            MT x 128 positions per tile
+//   A      = the (R+KH-1) x pw input patch of a 64-channel block, fetched ONCE by a tiled TMA load with
+//            zero fill for the border, 128-byte swizzled rows.  Tap (ky,kx) is the same patch read
+//            through a descriptor whose start address is shifted by (ky*pw + kx) rows: the 128-byte
+//            swizzle is a function of the absolute shared-memory address, so a row-shifted view is a
+//            valid K-major operand (checked on hardware by tools/probe_umma_shift.cu)
+//   B      = weights [Cout][tap][64] K-major, one TMA tile per (tap, channel block), own ring
+//   rest   = as conv_umma_persistent_kernel: TMEM double buffer, 8 epilogue warps
+template <int MT>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const int SA = p.a_stages, SB = p.b_stages, BN = p.block_n;
+  const uint32_t b_stage_bytes = (uint32_t)BN * 128;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + SA * p.a_stage_bytes;
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)SA * p.a_stage_bytes + (size_t)SB * b_stage_bytes);
+  float* s_scale = s_bias + 256;
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  const uint32_t bar_a_full = smem_u32(bars);
+  const uint32_t bar_a_empty = bar_a_full + 8 * SA;
+  const uint32_t bar_b_full = bar_a_empty + 8 * SA;
+  const uint32_t bar_b_empty = bar_b_full + 8 * SB;
+  const uint32_t bar_tmem_full = bar_b_empty + 8 * SB;
+  const uint32_t bar_tmem_empty = bar_tmem_full + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles_n = (p.Cout + BN - 1) / BN;
+  const int total_tiles = p.NB * p.bands * n_tiles_n;
+  const int taps = p.KH * p.KW;
+  const uint32_t acc_cols = (uint32_t)(MT * BN);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(bar_a_full + 8 * s, 1); mbar_init(bar_a_empty + 8 * s, 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tmem_full + 8 * b, 1); mbar_init(bar_tmem_empty + 8 * b, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: patches and weight tiles =====================
+    if (lane == 0) {
+      uint32_t ia = 0, ib = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n0 = (t % n_tiles_n) * BN;
+        const int tb = t / n_tiles_n;
+        const int band = tb % p.bands, n = tb / p.bands;
+        const int y0 = band * p.R;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          {
+            const uint32_t s = ia % (uint32_t)SA, ph = (ia / (uint32_t)SA) & 1u;
+            mbar_wait(bar_a_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
+            mbar_arrive_expect_tx(bar_a_full + 8 * s, p.a_tx_bytes);
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(sA + s * p.a_stage_bytes), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_a_full + 8 * s),
+                "r"(cb * kBlockK), "r"(-p.pW), "r"(y0 - p.pH), "r"(n)
+                : "memory");
+            ++ia;
+          }
+          for (int tap = 0; tap < taps; ++tap, ++ib) {
+            const uint32_t s = ib % (uint32_t)SB, ph = (ib / (uint32_t)SB) & 1u;
+            mbar_wait(bar_b_empty + 8 * s, ph ^ 1u, p.error_flag, 6);
+            mbar_arrive_expect_tx(bar_b_full + 8 * s, b_stage_bytes);
+            tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_b_full + 8 * s, (tap * p.cblocks + cb) * kBlockK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      uint32_t ia = 0, ib = 0, tile_iter = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+        const uint32_t buf = tile_iter & 1u, use = tile_iter >> 1;
+        mbar_wait(bar_tmem_empty + 8 * buf, (use & 1u) ^ 1u, p.error_flag, 5);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * acc_cols;
+        uint32_t first = 1;
+        for (int cb = 0; cb < p.cblocks; ++cb, ++ia) {
+          const uint32_t sa = ia % (uint32_t)SA, pha = (ia / (uint32_t)SA) & 1u;
+          mbar_wait(bar_a_full + 8 * sa, pha, p.error_flag, 2);
+          tc_fence_after();
+          const uint32_t patch = sA + sa * p.a_stage_bytes;
+          int ky = 0, kx = 0;
+          for (int tap = 0; tap < taps; ++tap, ++ib) {
+            const uint32_t sb = ib % (uint32_t)SB, phb = (ib / (uint32_t)SB) & 1u;
+            mbar_wait(bar_b_full + 8 * sb, phb, p.error_flag, 7);
+            tc_fence_after();
+            const uint64_t bdesc = make_sw128_desc(sB + sb * b_stage_bytes);
+            const uint32_t a0 = patch + (uint32_t)(ky * p.pw + kx) * 128u;  // tap = row shift of the patch
+#pragma unroll
+            for (int h = 0; h < MT; ++h) {
+              const uint64_t adesc = make_sw128_desc(a0 + (uint32_t)h * (kBlockM * 128u));
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                umma_bf16(acc + (uint32_t)(h * BN), adesc + 2 * k, bdesc + 2 * k, idesc, first ? (uint32_t)(k != 0) : 1u);
+              }
+            }
+            first = 0;
+            umma_commit(bar_b_empty + 8 * sb);
+            if (++kx == p.KW) { kx = 0; ++ky; }
+          }
+          umma_commit(bar_a_empty + 8 * sa);
+        }
+        umma_commit(bar_tmem_full + 8 * buf);
+      }
+    }
+  } else {
+    // ===================== epilogue warps (8) =====================
+    const int wq = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int chunks = BN >> 4;
+    const bool simple = (p.res == nullptr) && (p.raw == nullptr) && (p.out != nullptr);
+    ConvKernelParams ep{};  // the fields epilogue_chunk reads
+    ep.Cout = p.Cout; ep.relu = p.relu; ep.out = p.out; ep.out_cs = p.out_cs; ep.out_coff = p.out_coff;
+    ep.raw = p.raw; ep.raw_cs = p.raw_cs; ep.raw_coff = p.raw_coff; ep.res = p.res; ep.res_cs = p.res_cs;
+    ep.res_coff = p.res_coff; ep.epi_staged = 0; ep.scale = p.scale;
+    uint32_t tile_iter = 0;
+    int loaded_n0 = -1;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+      const int n0 = (t % n_tiles_n) * BN;
+      const int tb = t / n_tiles_n;
+      const int band = tb % p.bands, n = tb / p.bands;
+      const int y0 = band * p.R;
+      if (n0 != loaded_n0) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = threadIdx.x - 64; i < BN; i += 256) {
+          const int c = n0 + i;
+          const bool ok = c < p.Cout;
+          const float bi = (ok && p.bias) ? p.bias[c] : 0.f;
+          const float sc = (ok && p.scale) ? p.scale[c] : 1.f;
+          const float sh = (ok && p.scale) ? p.shift[c] : 0.f;
+          s_bias[i] = bi; s_scale[i] = sc; s_shift[i] = simple ? fmaf(bi, sc, sh) : sh;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        loaded_n0 = n0;
+      }
+      const uint32_t buf = tile_iter & 1u, use = tile_iter >> 1;
+      mbar_wait(bar_tmem_full + 8 * buf, use & 1u, p.error_flag, 4);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < MT; ++h) {
+        const int pos = h * kBlockM + wq * 32 + lane;   // position on the padded-width grid
+        const int r = pos / p.pw, c = pos - r * p.pw;
+        const bool row_ok = (r < p.R) && (c < p.OW) && (y0 + r < p.OH);
+        const int m = ((n * p.OH) + y0 + r) * p.OW + c;
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols + (uint32_t)(h * BN);
+        const int c_begin = half ? (chunks + 1) / 2 : 0;
+        const int c_end = half ? chunks : (chunks + 1) / 2;
+        for (int cc = c_begin; cc < c_end; ++cc)
+          epilogue_chunk(ep, taddr + (uint32_t)(cc * 16), m, row_ok, n0 + cc * 16, cc * 16, s_bias, s_scale, s_shift,
+                         simple, 0u);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tmem_empty + 8 * buf) : "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
 }  // namespace
 
 cudaError_t conv_umma_configure() {
@@ -666,7 +856,21 @@ cudaError_t conv_umma_configure() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_umma_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_conv_halo(const HaloKernelParams& p, int m_halves, const CUtensorMap& tmX, const CUtensorMap& tmB,
+                             cudaStream_t stream) {
+  const int tiles = p.NB * p.bands * ((p.Cout + p.block_n - 1) / p.block_n);
+  const int grid = tiles < p.num_sms ? tiles : p.num_sms;
+  const size_t smem = halo_smem_bytes(p);
+  if (m_halves == 2) conv_halo_kernel<2><<<grid, kPersistThreads, smem, stream>>>(p, tmX, tmB);
+  else conv_halo_kernel<1><<<grid, kPersistThreads, smem, stream>>>(p, tmX, tmB);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_conv_umma(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,

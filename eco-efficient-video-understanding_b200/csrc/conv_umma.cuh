@@ -60,6 +60,33 @@ struct ConvKernelParams {
   int* error_flag;                   // set non-zero if an mbarrier wait times out
 };
 
+// ---- halo-resident 2-D convolution (stride 1): the input patch of a tile is loaded ONCE and every
+// filter tap reads it through a row-shifted UMMA descriptor (no per-tap im2col traffic) ----
+struct HaloKernelParams {
+  int NB, OH, OW;            // output grid
+  int KH, KW, pH, pW;
+  int pw;                    // patch width  = OW + KW - 1 (output positions are enumerated on this padded grid)
+  int R;                     // output rows per tile
+  int bands;                 // ceil(OH / R)
+  int cblocks;               // ceil(Cin / 64)
+  int block_n, Cout;
+  int a_stages, b_stages;
+  uint32_t a_stage_bytes;    // allocated bytes per A patch slot (patch + over-read slack, 1024-aligned)
+  uint32_t a_tx_bytes;       // bytes one patch load delivers = 128 * pw * (R + KH - 1)
+  int tmem_cols, num_sms;
+  const float* bias; const float* scale; const float* shift;
+  int relu;
+  __nv_bfloat16* out;   long long out_cs;  int out_coff;
+  __nv_bfloat16* raw;   long long raw_cs;  int raw_coff;
+  const __nv_bfloat16* res; long long res_cs; int res_coff;
+  int* error_flag;
+};
+inline size_t halo_smem_bytes(const HaloKernelParams& p) {
+  return 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.block_n * 128 + 3 * 256 * sizeof(float) + 512;
+}
+cudaError_t launch_conv_halo(const HaloKernelParams& p, int m_halves, const CUtensorMap& tmX, const CUtensorMap& tmB,
+                             cudaStream_t stream);
+
 // dynamic shared memory needed for (block_n, stages)
 inline size_t conv_epi_stage_bytes(int epi_group) { return (size_t)8 * 32 * ((size_t)epi_group * 32 + 16); }
 inline size_t conv_smem_bytes(int block_n, int stages, int m_halves = 1, size_t epi_stage = 0) {

@@ -89,6 +89,7 @@ void HostBuf::resize(size_t count, bool try_pin) {
 }
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static int pow2_at_least(int v);
 
 static bool is_data_layer(const std::string& t) {
   return t == "VideoData" || t == "Data" || t == "ImageData" || t == "MemoryData" || t == "Input" ||
@@ -526,6 +527,7 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "use_graph") use_graph_ = v != 0;
   else if (key == "persistent") persistent_ = v;  // 0 never, 1 auto (per layer), 2 always
   else if (key == "epi_staged") epi_staged_ = v != 0;
+  else if (key == "halo") halo_ = v;
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
   else ECO_CHECK(false, "unknown option '" << key << "'");
   free_plan();
@@ -725,6 +727,61 @@ void Net::make_tensor_maps(ConvOp& c) {
                                                                               << layers_[c.conv_layer].name);
     c.kp.a_mode = A_GATHER;  // auto mode: fall back to the software gather for this layer
   }
+}
+
+// Decide whether a convolution runs on the halo-resident kernel and set it up.
+bool Net::plan_halo(ConvOp& c) {
+  static EncodeTiledFn enc_tiled = (EncodeTiledFn)driver_fn("cuTensorMapEncodeTiled");
+  c.halo = false;
+  const ConvKernelParams& k = c.kp;
+  if (halo_ == 0 || c.stem || c.stem_in || k.nsp != 2 || k.a_mode != A_TMA_IM2COL) return false;
+  if (k.sH != 1 || k.sW != 1 || k.KH * k.KW <= 1 || k.KH > 5 || k.KW > 5) return false;
+  const int pw = k.OW + k.KW - 1;
+  if (pw > 128) return false;
+  int mt = 1;
+  if (k.block_n <= 128 && 256 / pw >= 2 &&
+      (halo_ == 2 || (long long)c.NB * ((k.OH + (256 / pw) - 1) / (256 / pw)) >= 2LL * g_num_sms))
+    mt = 2;  // two 128-position halves share every weight tile
+  int R = std::min(k.OH, (128 * mt) / pw);
+  if (R < 1) return false;
+  const double eff = (double)R * k.OW / (128.0 * mt);
+  if (eff < 0.7) return false;
+  HaloKernelParams& h = c.hp;
+  h = HaloKernelParams{};
+  h.NB = c.NB; h.OH = k.OH; h.OW = k.OW; h.KH = k.KH; h.KW = k.KW; h.pH = k.pH; h.pW = k.pW;
+  h.pw = pw; h.R = R; h.bands = (k.OH + R - 1) / R;
+  h.cblocks = k.cblocks; h.block_n = k.block_n; h.Cout = k.Cout;
+  const int patch_rows = (R + k.KH - 1) * pw;
+  const int need_rows = std::max(patch_rows, (k.KH - 1) * pw + (k.KW - 1) + 128 * mt);
+  h.a_stage_bytes = (uint32_t)round_up(need_rows * 128, 1024);
+  h.a_tx_bytes = (uint32_t)patch_rows * 128u;
+  const size_t avail = (size_t)227 * 1024 - 1024 - 3 * 1024 - 512;
+  const size_t bstage = (size_t)k.block_n * 128;
+  h.a_stages = 2;
+  if ((size_t)3 * h.a_stage_bytes + 4 * bstage <= avail && h.cblocks > 1) h.a_stages = 3;
+  const size_t left = avail - (size_t)h.a_stages * h.a_stage_bytes;
+  h.b_stages = (int)std::min<size_t>(8, left / bstage);
+  if (h.b_stages < 2) return false;
+  h.tmem_cols = pow2_at_least(2 * mt * k.block_n);
+  if (h.tmem_cols > 512) return false;
+  h.num_sms = g_num_sms;
+  h.bias = k.bias; h.scale = k.scale; h.shift = k.shift; h.relu = k.relu;
+  h.out = k.out; h.out_cs = k.out_cs; h.out_coff = k.out_coff;
+  h.raw = k.raw; h.raw_cs = k.raw_cs; h.raw_coff = k.raw_coff;
+  h.res = k.res; h.res_cs = k.res_cs; h.res_coff = k.res_coff;
+  h.error_flag = k.error_flag;
+  // tiled map over the input [C, W, H, N]; box = one 64-channel block of the whole patch, zero fill outside
+  cuuint64_t dims[4] = {(cuuint64_t)k.Cin, (cuuint64_t)k.IW, (cuuint64_t)k.IH, (cuuint64_t)c.NB};
+  cuuint64_t strides[3] = {(cuuint64_t)k.x_sW * 2, (cuuint64_t)k.x_sH * 2, (cuuint64_t)k.x_sN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)pw, (cuuint32_t)(R + k.KH - 1), 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc_tiled(&c.tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)k.x, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  c.halo = true;
+  c.halo_mt = mt;
+  return true;
 }
 
 // =====================================================================================
@@ -1316,6 +1373,7 @@ void Net::plan() {
             kp.tmem_cols = pow2_at_least(kp.block_n);
           }
         }
+        plan_halo(c);
         const double taps = (double)c.K[0] * c.K[1] * c.K[2];
         c.flops = 2.0 * kp.M * c.Cout * taps * c.Cin;
         c.bytes = 2.0 * ((double)c.NB * c.I[0] * c.I[1] * c.I[2] * c.Cin + (double)kp.M * c.Cout + (double)c.Cout * taps * c.Cin);
@@ -1634,7 +1692,8 @@ void Net::run_op(Op& op, bool with_xform) {
     case Op::CONV: {
       ConvOp& c = convs_[op.conv];
       if (c.stem_in && with_xform) run_input_xform(c, nullptr);
-      CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.tmB, stream_));
+      if (c.halo) CUDA_OK(launch_conv_halo(c.hp, c.halo_mt, c.tmX, c.tmB, stream_));
+      else CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.tmB, stream_));
       if (c.out_tensor >= 0) mark_written(c.out_tensor);
       if (c.raw_tensor >= 0) mark_written(c.raw_tensor);
       break;

@@ -127,6 +127,10 @@ struct ConvOp {
   int stem_CH = 0, stem_CW = 0;
   ConvKernelParams kp{};
   CUtensorMap tmA{}, tmB{};
+  bool halo = false;          // halo-resident kernel (2-D, stride 1, filter > 1x1)
+  int halo_mt = 1;
+  HaloKernelParams hp{};
+  CUtensorMap tmX{};
   double flops = 0, bytes = 0;
 };
 
@@ -197,6 +201,7 @@ class Net {
   bool use_graph_ = false;
   int persistent_ = 1;
   int dual_m_ = 1;
+  int halo_ = 1;  // 0 off, 1 auto
   bool epi_staged_ = true;
   bool user_stream_ = false;
   // plan
@@ -234,6 +239,7 @@ class Net {
   int add_tensor(const std::string& name);
   void plan_conv_group(int li, std::vector<bool>& done);
   void make_tensor_maps(ConvOp& c);
+  bool plan_halo(ConvOp& c);
   void download(Tensor& t);
   void upload(Tensor& t);
   ClView view(const Tensor& t) const;

@@ -48,12 +48,12 @@ def two_conv_net(shape, cmid, cout, k, s, p):
 PLAIN = {"gp", "gp_r", "fc"}  # blobs that are plain fp32 on the device
 
 
-def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True, persistent=True, dual_m=1):
+def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True, persistent=True, dual_m=1, halo=1):
     ref = refnet.RefNet(txt).init_params(seed + 1)
     rng = np.random.default_rng(seed)
     x = rng.normal(size=shape).astype(np.float32)
     want = ref.forward(x, bf16=True)
-    net = make_net(txt, keep_all=keep_all, a_mode=a_mode, persistent=persistent, dual_m=dual_m)
+    net = make_net(txt, keep_all=keep_all, a_mode=a_mode, persistent=persistent, dual_m=dual_m, halo=halo)
     load_params(net, ref.params_dict())
     net.blobs["data"].data[...] = x
     net.forward()
@@ -84,11 +84,32 @@ CONV2D = [
 ]
 
 
-@pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
+@pytest.mark.parametrize("mode", ["gather", "im2col", "halo"])
 @pytest.mark.parametrize("case", CONV2D, ids=["c%d" % i for i in range(len(CONV2D))])
-def test_conv2d(gpu, case, a_mode):
+def test_conv2d(gpu, case, mode):
+    # "im2col": per-tap TMA im2col loads; "halo": stride-1 filters read a patch loaded once (auto-selected
+    # when eligible, otherwise identical to im2col)
     shape, cmid, cout, k, s, p = case
-    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, a_mode, check=("a_bn", "c", "c_bn"))
+    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 0 if mode == "gather" else 1, check=("a_bn", "c", "c_bn"),
+             halo=1 if mode == "halo" else 0)
+
+
+HALO = [
+    ((2, 8, 28, 28), 64, 64, [3, 3], [1, 1], [1, 1]),       # inception_3a_3x3
+    ((2, 8, 28, 28), 96, 96, [3, 3], [1, 1], [1, 1]),       # double_3x3_2: Cin 96 (zero-filled second block)
+    ((1, 8, 56, 56), 64, 192, [3, 3], [1, 1], [1, 1]),      # conv2_3x3
+    ((3, 8, 14, 14), 128, 160, [3, 3], [1, 1], [1, 1]),     # ECO-Full 4c geometry
+    ((2, 8, 20, 23), 64, 32, [5, 3], [1, 1], [2, 1]),       # rectangular filter, ragged last band
+    ((2, 8, 17, 9), 64, 64, [3, 3], [1, 1], [0, 0]),        # no padding
+    ((1, 8, 12, 12), 256, 352, [3, 3], [1, 1], [1, 1]),     # four channel blocks, two N tiles
+]
+
+
+@pytest.mark.parametrize("force_mt2", [False, True], ids=["mt1", "mt2"])
+@pytest.mark.parametrize("case", HALO, ids=["h%d" % i for i in range(len(HALO))])
+def test_conv2d_halo_kernel(gpu, case, force_mt2):
+    shape, cmid, cout, k, s, p = case
+    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 1, check=("a_bn", "c", "c_bn"), halo=2 if force_mt2 else 1)
 
 
 CONV3D = [
