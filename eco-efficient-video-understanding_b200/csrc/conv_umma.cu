@@ -367,32 +367,49 @@ conv_umma_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap t
 
 
 // ------------------------------------------------------------------------------------------------
-// Persistent variant (A via TMA im2col only).  One CTA per SM walks the tile list.
-//   * tile = (MT x 128) output positions x block_n channels; with MT = 2 the two 128-row halves share
-//     every weight tile in shared memory (half the B traffic per FLOP, for block_n <= 128)
-//   * TMEM accumulators are double-buffered (2 x MT x block_n fp32 columns <= 512): the epilogue of
-//     tile i overlaps the MMAs of tile i+1; the smem ring streams across tile boundaries
-//   * 10 warps: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = epilogue; two epilogue warps
-//     per TMEM lane quarter split the 16-column chunks between them
-constexpr int kPersistThreads = 320;
+// Register-resident epilogue used by the persistent and the halo kernels.
+// The destination pointers / strides are copied into registers once per kernel (the "memory" clobbers of
+// the surrounding inline PTX would otherwise make the compiler re-read them from the constant bank in
+// every chunk), 32 columns are processed per TMEM load, and two loads are in flight before the wait,
+// so each epilogue warp has 64 independent values to work on instead of a 16-value dependent chain.
+struct EpiArgs {
+  __nv_bfloat16* out; long long out_cs; int out_coff;
+  __nv_bfloat16* raw; long long raw_cs; int raw_coff;
+  const __nv_bfloat16* res; long long res_cs; int res_coff;
+  int Cout, relu, simple;
+};
 
-// Computes one 16-column chunk of the epilogue for this thread's row.  `raw` (if any) is stored
-// directly; the final value y is written as 32 bytes of bf16 into the warp's staging row at
-// `stage_dst` (shared memory) -- the caller copies staged rows out with row-contiguous 16-byte
-// stores so that every global store instruction covers whole 32-byte sectors.
-__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32_t taddr, int m, bool row_ok, int cg,
-                                               int c0, const float* s_bias, const float* s_scale,
-                                               const float* s_shift, bool simple, uint32_t stage_dst) {
-  uint32_t v[16];
-  tmem_ld16(taddr, v);
-  const int nvalid = p.Cout - cg;
-  float f[16];
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// finish NV = 16 or 32 accumulator columns of one output position: v -> (raw) -> y -> global
+template <int NV>
+__device__ __forceinline__ void epi_finish(const EpiArgs& e, const uint32_t (&v)[NV], long long m, bool row_ok, int cg,
+                                           int c0, const float* s_bias, const float* s_scale, const float* s_shift) {
+  const int nvalid = e.Cout - cg;
+  if (!row_ok || nvalid <= 0) return;
+  float f[NV];
   const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
   const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
-  if (simple) {
-    // no raw / residual consumer: bias is pre-folded into the shift, y = relu?(acc * scale + shift')
+  if (e.simple) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NV / 4; ++j) {
       const float4 a = sc4[j], b = sh4[j];
       f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), a.x, b.x);
       f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y);
@@ -402,20 +419,22 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32
   } else {
     const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NV / 4; ++j) {
       const float4 b = bi4[j];
       f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
       f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
       f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
       f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
     }
-    if (row_ok && nvalid > 0) {
-      if (p.res) load16_bf16_add(p.res + (long long)m * p.res_cs + p.res_coff + cg, f, nvalid);
-      if (p.raw) store16_bf16(p.raw + (long long)m * p.raw_cs + p.raw_coff + cg, f, nvalid);
-    }
-    if (!p.out) return;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int q = 0; q < NV / 16; ++q) {
+      float (&fq)[16] = *reinterpret_cast<float (*)[16]>(&f[16 * q]);
+      if (e.res) load16_bf16_add(e.res + m * e.res_cs + e.res_coff + cg + 16 * q, fq, nvalid - 16 * q);
+      if (e.raw) store16_bf16(e.raw + m * e.raw_cs + e.raw_coff + cg + 16 * q, fq, nvalid - 16 * q);
+    }
+    if (!e.out) return;
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) {
       const float4 a = sc4[j], b = sh4[j];
       f[4 * j + 0] = fmaf(f[4 * j + 0], a.x, b.x);
       f[4 * j + 1] = fmaf(f[4 * j + 1], a.y, b.y);
@@ -423,21 +442,64 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32
       f[4 * j + 3] = fmaf(f[4 * j + 3], a.w, b.w);
     }
   }
-  if (p.relu) {
+  if (e.relu) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+    for (int j = 0; j < NV; ++j) f[j] = fmaxf(f[j], 0.f);
   }
-  if (!p.epi_staged) {
-    if (row_ok && nvalid > 0) store16_bf16(p.out + (long long)m * p.out_cs + p.out_coff + cg, f, nvalid);
-    return;
+#pragma unroll
+  for (int q = 0; q < NV / 16; ++q) {
+    float (&fq)[16] = *reinterpret_cast<float (*)[16]>(&f[16 * q]);
+    store16_bf16(e.out + m * e.out_cs + e.out_coff + cg + 16 * q, fq, nvalid - 16 * q);
   }
-  const uint32_t w0 = pack_bf16x2(f[0], f[1]), w1 = pack_bf16x2(f[2], f[3]), w2 = pack_bf16x2(f[4], f[5]),
-                 w3 = pack_bf16x2(f[6], f[7]), w4 = pack_bf16x2(f[8], f[9]), w5 = pack_bf16x2(f[10], f[11]),
-                 w6 = pack_bf16x2(f[12], f[13]), w7 = pack_bf16x2(f[14], f[15]);
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_dst + 16), "r"(w4), "r"(w5), "r"(w6), "r"(w7)
-               : "memory");
 }
+
+// One epilogue warp's work for one tile: MT halves x its column range [c_begin, c_end) (16-column chunks).
+//   taddr_h0: TMEM address of (lane quarter, accumulator half 0, column 0); halves are BN columns apart.
+//   m_of(h), ok_of(h): output position / validity of this thread's row in half h.
+template <int MT, typename RowFn>
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr_h0, int BN, int n0, int c_begin, int c_end,
+                                              const float* s_bias, const float* s_scale, const float* s_shift,
+                                              RowFn row_of) {
+  long long mrow[MT];
+  bool rok[MT];
+#pragma unroll
+  for (int h = 0; h < MT; ++h) row_of(h, mrow[h], rok[h]);
+  const int npairs = (c_end - c_begin) >> 1;       // 32-column groups
+  const bool tail16 = ((c_end - c_begin) & 1) != 0;
+  const int items = MT * npairs;
+  for (int i = 0; i < items; i += 2) {
+    uint32_t va[32], vb[32];
+    const int h0 = i / npairs, g0 = i - h0 * npairs;
+    const bool two = (i + 1) < items;
+    const int h1 = two ? (i + 1) / npairs : h0, g1 = two ? (i + 1) - h1 * npairs : g0;
+    const int ca = c_begin + 2 * g0, cb = c_begin + 2 * g1;
+    tmem_ld32_nowait(taddr_h0 + (uint32_t)(h0 * BN + ca * 16), va);
+    if (two) tmem_ld32_nowait(taddr_h0 + (uint32_t)(h1 * BN + cb * 16), vb);
+    tmem_wait_ld();
+    epi_finish<32>(e, va, mrow[h0], rok[h0], n0 + ca * 16, ca * 16, s_bias, s_scale, s_shift);
+    if (two) epi_finish<32>(e, vb, mrow[h1], rok[h1], n0 + cb * 16, cb * 16, s_bias, s_scale, s_shift);
+  }
+  if (tail16) {
+    const int ct = c_end - 1;
+#pragma unroll
+    for (int h = 0; h < MT; ++h) {
+      uint32_t v[16];
+      tmem_ld16_nowait(taddr_h0 + (uint32_t)(h * BN + ct * 16), v);
+      tmem_wait_ld();
+      epi_finish<16>(e, v, mrow[h], rok[h], n0 + ct * 16, ct * 16, s_bias, s_scale, s_shift);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant (A via TMA im2col only).  One CTA per SM walks the tile list.
+//   * tile = (MT x 128) output positions x block_n channels; with MT = 2 the two 128-row halves share
+//     every weight tile in shared memory (half the B traffic per FLOP, for block_n <= 128)
+//   * TMEM accumulators are double-buffered (2 x MT x block_n fp32 columns <= 512): the epilogue of
+//     tile i overlaps the MMAs of tile i+1; the smem ring streams across tile boundaries
+//   * 10 warps: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = epilogue; two epilogue warps
+//     per TMEM lane quarter split the 16-column chunks between them
+constexpr int kPersistThreads = 320;
 
 template <int MT>
 __global__ void __launch_bounds__(kPersistThreads, 1)
@@ -465,9 +527,6 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   const uint32_t bar_tmem_full = bar_empty + 8 * S;      // [2]
   const uint32_t bar_tmem_empty = bar_tmem_full + 16;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
-  // epilogue staging: 8 warps x 32 rows x (epi_group chunks x 32 B + 16 B pad)
-  const uint32_t stage_pitch = (uint32_t)p.epi_group * 32u + 16u;
-  const uint32_t stage_base = smem_u32(bars) + 512u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -580,6 +639,14 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
     const int half = (warp - 2) >> 2;   // which of the two warps of that quarter
     const int chunks = BN >> 4;
     const bool simple = (p.res == nullptr) && (p.raw == nullptr) && (p.out != nullptr);
+    EpiArgs e;
+    e.out = p.out; e.out_cs = p.out_cs; e.out_coff = p.out_coff;
+    e.raw = p.raw; e.raw_cs = p.raw_cs; e.raw_coff = p.raw_coff;
+    e.res = p.res; e.res_cs = p.res_cs; e.res_coff = p.res_coff;
+    e.Cout = p.Cout; e.relu = p.relu; e.simple = simple ? 1 : 0;
+    const int M = p.M;
+    const int c_begin = half ? (chunks + 1) / 2 : 0;
+    const int c_end = half ? chunks : (chunks + 1) / 2;
     uint32_t tile_iter = 0;
     int loaded_n0 = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
@@ -604,45 +671,12 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
       const uint32_t use = tile_iter >> 1;
       mbar_wait(bar_tmem_full + 8 * buf, use & 1u, p.error_flag, 4);
       tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < MT; ++h) {
-        const int mrow0 = m0 + h * kBlockM + wq * 32;  // first output position of this warp's 32 rows
-        const int m = mrow0 + lane;
-        const bool row_ok = m < p.M;
-        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols + (uint32_t)(h * BN);
-        // this warp's contiguous chunk range: the two warps of a lane quarter split the columns in half
-        const int c_begin = half ? (chunks + 1) / 2 : 0;
-        const int c_end = half ? chunks : (chunks + 1) / 2;
-        const uint32_t my_stage = stage_base + (uint32_t)(warp - 2) * 32u * stage_pitch;
-        for (int cgrp = c_begin; cgrp < c_end; cgrp += p.epi_group) {
-          const int gcount = min(p.epi_group, c_end - cgrp);
-          for (int k = 0; k < gcount; ++k) {
-            const int c = cgrp + k;
-            epilogue_chunk(p, taddr + (uint32_t)(c * 16), m, row_ok, n0 + c * 16, c * 16, s_bias, s_scale, s_shift,
-                           simple, my_stage + (uint32_t)lane * stage_pitch + (uint32_t)k * 32u);
-          }
-          if (p.out && p.epi_staged) {
-            __syncwarp();
-            // copy out: consecutive lanes take consecutive 16-byte pieces of a row -> whole sectors / lines
-            const int ppr = gcount * 2;  // 16-byte pieces per row in this group
-            const int col0 = n0 + cgrp * 16;
-            for (int idx = lane; idx < 32 * ppr; idx += 32) {
-              const int r = idx / ppr;
-              const int piece = idx - r * ppr;
-              const int mm = mrow0 + r;
-              const int col = col0 + piece * 8;
-              if (mm < p.M && col < p.Cout) {
-                uint4 val;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                             : "r"(my_stage + (uint32_t)r * stage_pitch + (uint32_t)piece * 16u));
-                *reinterpret_cast<uint4*>(p.out + (long long)mm * p.out_cs + p.out_coff + col) = val;
-              }
-            }
-            __syncwarp();
-          }
-        }
-      }
+      const int mbase = m0 + wq * 32 + lane;
+      epilogue_tile<MT>(e, tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols, BN, n0, c_begin, c_end, s_bias,
+                        s_scale, s_shift, [&](int h, long long& m, bool& ok) {
+                          m = mbase + h * kBlockM;
+                          ok = m < M;
+                        });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -795,17 +829,21 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
     const int half = (warp - 2) >> 2;
     const int chunks = BN >> 4;
     const bool simple = (p.res == nullptr) && (p.raw == nullptr) && (p.out != nullptr);
-    ConvKernelParams ep{};  // the fields epilogue_chunk reads
-    ep.Cout = p.Cout; ep.relu = p.relu; ep.out = p.out; ep.out_cs = p.out_cs; ep.out_coff = p.out_coff;
-    ep.raw = p.raw; ep.raw_cs = p.raw_cs; ep.raw_coff = p.raw_coff; ep.res = p.res; ep.res_cs = p.res_cs;
-    ep.res_coff = p.res_coff; ep.epi_staged = 0; ep.scale = p.scale;
+    EpiArgs e;
+    e.out = p.out; e.out_cs = p.out_cs; e.out_coff = p.out_coff;
+    e.raw = p.raw; e.raw_cs = p.raw_cs; e.raw_coff = p.raw_coff;
+    e.res = p.res; e.res_cs = p.res_cs; e.res_coff = p.res_coff;
+    e.Cout = p.Cout; e.relu = p.relu; e.simple = simple ? 1 : 0;
+    const int pw = p.pw, R = p.R, OW = p.OW, OH = p.OH;
+    const int c_begin = half ? (chunks + 1) / 2 : 0;
+    const int c_end = half ? chunks : (chunks + 1) / 2;
     uint32_t tile_iter = 0;
     int loaded_n0 = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
       const int n0 = (t % n_tiles_n) * BN;
       const int tb = t / n_tiles_n;
       const int band = tb % p.bands, n = tb / p.bands;
-      const int y0 = band * p.R;
+      const int y0 = band * R;
       if (n0 != loaded_n0) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int i = threadIdx.x - 64; i < BN; i += 256) {
@@ -822,19 +860,13 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
       const uint32_t buf = tile_iter & 1u, use = tile_iter >> 1;
       mbar_wait(bar_tmem_full + 8 * buf, use & 1u, p.error_flag, 4);
       tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < MT; ++h) {
-        const int pos = h * kBlockM + wq * 32 + lane;   // position on the padded-width grid
-        const int r = pos / p.pw, c = pos - r * p.pw;
-        const bool row_ok = (r < p.R) && (c < p.OW) && (y0 + r < p.OH);
-        const int m = ((n * p.OH) + y0 + r) * p.OW + c;
-        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols + (uint32_t)(h * BN);
-        const int c_begin = half ? (chunks + 1) / 2 : 0;
-        const int c_end = half ? chunks : (chunks + 1) / 2;
-        for (int cc = c_begin; cc < c_end; ++cc)
-          epilogue_chunk(ep, taddr + (uint32_t)(cc * 16), m, row_ok, n0 + cc * 16, cc * 16, s_bias, s_scale, s_shift,
-                         simple, 0u);
-      }
+      epilogue_tile<MT>(e, tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols, BN, n0, c_begin, c_end, s_bias,
+                        s_scale, s_shift, [&](int h, long long& m, bool& ok) {
+                          const int pos = h * kBlockM + wq * 32 + lane;  // position on the padded-width grid
+                          const int r = pos / pw, c = pos - r * pw;
+                          ok = (r < R) && (c < OW) && (y0 + r < OH);
+                          m = ((long long)n * OH + y0 + r) * OW + c;
+                        });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tmem_empty + 8 * buf) : "memory");

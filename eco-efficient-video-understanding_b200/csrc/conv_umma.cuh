@@ -88,7 +88,7 @@ cudaError_t launch_conv_halo(const HaloKernelParams& p, int m_halves, const CUte
                              cudaStream_t stream);
 
 // dynamic shared memory needed for (block_n, stages)
-inline size_t conv_epi_stage_bytes(int epi_group) { return (size_t)8 * 32 * ((size_t)epi_group * 32 + 16); }
+inline size_t conv_epi_stage_bytes(int epi_group) { return epi_group ? (size_t)8 * 32 * ((size_t)epi_group * 32 + 16) : 0; }
 inline size_t conv_smem_bytes(int block_n, int stages, int m_halves = 1, size_t epi_stage = 0) {
   size_t a = (size_t)stages * kBlockM * 128 * m_halves;
   size_t b = (size_t)stages * block_n * 128;

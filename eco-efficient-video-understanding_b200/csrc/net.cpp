@@ -1361,10 +1361,8 @@ void Net::plan() {
             // shared memory: 227 KB - alignment slack - constants - barriers; the epilogue staging takes
             // 4 chunks per copy-out (128-byte row pieces) unless that would cost a pipeline stage
             const size_t avail = (size_t)227 * 1024 - 1024 - 3 * 1024 - 512;
-            kp.epi_group = 4;
-            kp.epi_staged = epi_staged_ ? 1 : 0;
-            size_t st4 = (avail - conv_epi_stage_bytes(4)) / stage_bytes, st2 = (avail - conv_epi_stage_bytes(2)) / stage_bytes;
-            if (st4 < st2 && st4 < 6) kp.epi_group = 2;
+            kp.epi_group = 0;  // the epilogue keeps its values in registers and stores 64-byte row pieces directly
+            kp.epi_staged = 0;
             kp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (avail - conv_epi_stage_bytes(kp.epi_group)) / stage_bytes));
             kp.tmem_cols = pow2_at_least(2 * kp.m_halves * kp.block_n);
           } else {
