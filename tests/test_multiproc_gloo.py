@@ -25,8 +25,12 @@ g.close()
 def _torchrun(args, timeout=240):
     env = dict(os.environ)
     env["OMP_NUM_THREADS"] = "2"
+    import socket
+    with socket.socket() as sk:   # a free port: parallel test runs must not collide on the rendezvous
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29611"] + args
+           "127.0.0.1", "--master-port", str(port)] + args
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
 
 
