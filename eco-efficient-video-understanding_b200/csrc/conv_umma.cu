@@ -373,6 +373,7 @@ conv_umma_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap t
 // every chunk), 32 columns are processed per TMEM load, and two loads are in flight before the wait,
 // so each epilogue warp has 64 independent values to work on instead of a 16-value dependent chain.
 struct EpiArgs {
+  int dbg;
   __nv_bfloat16* out; long long out_cs; int out_coff;
   __nv_bfloat16* raw; long long raw_cs; int raw_coff;
   const __nv_bfloat16* res; long long res_cs; int res_coff;
@@ -404,6 +405,7 @@ __device__ __forceinline__ void epi_finish(const EpiArgs& e, const uint32_t (&v)
                                            int c0, const float* s_bias, const float* s_scale, const float* s_shift) {
   const int nvalid = e.Cout - cg;
   if (!row_ok || nvalid <= 0) return;
+  if ((e.dbg & 1) && v[0] != 0x7fc00001u) return;  // development: results computed but never stored
   float f[NV];
   const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
   const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
@@ -473,9 +475,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr_h
     const bool two = (i + 1) < items;
     const int h1 = two ? (i + 1) / npairs : h0, g1 = two ? (i + 1) - h1 * npairs : g0;
     const int ca = c_begin + 2 * g0, cb = c_begin + 2 * g1;
-    tmem_ld32_nowait(taddr_h0 + (uint32_t)(h0 * BN + ca * 16), va);
-    if (two) tmem_ld32_nowait(taddr_h0 + (uint32_t)(h1 * BN + cb * 16), vb);
-    tmem_wait_ld();
+    if (!(e.dbg & 2)) {
+      tmem_ld32_nowait(taddr_h0 + (uint32_t)(h0 * BN + ca * 16), va);
+      if (two) tmem_ld32_nowait(taddr_h0 + (uint32_t)(h1 * BN + cb * 16), vb);
+      tmem_wait_ld();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { va[j] = 0x3f800000u; vb[j] = 0x3f800000u; }
+    }
     epi_finish<32>(e, va, mrow[h0], rok[h0], n0 + ca * 16, ca * 16, s_bias, s_scale, s_shift);
     if (two) epi_finish<32>(e, vb, mrow[h1], rok[h1], n0 + cb * 16, cb * 16, s_bias, s_scale, s_shift);
   }
@@ -499,7 +506,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr_h
 //     tile i overlaps the MMAs of tile i+1; the smem ring streams across tile boundaries
 //   * 10 warps: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = epilogue; two epilogue warps
 //     per TMEM lane quarter split the 16-column chunks between them
-constexpr int kPersistThreads = 320;
+constexpr int kPersistThreads = 384;  // warps: 0 B producer, 1 MMA, 2-9 epilogue, 10-11 A producers
 
 template <int MT>
 __global__ void __launch_bounds__(kPersistThreads, 1)
@@ -559,42 +566,52 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   const int num_kb = p.num_kb;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: weight tiles (+ arms the stage barrier) =====================
+    // Three independent producer threads (this one and warps 10/11 for the two A halves) each issue one
+    // TMA per K block: the per-issue latency of a single thread (empty-wait + expect_tx + issue) no longer
+    // bounds the load rate of short-K tiles.
     if (lane == 0) {
-      uint32_t it = 0;  // running K-block counter across tiles
+      uint32_t it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n0 = (t % n_tiles_n) * BN;
-        int cw[MT], chh[MT], cd[MT], cn[MT];
-        bool live[MT];  // a half that starts beyond the last output position is never loaded
         uint32_t tile_tx = b_stage_bytes;
 #pragma unroll
-        for (int h = 0; h < MT; ++h) {
-          int r = (t / n_tiles_n) * TILE_M + h * kBlockM;
-          live[h] = r < p.M;
-          if (live[h]) tile_tx += a_half_bytes;
-          const int q = r % p.OW; r /= p.OW;
-          const int pp = r % p.OH; r /= p.OH;
-          const int z = r % p.OD;
-          cn[h] = r / p.OD;
-          cw[h] = q * p.sW - p.pW; chh[h] = pp * p.sH - p.pH; cd[h] = z * p.sD - p.pD;
-        }
-        int cb = 0, kx = 0, ky = 0, kz = 0;
+        for (int h = 0; h < MT; ++h)
+          if ((t / n_tiles_n) * TILE_M + h * kBlockM < p.M) tile_tx += a_half_bytes;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % (uint32_t)S;
           const uint32_t ph = (it / (uint32_t)S) & 1u;
           mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, tile_tx);
           tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
-#pragma unroll
-          for (int h = 0; h < MT; ++h) {
-            if (!live[h]) continue;
+        }
+      }
+    }
+  } else if (warp >= 10) {
+    // ===================== TMA producers: activations, one warp per 128-row half =====================
+    const int h = warp - 10;
+    if (lane == 0 && h < MT) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int r = (t / n_tiles_n) * TILE_M + h * kBlockM;
+        const bool live = r < p.M;  // a half that starts beyond the last output position is never loaded
+        const int q = r % p.OW; r /= p.OW;
+        const int pp = r % p.OH; r /= p.OH;
+        const int z = r % p.OD;
+        const int n = r / p.OD;
+        const int cw = q * p.sW - p.pW, chh = pp * p.sH - p.pH, cd = z * p.sD - p.pD;
+        int cb = 0, kx = 0, ky = 0, kz = 0;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          if (live) {
+            const uint32_t s = it % (uint32_t)S;
+            const uint32_t ph = (it / (uint32_t)S) & 1u;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 8);
             const uint32_t dst = sA + s * a_stage_bytes + h * a_half_bytes;
             if (p.nsp == 3)
-              tma_im2col_5d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cd[h], cn[h], (uint16_t)kx,
-                            (uint16_t)ky, (uint16_t)kz);
+              tma_im2col_5d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, cd, n, (uint16_t)kx, (uint16_t)ky,
+                            (uint16_t)kz);
             else
-              tma_im2col_4d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cn[h], (uint16_t)kx,
-                            (uint16_t)ky);
+              tma_im2col_4d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, n, (uint16_t)kx, (uint16_t)ky);
           }
           if (++cb == p.cblocks) {
             cb = 0;
@@ -626,7 +643,8 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
             const uint64_t adesc = make_sw128_desc(sA + s * a_stage_bytes + h * a_half_bytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              umma_bf16(acc + (uint32_t)(h * BN), adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+              if (!(p.debug_flags & 4))
+                umma_bf16(acc + (uint32_t)(h * BN), adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
           }
           umma_commit(bar_empty + 8 * s);
         }
@@ -643,7 +661,7 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
     e.out = p.out; e.out_cs = p.out_cs; e.out_coff = p.out_coff;
     e.raw = p.raw; e.raw_cs = p.raw_cs; e.raw_coff = p.raw_coff;
     e.res = p.res; e.res_cs = p.res_cs; e.res_coff = p.res_coff;
-    e.Cout = p.Cout; e.relu = p.relu; e.simple = simple ? 1 : 0;
+    e.Cout = p.Cout; e.relu = p.relu; e.simple = simple ? 1 : 0; e.dbg = p.debug_flags;
     const int M = p.M;
     const int c_begin = half ? (chunks + 1) / 2 : 0;
     const int c_end = half ? chunks : (chunks + 1) / 2;
@@ -754,27 +772,35 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer: patches and weight tiles =====================
+    // ===================== TMA producer: input patches =====================
     if (lane == 0) {
-      uint32_t ia = 0, ib = 0;
+      uint32_t ia = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n0 = (t % n_tiles_n) * BN;
         const int tb = t / n_tiles_n;
         const int band = tb % p.bands, n = tb / p.bands;
         const int y0 = band * p.R;
+        for (int cb = 0; cb < p.cblocks; ++cb, ++ia) {
+          const uint32_t s = ia % (uint32_t)SA, ph = (ia / (uint32_t)SA) & 1u;
+          mbar_wait(bar_a_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
+          mbar_arrive_expect_tx(bar_a_full + 8 * s, p.a_tx_bytes);
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(sA + s * p.a_stage_bytes), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_a_full + 8 * s),
+              "r"(cb * kBlockK), "r"(-p.pW), "r"(y0 - p.pH), "r"(n)
+              : "memory");
+        }
+      }
+    }
+  } else if (warp >= 10) {
+    // ===================== TMA producers: weight tiles, two threads interleaved =====================
+    const uint32_t me = (uint32_t)(warp - 10);
+    if (lane == 0) {
+      uint32_t ib = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n0 = (t % n_tiles_n) * BN;
         for (int cb = 0; cb < p.cblocks; ++cb) {
-          {
-            const uint32_t s = ia % (uint32_t)SA, ph = (ia / (uint32_t)SA) & 1u;
-            mbar_wait(bar_a_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
-            mbar_arrive_expect_tx(bar_a_full + 8 * s, p.a_tx_bytes);
-            asm volatile(
-                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                ::"r"(sA + s * p.a_stage_bytes), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_a_full + 8 * s),
-                "r"(cb * kBlockK), "r"(-p.pW), "r"(y0 - p.pH), "r"(n)
-                : "memory");
-            ++ia;
-          }
           for (int tap = 0; tap < taps; ++tap, ++ib) {
+            if ((ib & 1u) != me) continue;
             const uint32_t s = ib % (uint32_t)SB, ph = (ib / (uint32_t)SB) & 1u;
             mbar_wait(bar_b_empty + 8 * s, ph ^ 1u, p.error_flag, 6);
             mbar_arrive_expect_tx(bar_b_full + 8 * s, b_stage_bytes);
@@ -833,7 +859,7 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
     e.out = p.out; e.out_cs = p.out_cs; e.out_coff = p.out_coff;
     e.raw = p.raw; e.raw_cs = p.raw_cs; e.raw_coff = p.raw_coff;
     e.res = p.res; e.res_cs = p.res_cs; e.res_coff = p.res_coff;
-    e.Cout = p.Cout; e.relu = p.relu; e.simple = simple ? 1 : 0;
+    e.Cout = p.Cout; e.relu = p.relu; e.simple = simple ? 1 : 0; e.dbg = 0;
     const int pw = p.pw, R = p.R, OW = p.OW, OH = p.OH;
     const int c_begin = half ? (chunks + 1) / 2 : 0;
     const int c_end = half ? chunks : (chunks + 1) / 2;

@@ -528,6 +528,7 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "persistent") persistent_ = v;  // 0 never, 1 auto (per layer), 2 always
   else if (key == "epi_staged") epi_staged_ = v != 0;
   else if (key == "halo") halo_ = v;
+  else if (key == "debug_flags") debug_flags_ = v;
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
   else ECO_CHECK(false, "unknown option '" << key << "'");
   free_plan();
@@ -1363,6 +1364,7 @@ void Net::plan() {
             const size_t avail = (size_t)227 * 1024 - 1024 - 3 * 1024 - 512;
             kp.epi_group = 0;  // the epilogue keeps its values in registers and stores 64-byte row pieces directly
             kp.epi_staged = 0;
+            kp.debug_flags = debug_flags_;
             kp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (avail - conv_epi_stage_bytes(kp.epi_group)) / stage_bytes));
             kp.tmem_cols = pow2_at_least(2 * kp.m_halves * kp.block_n);
           } else {

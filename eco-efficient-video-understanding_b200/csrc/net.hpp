@@ -202,6 +202,7 @@ class Net {
   int persistent_ = 1;
   int dual_m_ = 1;
   int halo_ = 1;  // 0 off, 1 auto
+  int debug_flags_ = 0;
   bool epi_staged_ = true;
   bool user_stream_ = false;
   // plan
