@@ -99,6 +99,16 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
   return d;
 }
+// K-major, 32-byte-swizzled operand (rows of 32 B = 16 bf16, 8-row groups 256 B apart)
+__device__ __forceinline__ uint64_t make_sw32_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;  // SWIZZLE_32B
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=block_n
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
@@ -732,11 +742,12 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
-  const int SA = p.a_stages, SB = p.b_stages, BN = p.block_n;
+  const int SA = p.a_stages, SB = p.b_resident ? 1 : p.b_stages, BN = p.block_n;
   const uint32_t b_stage_bytes = (uint32_t)BN * 128;
+  const uint32_t b_region = p.b_resident ? (uint32_t)p.b_kblocks * b_stage_bytes : (uint32_t)SB * b_stage_bytes;
   const uint32_t sA = base;
   const uint32_t sB = sA + SA * p.a_stage_bytes;
-  float* s_bias = reinterpret_cast<float*>(smem + (size_t)SA * p.a_stage_bytes + (size_t)SB * b_stage_bytes);
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)SA * p.a_stage_bytes + (size_t)b_region);
   float* s_scale = s_bias + 256;
   float* s_shift = s_scale + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
@@ -772,8 +783,14 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer: input patches =====================
+    // ===================== TMA producer: input patches (+ the resident weights, once) =====================
     if (lane == 0) {
+      if (p.b_resident) {
+        // b_full[0] doubles as the "weights resident" barrier: armed once, completes once
+        mbar_arrive_expect_tx(bar_b_full, (uint32_t)p.b_kblocks * b_stage_bytes);
+        for (int kbk = 0; kbk < p.b_kblocks; ++kbk)
+          tma_load_2d(sB + kbk * b_stage_bytes, &tmB, bar_b_full, kbk * kBlockK, 0);
+      }
       uint32_t ia = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int tb = t / n_tiles_n;
@@ -794,7 +811,7 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
   } else if (warp >= 10) {
     // ===================== TMA producers: weight tiles, two threads interleaved =====================
     const uint32_t me = (uint32_t)(warp - 10);
-    if (lane == 0) {
+    if (lane == 0 && !p.b_resident) {
       uint32_t ib = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n0 = (t % n_tiles_n) * BN;
@@ -813,7 +830,14 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BN);
+      const uint32_t rb = (uint32_t)p.row_bytes;
+      const bool sw32 = p.row_bytes == 32;
+      const int ksteps = p.row_bytes / 32;  // UMMA K=16 steps per tap: 4 (64 ch) or 1 (16-ch stem cells)
       uint32_t ia = 0, ib = 0, tile_iter = 0;
+      if (p.b_resident) {
+        mbar_wait(bar_b_full, 0, p.error_flag, 7);
+        tc_fence_after();
+      }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
         const uint32_t buf = tile_iter & 1u, use = tile_iter >> 1;
         mbar_wait(bar_tmem_empty + 8 * buf, (use & 1u) ^ 1u, p.error_flag, 5);
@@ -826,22 +850,33 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
           tc_fence_after();
           const uint32_t patch = sA + sa * p.a_stage_bytes;
           int ky = 0, kx = 0;
-          for (int tap = 0; tap < taps; ++tap, ++ib) {
-            const uint32_t sb = ib % (uint32_t)SB, phb = (ib / (uint32_t)SB) & 1u;
-            mbar_wait(bar_b_full + 8 * sb, phb, p.error_flag, 7);
-            tc_fence_after();
-            const uint64_t bdesc = make_sw128_desc(sB + sb * b_stage_bytes);
-            const uint32_t a0 = patch + (uint32_t)(ky * p.pw + kx) * 128u;  // tap = row shift of the patch
+          for (int tap = 0; tap < taps; ++tap) {
+            // weight K position of this (tap, channel block): 64 ch -> one K block per (tap, cb);
+            // stem cells -> 16 columns inside K block tap/4
+            const int bk_elem = sw32 ? tap * 16 : (tap * p.cblocks + cb) * kBlockK;
+            uint32_t btile;
+            uint32_t sb = 0;
+            if (p.b_resident) {
+              btile = sB + (uint32_t)(bk_elem / kBlockK) * b_stage_bytes;
+            } else {
+              sb = ib % (uint32_t)SB;
+              const uint32_t phb = (ib / (uint32_t)SB) & 1u;
+              mbar_wait(bar_b_full + 8 * sb, phb, p.error_flag, 7);
+              tc_fence_after();
+              btile = sB + sb * b_stage_bytes;
+              ++ib;
+            }
+            const uint64_t bdesc = make_sw128_desc(btile) + (uint64_t)((bk_elem % kBlockK) * 2 / 16);
+            const uint32_t a0 = patch + (uint32_t)(ky * p.pw + kx) * rb;  // tap = row shift of the patch
 #pragma unroll
             for (int h = 0; h < MT; ++h) {
-              const uint64_t adesc = make_sw128_desc(a0 + (uint32_t)h * (kBlockM * 128u));
-#pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint32_t ah = a0 + (uint32_t)h * (kBlockM * rb);
+              const uint64_t adesc = sw32 ? make_sw32_desc(ah) : make_sw128_desc(ah);
+              for (int k = 0; k < ksteps; ++k)
                 umma_bf16(acc + (uint32_t)(h * BN), adesc + 2 * k, bdesc + 2 * k, idesc, first ? (uint32_t)(k != 0) : 1u);
-              }
             }
             first = 0;
-            umma_commit(bar_b_empty + 8 * sb);
+            if (!p.b_resident) umma_commit(bar_b_empty + 8 * sb);
             if (++kx == p.KW) { kx = 0; ++ky; }
           }
           umma_commit(bar_a_empty + 8 * sa);

@@ -74,6 +74,9 @@ struct HaloKernelParams {
   int a_stages, b_stages;
   uint32_t a_stage_bytes;    // allocated bytes per A patch slot (patch + over-read slack, 1024-aligned)
   uint32_t a_tx_bytes;       // bytes one patch load delivers = 128 * pw * (R + KH - 1)
+  int row_bytes;             // bytes per patch pixel: 128 (64 ch, SWIZZLE_128B) or 32 (16 ch, SWIZZLE_32B: the stem cells)
+  int b_resident;            // 1: all weight tiles live in shared memory for the whole kernel (single N tile)
+  int b_kblocks;             // number of 64-wide weight K blocks (= Ktotal / 64)
   int tmem_cols, num_sms;
   const float* bias; const float* scale; const float* shift;
   int relu;
@@ -83,7 +86,8 @@ struct HaloKernelParams {
   int* error_flag;
 };
 inline size_t halo_smem_bytes(const HaloKernelParams& p) {
-  return 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.block_n * 128 + 3 * 256 * sizeof(float) + 512;
+  const size_t b = p.b_resident ? (size_t)p.b_kblocks * p.block_n * 128 : (size_t)p.b_stages * p.block_n * 128;
+  return 1024 + (size_t)p.a_stages * p.a_stage_bytes + b + 3 * 256 * sizeof(float) + 512;
 }
 cudaError_t launch_conv_halo(const HaloKernelParams& p, int m_halves, const CUtensorMap& tmX, const CUtensorMap& tmB,
                              cudaStream_t stream);

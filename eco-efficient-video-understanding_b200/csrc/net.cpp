@@ -731,38 +731,65 @@ void Net::make_tensor_maps(ConvOp& c) {
 }
 
 // Decide whether a convolution runs on the halo-resident kernel and set it up.
+//   * stride-1 2-D filters larger than 1x1 on 64-channel blocks (128-byte pixel rows), and
+//   * the 7x7/s2 stem, which is a 4x4/s1 filter over 16-channel space-to-depth cells (32-byte rows).
+// The kernel is only worth it when the weights can stay resident in shared memory (measured:
+// profiles/r01g_*): with streamed 8-12 KB weight tiles it is no faster than per-tap TMA im2col.
 bool Net::plan_halo(ConvOp& c) {
   static EncodeTiledFn enc_tiled = (EncodeTiledFn)driver_fn("cuTensorMapEncodeTiled");
   c.halo = false;
   const ConvKernelParams& k = c.kp;
-  if (halo_ == 0 || c.stem || c.stem_in || k.nsp != 2 || k.a_mode != A_TMA_IM2COL) return false;
-  if (k.sH != 1 || k.sW != 1 || k.KH * k.KW <= 1 || k.KH > 5 || k.KW > 5) return false;
-  const int pw = k.OW + k.KW - 1;
+  if (halo_ == 0 || k.nsp != 2 || k.a_mode != A_TMA_IM2COL) return false;
+  int KH, KW, pH, pW, OH, OW, IH, IW, cin, row_bytes, cblocks;
+  long long sW, sH, sN;  // element strides of the tensor the patch is cut from
+  const void* xbase = k.x;
+  if (c.stem) {
+    KH = KW = 4; pH = pW = 0; OH = c.O[1]; OW = c.O[2]; IH = c.stem_CH; IW = c.stem_CW;
+    cin = 16; row_bytes = 32; cblocks = 1;
+    sW = 16; sH = (long long)c.stem_CW * 16; sN = (long long)c.stem_CH * c.stem_CW * 16;
+  } else {
+    if (c.stem_in) return false;
+    if (k.sH != 1 || k.sW != 1 || k.KH * k.KW <= 1 || k.KH > 5 || k.KW > 5) return false;
+    KH = k.KH; KW = k.KW; pH = k.pH; pW = k.pW; OH = k.OH; OW = k.OW; IH = k.IH; IW = k.IW;
+    cin = k.Cin; row_bytes = 128; cblocks = k.cblocks;
+    sW = k.x_sW; sH = k.x_sH; sN = k.x_sN;
+  }
+  const int pw = OW + KW - 1;
   if (pw > 128) return false;
   int mt = 1;
   if (k.block_n <= 128 && 256 / pw >= 2 &&
-      (halo_ == 2 || (long long)c.NB * ((k.OH + (256 / pw) - 1) / (256 / pw)) >= 2LL * g_num_sms))
+      (halo_ == 2 || (long long)c.NB * ((OH + (256 / pw) - 1) / (256 / pw)) >= 2LL * g_num_sms))
     mt = 2;  // two 128-position halves share every weight tile
-  int R = std::min(k.OH, (128 * mt) / pw);
+  const int R = std::min(OH, (128 * mt) / pw);
   if (R < 1) return false;
-  const double eff = (double)R * k.OW / (128.0 * mt);
-  if (eff < 0.7) return false;
+  if ((double)R * OW / (128.0 * mt) < 0.7) return false;
   HaloKernelParams& h = c.hp;
   h = HaloKernelParams{};
-  h.NB = c.NB; h.OH = k.OH; h.OW = k.OW; h.KH = k.KH; h.KW = k.KW; h.pH = k.pH; h.pW = k.pW;
-  h.pw = pw; h.R = R; h.bands = (k.OH + R - 1) / R;
-  h.cblocks = k.cblocks; h.block_n = k.block_n; h.Cout = k.Cout;
-  const int patch_rows = (R + k.KH - 1) * pw;
-  const int need_rows = std::max(patch_rows, (k.KH - 1) * pw + (k.KW - 1) + 128 * mt);
-  h.a_stage_bytes = (uint32_t)round_up(need_rows * 128, 1024);
-  h.a_tx_bytes = (uint32_t)patch_rows * 128u;
+  h.NB = c.NB; h.OH = OH; h.OW = OW; h.KH = KH; h.KW = KW; h.pH = pH; h.pW = pW;
+  h.pw = pw; h.R = R; h.bands = (OH + R - 1) / R;
+  h.cblocks = cblocks; h.block_n = k.block_n; h.Cout = k.Cout;
+  h.row_bytes = row_bytes;
+  h.b_kblocks = (int)(c.Ktotal / kBlockK);
+  const int patch_rows = (R + KH - 1) * pw;
+  const int need_rows = std::max(patch_rows, (KH - 1) * pw + (KW - 1) + 128 * mt);
+  h.a_stage_bytes = (uint32_t)round_up(need_rows * row_bytes, 1024);
+  h.a_tx_bytes = (uint32_t)patch_rows * (uint32_t)row_bytes;
   const size_t avail = (size_t)227 * 1024 - 1024 - 3 * 1024 - 512;
   const size_t bstage = (size_t)k.block_n * 128;
-  h.a_stages = 2;
-  if ((size_t)3 * h.a_stage_bytes + 4 * bstage <= avail && h.cblocks > 1) h.a_stages = 3;
-  const size_t left = avail - (size_t)h.a_stages * h.a_stage_bytes;
-  h.b_stages = (int)std::min<size_t>(8, left / bstage);
-  if (h.b_stages < 2) return false;
+  const size_t b_all = (size_t)h.b_kblocks * bstage;
+  const int n_tiles_n = (k.Cout + k.block_n - 1) / k.block_n;
+  h.b_resident = (n_tiles_n == 1 && b_all + 2 * (size_t)h.a_stage_bytes <= avail) ? 1 : 0;
+  if (!h.b_resident && halo_ != 3) return false;  // halo:3 forces the streamed-weights variant (tests / A-B)
+  if (h.b_resident) {
+    h.a_stages = (int)std::min<size_t>(4, (avail - b_all) / h.a_stage_bytes);
+    h.b_stages = 1;
+  } else {
+    h.a_stages = 2;
+    if ((size_t)3 * h.a_stage_bytes + 4 * bstage <= avail && h.cblocks > 1) h.a_stages = 3;
+    const size_t left = avail - (size_t)h.a_stages * h.a_stage_bytes;
+    h.b_stages = (int)std::min<size_t>(8, left / bstage);
+    if (h.b_stages < 2) return false;
+  }
   h.tmem_cols = pow2_at_least(2 * mt * k.block_n);
   if (h.tmem_cols > 512) return false;
   h.num_sms = g_num_sms;
@@ -771,14 +798,15 @@ bool Net::plan_halo(ConvOp& c) {
   h.raw = k.raw; h.raw_cs = k.raw_cs; h.raw_coff = k.raw_coff;
   h.res = k.res; h.res_cs = k.res_cs; h.res_coff = k.res_coff;
   h.error_flag = k.error_flag;
-  // tiled map over the input [C, W, H, N]; box = one 64-channel block of the whole patch, zero fill outside
-  cuuint64_t dims[4] = {(cuuint64_t)k.Cin, (cuuint64_t)k.IW, (cuuint64_t)k.IH, (cuuint64_t)c.NB};
-  cuuint64_t strides[3] = {(cuuint64_t)k.x_sW * 2, (cuuint64_t)k.x_sH * 2, (cuuint64_t)k.x_sN * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)pw, (cuuint32_t)(R + k.KH - 1), 1};
+  // tiled map over [C, W, H, N]; box = one channel block of the whole patch, zero fill outside the image
+  cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)c.NB};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)(row_bytes / 2), (cuuint32_t)pw, (cuuint32_t)(R + KH - 1), 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc_tiled(&c.tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)k.x, dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc_tiled(&c.tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xbase), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   c.halo = true;
   c.halo_mt = mt;

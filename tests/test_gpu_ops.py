@@ -105,11 +105,14 @@ HALO = [
 ]
 
 
-@pytest.mark.parametrize("force_mt2", [False, True], ids=["mt1", "mt2"])
+@pytest.mark.parametrize("mode", ["auto", "mt2", "stream"])
 @pytest.mark.parametrize("case", HALO, ids=["h%d" % i for i in range(len(HALO))])
-def test_conv2d_halo_kernel(gpu, case, force_mt2):
+def test_conv2d_halo_kernel(gpu, case, mode):
+    # auto: weights resident in smem when they fit (else the im2col kernel); mt2: two 128-position halves per
+    # tile forced; stream: the halo kernel even when the weights must be streamed per tap
     shape, cmid, cout, k, s, p = case
-    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 1, check=("a_bn", "c", "c_bn"), halo=2 if force_mt2 else 1)
+    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 1, check=("a_bn", "c", "c_bn"),
+             halo={"auto": 1, "mt2": 2, "stream": 3}[mode])
 
 
 CONV3D = [
@@ -152,12 +155,14 @@ def test_conv3d_many_tiles_persistent(gpu):
     run_case(two_conv_net(shape, 128, 512, [3, 3, 3], [1, 1, 1], [1, 1, 1]), shape, 1, check=("c", "c_bn"))
 
 
-@pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
+@pytest.mark.parametrize("mode", ["gather", "im2col", "halo", "halo_mt2"])
 @pytest.mark.parametrize("hw", [(32, 32), (30, 34), (224, 224)])
-def test_stem_7x7_s2(gpu, hw, a_mode):
-    # conv1_7x7_s2 on fp32 NCHW input: space-to-depth transform + 4x1 window conv
+def test_stem_7x7_s2(gpu, hw, mode):
+    # conv1_7x7_s2 on fp32 NCHW input: space-to-depth transform, then either the 4x1 overlapping-window view
+    # (gather / im2col) or the halo kernel over 16-channel cells (32-byte swizzled rows, resident weights)
     shape = (2, 3) + hw
-    run_case(conv_net(shape, 64, [7, 7], [2, 2], [3, 3]), shape, a_mode, check=("c", "c_bn"))
+    run_case(conv_net(shape, 64, [7, 7], [2, 2], [3, 3]), shape, 0 if mode == "gather" else 1, check=("c", "c_bn"),
+             halo={"gather": 0, "im2col": 0, "halo": 1, "halo_mt2": 2}[mode])
 
 
 @pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])
