@@ -201,7 +201,7 @@ class Net {
   bool use_graph_ = false;
   int persistent_ = 1;
   int dual_m_ = 1;
-  int halo_ = 1;  // 0 off, 1 auto
+  int halo_ = 0;  // 0 off (default: measured slower, profiles/r01h), 1 auto (resident weights only), 2 force two halves, 3 allow streamed weights
   int debug_flags_ = 0;
   bool epi_staged_ = true;
   bool user_stream_ = false;
