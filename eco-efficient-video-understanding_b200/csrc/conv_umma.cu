@@ -516,7 +516,71 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t taddr_h
 //     tile i overlaps the MMAs of tile i+1; the smem ring streams across tile boundaries
 //   * 10 warps: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = epilogue; two epilogue warps
 //     per TMEM lane quarter split the 16-column chunks between them
-constexpr int kPersistThreads = 384;  // warps: 0 B producer, 1 MMA, 2-9 epilogue, 10-11 A producers
+constexpr int kPersistThreads = 320;  // persistent im2col kernel: warp 0 TMA producer, 1 MMA, 2-9 epilogue
+constexpr int kHaloThreads = 384;     // halo kernel: + warps 10-11 (weight-tile producers)
+
+// Computes one 16-column chunk of the epilogue for this thread's row.  `raw` (if any) is stored
+// directly; the final value y is written as 32 bytes of bf16 into the warp's staging row at
+// `stage_dst` (shared memory) -- the caller copies staged rows out with row-contiguous 16-byte
+// stores so that every global store instruction covers whole 32-byte sectors.
+__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32_t taddr, int m, bool row_ok, int cg,
+                                               int c0, const float* s_bias, const float* s_scale,
+                                               const float* s_shift, bool simple, uint32_t stage_dst) {
+  uint32_t v[16];
+  tmem_ld16(taddr, v);
+  const int nvalid = p.Cout - cg;
+  float f[16];
+  const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
+  const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
+  if (simple) {
+    // no raw / residual consumer: bias is pre-folded into the shift, y = relu?(acc * scale + shift')
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = sc4[j], b = sh4[j];
+      f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), a.x, b.x);
+      f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y);
+      f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z);
+      f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w);
+    }
+  } else {
+    const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b = bi4[j];
+      f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+      f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+      f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+      f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+    }
+    if (row_ok && nvalid > 0) {
+      if (p.res) load16_bf16_add(p.res + (long long)m * p.res_cs + p.res_coff + cg, f, nvalid);
+      if (p.raw) store16_bf16(p.raw + (long long)m * p.raw_cs + p.raw_coff + cg, f, nvalid);
+    }
+    if (!p.out) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = sc4[j], b = sh4[j];
+      f[4 * j + 0] = fmaf(f[4 * j + 0], a.x, b.x);
+      f[4 * j + 1] = fmaf(f[4 * j + 1], a.y, b.y);
+      f[4 * j + 2] = fmaf(f[4 * j + 2], a.z, b.z);
+      f[4 * j + 3] = fmaf(f[4 * j + 3], a.w, b.w);
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (!p.epi_staged) {
+    if (row_ok && nvalid > 0) store16_bf16(p.out + (long long)m * p.out_cs + p.out_coff + cg, f, nvalid);
+    return;
+  }
+  const uint32_t w0 = pack_bf16x2(f[0], f[1]), w1 = pack_bf16x2(f[2], f[3]), w2 = pack_bf16x2(f[4], f[5]),
+                 w3 = pack_bf16x2(f[6], f[7]), w4 = pack_bf16x2(f[8], f[9]), w5 = pack_bf16x2(f[10], f[11]),
+                 w6 = pack_bf16x2(f[12], f[13]), w7 = pack_bf16x2(f[14], f[15]);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_dst + 16), "r"(w4), "r"(w5), "r"(w6), "r"(w7)
+               : "memory");
+}
 
 template <int MT>
 __global__ void __launch_bounds__(kPersistThreads, 1)
@@ -544,6 +608,9 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   const uint32_t bar_tmem_full = bar_empty + 8 * S;      // [2]
   const uint32_t bar_tmem_empty = bar_tmem_full + 16;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  // epilogue staging: 8 warps x 32 rows x (epi_group chunks x 32 B + 16 B pad)
+  const uint32_t stage_pitch = (uint32_t)p.epi_group * 32u + 16u;
+  const uint32_t stage_base = smem_u32(bars) + 512u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -576,52 +643,42 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   const int num_kb = p.num_kb;
 
   if (warp == 0) {
-    // ===================== TMA producer: weight tiles (+ arms the stage barrier) =====================
-    // Three independent producer threads (this one and warps 10/11 for the two A halves) each issue one
-    // TMA per K block: the per-issue latency of a single thread (empty-wait + expect_tx + issue) no longer
-    // bounds the load rate of short-K tiles.
+    // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0;  // running K-block counter across tiles
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n0 = (t % n_tiles_n) * BN;
+        int cw[MT], chh[MT], cd[MT], cn[MT];
+        bool live[MT];  // a half that starts beyond the last output position is never loaded
         uint32_t tile_tx = b_stage_bytes;
 #pragma unroll
-        for (int h = 0; h < MT; ++h)
-          if ((t / n_tiles_n) * TILE_M + h * kBlockM < p.M) tile_tx += a_half_bytes;
+        for (int h = 0; h < MT; ++h) {
+          int r = (t / n_tiles_n) * TILE_M + h * kBlockM;
+          live[h] = r < p.M;
+          if (live[h]) tile_tx += a_half_bytes;
+          const int q = r % p.OW; r /= p.OW;
+          const int pp = r % p.OH; r /= p.OH;
+          const int z = r % p.OD;
+          cn[h] = r / p.OD;
+          cw[h] = q * p.sW - p.pW; chh[h] = pp * p.sH - p.pH; cd[h] = z * p.sD - p.pD;
+        }
+        int cb = 0, kx = 0, ky = 0, kz = 0;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % (uint32_t)S;
           const uint32_t ph = (it / (uint32_t)S) & 1u;
           mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, tile_tx);
           tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
-        }
-      }
-    }
-  } else if (warp >= 10) {
-    // ===================== TMA producers: activations, one warp per 128-row half =====================
-    const int h = warp - 10;
-    if (lane == 0 && h < MT) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int r = (t / n_tiles_n) * TILE_M + h * kBlockM;
-        const bool live = r < p.M;  // a half that starts beyond the last output position is never loaded
-        const int q = r % p.OW; r /= p.OW;
-        const int pp = r % p.OH; r /= p.OH;
-        const int z = r % p.OD;
-        const int n = r / p.OD;
-        const int cw = q * p.sW - p.pW, chh = pp * p.sH - p.pH, cd = z * p.sD - p.pD;
-        int cb = 0, kx = 0, ky = 0, kz = 0;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          if (live) {
-            const uint32_t s = it % (uint32_t)S;
-            const uint32_t ph = (it / (uint32_t)S) & 1u;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 8);
+#pragma unroll
+          for (int h = 0; h < MT; ++h) {
+            if (!live[h]) continue;
             const uint32_t dst = sA + s * a_stage_bytes + h * a_half_bytes;
             if (p.nsp == 3)
-              tma_im2col_5d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, cd, n, (uint16_t)kx, (uint16_t)ky,
-                            (uint16_t)kz);
+              tma_im2col_5d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cd[h], cn[h], (uint16_t)kx,
+                            (uint16_t)ky, (uint16_t)kz);
             else
-              tma_im2col_4d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, n, (uint16_t)kx, (uint16_t)ky);
+              tma_im2col_4d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cn[h], (uint16_t)kx,
+                            (uint16_t)ky);
           }
           if (++cb == p.cblocks) {
             cb = 0;
@@ -653,8 +710,7 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
             const uint64_t adesc = make_sw128_desc(sA + s * a_stage_bytes + h * a_half_bytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              if (!(p.debug_flags & 4))
-                umma_bf16(acc + (uint32_t)(h * BN), adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+              umma_bf16(acc + (uint32_t)(h * BN), adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
           }
           umma_commit(bar_empty + 8 * s);
         }
@@ -667,14 +723,6 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
     const int half = (warp - 2) >> 2;   // which of the two warps of that quarter
     const int chunks = BN >> 4;
     const bool simple = (p.res == nullptr) && (p.raw == nullptr) && (p.out != nullptr);
-    EpiArgs e;
-    e.out = p.out; e.out_cs = p.out_cs; e.out_coff = p.out_coff;
-    e.raw = p.raw; e.raw_cs = p.raw_cs; e.raw_coff = p.raw_coff;
-    e.res = p.res; e.res_cs = p.res_cs; e.res_coff = p.res_coff;
-    e.Cout = p.Cout; e.relu = p.relu; e.simple = simple ? 1 : 0; e.dbg = p.debug_flags;
-    const int M = p.M;
-    const int c_begin = half ? (chunks + 1) / 2 : 0;
-    const int c_end = half ? chunks : (chunks + 1) / 2;
     uint32_t tile_iter = 0;
     int loaded_n0 = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
@@ -699,12 +747,45 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
       const uint32_t use = tile_iter >> 1;
       mbar_wait(bar_tmem_full + 8 * buf, use & 1u, p.error_flag, 4);
       tc_fence_after();
-      const int mbase = m0 + wq * 32 + lane;
-      epilogue_tile<MT>(e, tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols, BN, n0, c_begin, c_end, s_bias,
-                        s_scale, s_shift, [&](int h, long long& m, bool& ok) {
-                          m = mbase + h * kBlockM;
-                          ok = m < M;
-                        });
+#pragma unroll
+      for (int h = 0; h < MT; ++h) {
+        const int mrow0 = m0 + h * kBlockM + wq * 32;  // first output position of this warp's 32 rows
+        const int m = mrow0 + lane;
+        const bool row_ok = m < p.M;
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols + (uint32_t)(h * BN);
+        // this warp's contiguous chunk range: the two warps of a lane quarter split the columns in half
+        const int c_begin = half ? (chunks + 1) / 2 : 0;
+        const int c_end = half ? chunks : (chunks + 1) / 2;
+        const uint32_t my_stage = stage_base + (uint32_t)(warp - 2) * 32u * stage_pitch;
+        for (int cgrp = c_begin; cgrp < c_end; cgrp += p.epi_group) {
+          const int gcount = min(p.epi_group, c_end - cgrp);
+          for (int k = 0; k < gcount; ++k) {
+            const int c = cgrp + k;
+            epilogue_chunk(p, taddr + (uint32_t)(c * 16), m, row_ok, n0 + c * 16, c * 16, s_bias, s_scale, s_shift,
+                           simple, my_stage + (uint32_t)lane * stage_pitch + (uint32_t)k * 32u);
+          }
+          if (p.out && p.epi_staged) {
+            __syncwarp();
+            // copy out: consecutive lanes take consecutive 16-byte pieces of a row -> whole sectors / lines
+            const int ppr = gcount * 2;  // 16-byte pieces per row in this group
+            const int col0 = n0 + cgrp * 16;
+            for (int idx = lane; idx < 32 * ppr; idx += 32) {
+              const int r = idx / ppr;
+              const int piece = idx - r * ppr;
+              const int mm = mrow0 + r;
+              const int col = col0 + piece * 8;
+              if (mm < p.M && col < p.Cout) {
+                uint4 val;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                             : "r"(my_stage + (uint32_t)r * stage_pitch + (uint32_t)piece * 16u));
+                *reinterpret_cast<uint4*>(p.out + (long long)mm * p.out_cs + p.out_coff + col) = val;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -735,7 +816,7 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
 //   B      = weights [Cout][tap][64] K-major, one TMA tile per (tap, channel block), own ring
 //   rest   = as conv_umma_persistent_kernel: TMEM double buffer, 8 epilogue warps
 template <int MT>
-__global__ void __launch_bounds__(kPersistThreads, 1)
+__global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ uint8_t smem_raw[];
@@ -961,15 +1042,15 @@ cudaError_t launch_conv_halo(const HaloKernelParams& p, int m_halves, const CUte
   const int tiles = p.NB * p.bands * ((p.Cout + p.block_n - 1) / p.block_n);
   const int grid = tiles < p.num_sms ? tiles : p.num_sms;
   const size_t smem = halo_smem_bytes(p);
-  if (m_halves == 2) conv_halo_kernel<2><<<grid, kPersistThreads, smem, stream>>>(p, tmX, tmB);
-  else conv_halo_kernel<1><<<grid, kPersistThreads, smem, stream>>>(p, tmX, tmB);
+  if (m_halves == 2) conv_halo_kernel<2><<<grid, kHaloThreads, smem, stream>>>(p, tmX, tmB);
+  else conv_halo_kernel<1><<<grid, kHaloThreads, smem, stream>>>(p, tmX, tmB);
   return cudaGetLastError();
 }
 
 cudaError_t launch_conv_umma(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                              cudaStream_t stream) {
   const size_t smem = conv_smem_bytes(p.block_n, p.stages, p.persistent ? p.m_halves : 1,
-                                      p.persistent ? conv_epi_stage_bytes(p.epi_group) : 0);
+                                      (p.persistent && p.epi_staged) ? conv_epi_stage_bytes(p.epi_group) : 0);
   if (p.persistent) {
     const int tile_m = kBlockM * p.m_halves;
     const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.Cout + p.block_n - 1) / p.block_n);

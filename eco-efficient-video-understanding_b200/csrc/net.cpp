@@ -1390,10 +1390,10 @@ void Net::plan() {
             // shared memory: 227 KB - alignment slack - constants - barriers; the epilogue staging takes
             // 4 chunks per copy-out (128-byte row pieces) unless that would cost a pipeline stage
             const size_t avail = (size_t)227 * 1024 - 1024 - 3 * 1024 - 512;
-            kp.epi_group = 0;  // the epilogue keeps its values in registers and stores 64-byte row pieces directly
-            kp.epi_staged = 0;
+            kp.epi_group = 4;   // chunks per epilogue group
+            kp.epi_staged = epi_staged_ ? 1 : 0;  // default 0: direct 32-byte row-piece stores (measured faster, profiles/r01i)
             kp.debug_flags = debug_flags_;
-            kp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (avail - conv_epi_stage_bytes(kp.epi_group)) / stage_bytes));
+            kp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (avail - (kp.epi_staged ? conv_epi_stage_bytes(kp.epi_group) : 0)) / stage_bytes));
             kp.tmem_cols = pow2_at_least(2 * kp.m_halves * kp.block_n);
           } else {
             const size_t budget = kp.block_n <= 128 ? 100 * 1024 : 200 * 1024;

@@ -203,7 +203,7 @@ class Net {
   int dual_m_ = 1;
   int halo_ = 0;  // 0 off (default: measured slower, profiles/r01h), 1 auto (resident weights only), 2 force two halves, 3 allow streamed weights
   int debug_flags_ = 0;
-  bool epi_staged_ = true;
+  bool epi_staged_ = false;
   bool user_stream_ = false;
   // plan
   bool planned_ = false;
