@@ -47,50 +47,59 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled through NVML
+    every 5 ms (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []          # (t, sm_mhz, reasons bitmask)
         self.stop_flag = False
-        self.proc = None
+        self.max_mhz = None
+        self.windows = []       # [(t0, t1)] timed regions
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-                if self.stop_flag:
-                    break
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical GPUs; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                try:
+                    mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    try:
+                        rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.rows.append((time.perf_counter(), float(mhz), int(rs)))
+                except Exception:
+                    pass
+                time.sleep(0.005)
         except Exception:
             pass
 
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
     def finish(self):
         self.stop_flag = True
-        if self.proc:
-            try:
-                self.proc.terminate()
-            except Exception:
-                pass
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
+        self.join(timeout=1.0)
+        inside = [r for r in self.rows if any(a <= r[0] <= b for a, b in self.windows)] or self.rows
+        sm = [r[1] for r in inside]
+        reasons = set()
+        for r in inside:
+            for bit, name in self.REASONS.items():
+                if r[2] & bit:
                     reasons.add(name)
-        busy = [v for v in sm if v > 0]
-        return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=self.max_mhz, reasons=sorted(reasons),
+                    samples=len(sm))
 
 
 def cpu_reference_forward(model, segments, steps, warmup, threads=None):
@@ -192,13 +201,14 @@ def main():
     sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
     e0.record(stream)
     for _ in range(a.steps):
         net._forward(0, len(net.layers) - 1)
     e1.record(stream)
     barrier()
+    sampler.window(tw0, time.perf_counter())
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.finish()
     net.sync()
     launches = net.last_launch_count() * a.steps
     ms_step = ms_total / a.steps
@@ -222,6 +232,7 @@ def main():
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.window(t0, time.perf_counter())
     e2e_value = world * B * a.steps / (max(e2e_ms, wall_ms) / 1e3)
     assert np.isfinite(logits).all()
 
@@ -251,6 +262,8 @@ def main():
         if tk is not None:
             net.wait(tk)
     pipe_ms = grp.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    sampler.window(t0, time.perf_counter())
+    clocks = sampler.finish()
     e2e_pipe_value = world * B * a.steps / (pipe_ms / 1e3)
     assert torch.isfinite(pin_out[0]).all()
 
