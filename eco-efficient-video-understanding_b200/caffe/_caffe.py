@@ -67,6 +67,8 @@ def lib():
     L.eco_net_set_input_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.eco_blob_device_f32.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.eco_net_forward_pipelined.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+    L.eco_net_forward_pipelined_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_float), C.c_int, C.c_void_p,
+                                               C.c_size_t, C.POINTER(C.c_int)]
     L.eco_net_wait.argtypes = [C.c_void_p, C.c_int]
     L.eco_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.eco_host_free.argtypes = [C.c_void_p]

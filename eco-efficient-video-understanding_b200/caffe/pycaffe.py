@@ -203,6 +203,14 @@ class Net(object):
                                               C.c_void_p(int(host_out_ptr)), int(out_count), C.byref(t)))
         return t.value
 
+    def forward_pipelined_u8(self, host_in_ptr, count, mean, host_out_ptr, out_count):
+        """As forward_pipelined, fed from raw uint8 frames [F,3,H,W]; `mean` (per channel) is subtracted on the GPU."""
+        t = C.c_int()
+        m = (C.c_float * len(mean))(*[float(v) for v in mean])
+        check(lib().eco_net_forward_pipelined_u8(self._h, C.c_void_p(int(host_in_ptr)), int(count), m, len(mean),
+                                                 C.c_void_p(int(host_out_ptr)), int(out_count), C.byref(t)))
+        return t.value
+
     def wait(self, ticket):
         check(lib().eco_net_wait(self._h, int(ticket)))
 

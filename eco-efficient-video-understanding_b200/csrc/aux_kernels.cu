@@ -66,6 +66,46 @@ __global__ void stem_s2d_kernel(const float* __restrict__ src, __nv_bfloat16* __
   }
 }
 
+__global__ void stem_s2d_u8_kernel(const unsigned char* __restrict__ src, __nv_bfloat16* __restrict__ dst, int F, int H,
+                                   int W, int CH, int CW, float m0, float m1, float m2) {
+  const long long total = (long long)F * CH * CW;
+  const float mean[3] = {m0, m1, m2};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(t % CW);
+    const int Y = (int)((t / CW) % CH);
+    const long long f = t / ((long long)CW * CH);
+    const unsigned char* img = src + f * 3LL * H * W;
+    __align__(16) __nv_bfloat16 cell[16];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int y = 2 * Y + dy - 3, x = 2 * X + dx - 3;
+        const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          cell[(dy * 2 + dx) * 3 + c] =
+              __float2bfloat16_rn(ok ? (float)img[((long long)c * H + y) * W + x] - mean[c] : 0.f);
+      }
+#pragma unroll
+    for (int j = 12; j < 16; ++j) cell[j] = __float2bfloat16_rn(0.f);
+    uint4* o = reinterpret_cast<uint4*>(dst + t * 16);
+    o[0] = reinterpret_cast<const uint4*>(cell)[0];
+    o[1] = reinterpret_cast<const uint4*>(cell)[1];
+  }
+}
+__global__ void u8_to_f32_mean_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, long long outer, int C,
+                                      long long inner, float m0, float m1, float m2, float m3) {
+  const float mean[4] = {m0, m1, m2, m3};
+  const long long total = outer * C * inner;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((t / inner) % C);
+    dst[t] = (float)src[t] - mean[c & 3];
+  }
+}
+
 // ---------------------------------------------------------------- pooling, channels-last
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -517,6 +557,20 @@ cudaError_t launch_stem_s2d(const float* src, __nv_bfloat16* dst, int F, int H, 
   const long long n = (long long)F * CH * CW;
   if (n == 0) return cudaSuccess;
   stem_s2d_kernel<<<grid_cap(n), kThreads, 0, st>>>(src, dst, F, H, W, CH, CW);
+  return cudaGetLastError();
+}
+cudaError_t launch_stem_s2d_u8(const unsigned char* src, __nv_bfloat16* dst, int F, int H, int W, int CH, int CW,
+                               float mean0, float mean1, float mean2, cudaStream_t st) {
+  const long long n = (long long)F * CH * CW;
+  if (n == 0) return cudaSuccess;
+  stem_s2d_u8_kernel<<<grid_cap(n), kThreads, 0, st>>>(src, dst, F, H, W, CH, CW, mean0, mean1, mean2);
+  return cudaGetLastError();
+}
+cudaError_t launch_u8_to_f32_mean(const unsigned char* src, float* dst, long long outer, int C, long long inner,
+                                  float mean0, float mean1, float mean2, float mean3, cudaStream_t st) {
+  const long long n = outer * C * inner;
+  if (n == 0) return cudaSuccess;
+  u8_to_f32_mean_kernel<<<grid_cap(n), kThreads, 0, st>>>(src, dst, outer, C, inner, mean0, mean1, mean2, mean3);
   return cudaGetLastError();
 }
 cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {

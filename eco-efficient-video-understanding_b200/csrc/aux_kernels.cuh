@@ -24,6 +24,13 @@ cudaError_t launch_cl_to_f32(ClView src, float* dst, cudaStream_t st);
 // (cell (Y,X) channel (dy*2+dx)*3+c = x[c][2Y+dy-3][2X+dx-3], zero outside / channels 12..15).
 cudaError_t launch_stem_s2d(const float* src, __nv_bfloat16* dst, int F, int H, int W, int CH, int CW,
                             cudaStream_t st);
+// the same from raw uint8 frames [F,3,H,W] with the per-channel mean subtracted on the fly
+// (what DataTransformer::Transform does on the host in the reference, data_transformer.cpp:50-325: mean_value, no scale)
+cudaError_t launch_stem_s2d_u8(const unsigned char* src, __nv_bfloat16* dst, int F, int H, int W, int CH, int CW,
+                               float mean0, float mean1, float mean2, cudaStream_t st);
+// uint8 [outer, C, inner] -> fp32 minus per-channel mean (generic fallback for non-stem inputs, C <= 4)
+cudaError_t launch_u8_to_f32_mean(const unsigned char* src, float* dst, long long outer, int C, long long inner,
+                                  float mean0, float mean1, float mean2, float mean3, cudaStream_t st);
 
 struct PoolParams {
   const __nv_bfloat16* x; long long x_cs; int x_coff;

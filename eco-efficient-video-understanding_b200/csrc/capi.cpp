@@ -280,6 +280,14 @@ int eco_net_forward_pipelined(eco_net* net, const float* host_in, size_t count, 
   if (ticket) *ticket = t;
   ECO_API_END
 }
+int eco_net_forward_pipelined_u8(eco_net* net, const unsigned char* host_in, size_t count, const float* mean, int nmean,
+                                 float* host_out, size_t out_count, int* ticket) {
+  ECO_API_BEGIN
+  if (!g_mode_gpu) throw std::runtime_error("set_mode_cpu() was requested: libeco_b200 has no CPU execution path");
+  const int t = N(net).forward_pipelined_u8(host_in, count, mean, nmean, host_out, out_count);
+  if (ticket) *ticket = t;
+  ECO_API_END
+}
 int eco_net_wait(eco_net* net, int ticket) {
   ECO_API_BEGIN
   N(net).wait_ticket(ticket);

@@ -145,8 +145,15 @@ __device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const float (&f
     a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
     b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
     b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
-    reinterpret_cast<uint4*>(dst)[0] = a;
-    reinterpret_cast<uint4*>(dst)[1] = b;
+    if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+      // one 256-bit store = one whole 32-byte sector per request (STG.E.ENL2.256 on sm_100a)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z),
+                   "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                   : "memory");
+    } else {
+      reinterpret_cast<uint4*>(dst)[0] = a;
+      reinterpret_cast<uint4*>(dst)[1] = b;
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)

@@ -629,6 +629,7 @@ void Net::free_plan() {
       pipe_slot_[i] = nullptr;
     }
     pipe_iter_ = 0;
+    pipe_elem_bytes_ = 0;
   }
   if (!allocs_.empty()) {
     if (stream_) cudaStreamSynchronize(stream_);
@@ -1700,6 +1701,18 @@ void Net::sync() {
 // forward reads straight from a staging slot).
 void Net::run_input_xform(ConvOp& c, const float* src) {
   Tensor& x = tensors_[c.in_tensor];
+  if (u8_src_) {
+    // raw uint8 frames: mean subtraction fused into the transform (stem) or into a conversion pass
+    const unsigned char* u8 = static_cast<const unsigned char*>(u8_src_);
+    if (c.stem) {
+      CUDA_OK(launch_stem_s2d_u8(u8, c.stem_in, c.NB, c.I[1], c.I[2], c.stem_CH, c.stem_CW, u8_mean_[0], u8_mean_[1],
+                                 u8_mean_[2], stream_));
+      return;
+    }
+    CUDA_OK(launch_u8_to_f32_mean(u8, static_cast<float*>(x.dev), c.NB, c.Cin, (long long)c.I[0] * c.I[1] * c.I[2],
+                                  u8_mean_[0], u8_mean_[1], u8_mean_[2], u8_mean_[3], stream_));
+    src = nullptr;
+  }
   const float* in = src ? src : static_cast<const float*>(x.dev);
   if (c.stem) {
     CUDA_OK(launch_stem_s2d(in, c.stem_in, c.NB, c.I[1], c.I[2], c.stem_CH, c.stem_CW, stream_));
@@ -1818,17 +1831,31 @@ void Net::run_ops(bool full, int lo, int hi, const float* input_override, int* l
 // The caller owns two (pinned) input buffers and alternates them; results are copied to `host_out`
 // asynchronously and are valid after wait_ticket().
 int Net::forward_pipelined(const float* host_in, size_t count, float* host_out, size_t out_count) {
+  return forward_pipelined_any(host_in, count, 4, nullptr, host_out, out_count);
+}
+int Net::forward_pipelined_u8(const unsigned char* host_in, size_t count, const float* mean, int nmean, float* host_out,
+                              size_t out_count) {
+  float m[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4 && i < nmean; ++i) m[i] = mean[i];
+  return forward_pipelined_any(host_in, count, 1, m, host_out, out_count);
+}
+
+int Net::forward_pipelined_any(const void* host_in, size_t count, int elem_bytes, const float* mean4, float* host_out,
+                               size_t out_count) {
   if (!planned_) plan();
   upload_params();
   ECO_CHECK(inputs_.size() >= 1 && outputs_.size() >= 1, "forward_pipelined needs one input and one output blob");
   Tensor& tin = tensors_[vis_blobs_[inputs_[0]].tensor];
   Tensor& tout = tensors_[vis_blobs_[outputs_[0]].tensor];
   ECO_CHECK(tin.kind == Kind::F32 && count == (size_t)tin.count(), "forward_pipelined: input size mismatch");
+  ECO_CHECK(pipe_elem_bytes_ == 0 || pipe_elem_bytes_ == elem_bytes,
+            "forward_pipelined: do not mix fp32 and uint8 calls on one net without a reshape");
+  pipe_elem_bytes_ = elem_bytes;
   ECO_CHECK(tout.kind == Kind::F32 && tout.dev && out_count == (size_t)tout.count(), "forward_pipelined: output size mismatch");
   if (!copy_stream_) {
     CUDA_OK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-      pipe_slot_[i] = static_cast<float*>(dalloc(count * 4, false));
+      pipe_slot_[i] = static_cast<float*>(dalloc(count * (size_t)elem_bytes, false));
       CUDA_OK(cudaEventCreateWithFlags(&ev_h2d_[i], cudaEventDisableTiming));
       CUDA_OK(cudaEventCreateWithFlags(&ev_slot_free_[i], cudaEventDisableTiming));
       CUDA_OK(cudaEventCreateWithFlags(&ev_done_[i], cudaEventDisableTiming));
@@ -1836,7 +1863,7 @@ int Net::forward_pipelined(const float* host_in, size_t count, float* host_out, 
   }
   const int slot = (int)(pipe_iter_ & 1);
   if (pipe_iter_ >= 2) CUDA_OK(cudaStreamWaitEvent(copy_stream_, ev_slot_free_[slot], 0));
-  CUDA_OK(cudaMemcpyAsync(pipe_slot_[slot], host_in, count * 4, cudaMemcpyHostToDevice, copy_stream_));
+  CUDA_OK(cudaMemcpyAsync(pipe_slot_[slot], host_in, count * (size_t)elem_bytes, cudaMemcpyHostToDevice, copy_stream_));
   CUDA_OK(cudaEventRecord(ev_h2d_[slot], copy_stream_));
   CUDA_OK(cudaStreamWaitEvent(stream_, ev_h2d_[slot], 0));
   bool xform_only_input = false;
@@ -1845,11 +1872,17 @@ int Net::forward_pipelined(const float* host_in, size_t count, float* host_out, 
       xform_only_input = true;
   ECO_CHECK(xform_only_input, "forward_pipelined: the net input must feed a convolution directly");
   int launches = 0;
-  if (use_graph_) {
-    run_ops(true, 0, 0, pipe_slot_[slot], &launches);  // transforms read the slot, graph covers the rest
-  } else {
-    run_ops(true, 0, 0, pipe_slot_[slot], &launches);
+  if (mean4) {
+    u8_src_ = pipe_slot_[slot];
+    for (int i = 0; i < 4; ++i) u8_mean_[i] = mean4[i];
   }
+  try {
+    run_ops(true, 0, 0, mean4 ? nullptr : pipe_slot_[slot], &launches);  // transforms read the slot; the graph covers the rest
+  } catch (...) {
+    u8_src_ = nullptr;
+    throw;
+  }
+  u8_src_ = nullptr;
   // the slot is free once the transform has consumed it; conservatively: once this forward is enqueued
   // up to here the transform is the first kernel, so record right after the whole enqueue is cheap too
   CUDA_OK(cudaEventRecord(ev_slot_free_[slot], stream_));

@@ -176,6 +176,8 @@ class Net {
   void reshape();
   float forward(int start, int end);
   int forward_pipelined(const float* host_in, size_t count, float* host_out, size_t out_count);
+  int forward_pipelined_u8(const unsigned char* host_in, size_t count, const float* mean, int nmean, float* host_out,
+                           size_t out_count);
   void wait_ticket(int ticket);
   void sync();
   float* host_data(int vis_blob, bool for_write, size_t* count);
@@ -222,6 +224,11 @@ class Net {
   float* pipe_slot_[2] = {nullptr, nullptr};
   cudaEvent_t ev_h2d_[2] = {nullptr, nullptr}, ev_slot_free_[2] = {nullptr, nullptr}, ev_done_[2] = {nullptr, nullptr};
   unsigned long long pipe_iter_ = 0;
+  int pipe_elem_bytes_ = 0;
+  const void* u8_src_ = nullptr;
+  float u8_mean_[4] = {0, 0, 0, 0};
+  int forward_pipelined_any(const void* host_in, size_t count, int elem_bytes, const float* mean4, float* host_out,
+                            size_t out_count);
 
   void build_graph();
   void init_params();

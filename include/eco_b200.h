@@ -114,6 +114,11 @@ int eco_blob_device_f32(eco_net* net, int blob, const float** dev, size_t* count
  * two buffer pairs. */
 int eco_net_forward_pipelined(eco_net* net, const float* host_in, size_t count, float* host_out, size_t out_count,
                               int* ticket);
+/* the same fed from raw uint8 frames (caffe Datum layout [F,3,H,W]); `mean` (per channel, BGR order as in
+ * transform_param.mean_value) is subtracted on the device -- the part of DataTransformer::Transform
+ * (data_transformer.cpp) that the reference runs on the host before the data blob exists.  4x fewer PCIe bytes. */
+int eco_net_forward_pipelined_u8(eco_net* net, const unsigned char* host_in, size_t count, const float* mean, int nmean,
+                                 float* host_out, size_t out_count, int* ticket);
 int eco_net_wait(eco_net* net, int ticket);
 int eco_host_alloc(void** ptr, size_t bytes);   /* page-locked host memory */
 int eco_host_free(void* ptr);

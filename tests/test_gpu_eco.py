@@ -176,3 +176,31 @@ def test_pipelined_forward_matches_blocking_forward(gpu):
         for pi, po, _, _ in bufs:
             _caffe.lib().eco_host_free(pi)
             _caffe.lib().eco_host_free(po)
+
+
+def test_pipelined_uint8_frames_match_fp32_path(gpu):
+    """Raw uint8 frames + on-device mean subtraction (eco_net_forward_pipelined_u8) give bit-identical logits to
+    feeding `frame - mean` as fp32 through the caffe-style blob (what the reference's DataTransformer produces)."""
+    import ctypes
+    from caffe import _caffe
+    segments, batch = 4, 2
+    txt, ref, _ = oracle_lite(segments, batch)
+    net = make_net(txt, keep_all=False, graph=True)
+    load_params(net, ref.params_dict())
+    rng = np.random.default_rng(7)
+    mean = [104.0, 117.0, 123.0]
+    count, ocount = batch * segments * 3 * 224 * 224, batch * 101
+    pi, po = ctypes.c_void_p(), ctypes.c_void_p()
+    _caffe.check(_caffe.lib().eco_host_alloc(ctypes.byref(pi), count))
+    _caffe.check(_caffe.lib().eco_host_alloc(ctypes.byref(po), ocount * 4))
+    hin = np.ctypeslib.as_array(ctypes.cast(pi, ctypes.POINTER(ctypes.c_ubyte)), (count,))
+    hout = np.ctypeslib.as_array(ctypes.cast(po, ctypes.POINTER(ctypes.c_float)), (ocount,))
+    for _ in range(3):
+        u8 = rng.integers(0, 256, size=(batch * segments, 3, 224, 224), dtype=np.uint8)
+        net.blobs["data"].data[...] = u8.astype(np.float32) - np.array(mean, np.float32).reshape(1, 3, 1, 1)
+        want = net.forward()["fc8"].copy()
+        hin[:] = u8.ravel()
+        net.wait(net.forward_pipelined_u8(pi.value, count, mean, po.value, ocount))
+        assert np.array_equal(hout.reshape(batch, 101), want)
+    _caffe.lib().eco_host_free(pi)
+    _caffe.lib().eco_host_free(po)
