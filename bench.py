@@ -106,6 +106,18 @@ def cpu_reference_forward(model, segments, steps, warmup, threads=None):
     """The reference arm / cpu_baseline: oracle fp32 forward (caffe_3d's CPU algorithm), one clip per step."""
     import gen_eco_prototxt as gen
     from oracle import refnet
+    if not threads:
+        # all the host *cores* it can use: one OpenMP thread per physical core (SMT siblings only add
+        # contention to the SGEMM: 128 logical CPUs ran 50x slower than 64 threads on the GPU box's host)
+        try:
+            import psutil
+            threads = psutil.cpu_count(logical=False) or os.cpu_count()
+        except Exception:
+            threads = max(1, (os.cpu_count() or 2) // 2)
+        try:
+            threads = min(threads, len(os.sched_getaffinity(0)))
+        except Exception:
+            pass
     if threads:
         refnet.lib().ref_set_num_threads(int(threads))
     cores = int(refnet.lib().ref_num_threads())
