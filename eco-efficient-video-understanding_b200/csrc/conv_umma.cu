@@ -14,6 +14,7 @@
 //
 // Every mbarrier wait is bounded: a wait that exceeds ~2 s sets *error_flag and traps, so a
 // protocol bug fails loudly instead of hanging the GPU.
+#include <cstdio>
 #include "conv_umma.cuh"
 
 namespace eco {
@@ -178,6 +179,60 @@ __device__ __forceinline__ void load16_bf16_add(const __nv_bfloat16* src, float 
   }
 }
 
+// Exactly one lane of a converged warp.  The tcgen05 / TMA instructions take uniform-register operands: issued
+// under `if (lane == 0)` ptxas cannot prove a single active thread and wraps EVERY such instruction in an
+// ELECT / BRA.U.ANY serialisation loop (seen in the SASS, ~60 issue cycles per tcgen05.mma whatever N, measured
+// in tools/probe_commit.cu); under elect.sync it emits the bare instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// One K block of the main loop (call from the elected lane): up to 4 K steps into accumulator 0 and, if `live1`,
+// into accumulator 1 (second 128-row half sharing the weight tile), then tcgen05.commit -> `empty_bar`.
+__device__ __forceinline__ void mma_kblock(uint32_t acc0, uint32_t acc1, uint64_t ad0, uint64_t ad1, uint64_t bd,
+                                           uint32_t accflag, uint32_t ks, uint32_t live1, uint32_t idesc,
+                                           uint32_t empty_bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, ptrue, g1, g2, g3, h0, h1, h2, h3;\n\t"
+      ".reg .b64 a, b;\n\t"
+      "setp.ne.b32 pacc, %5, 0;\n\t"
+      "setp.eq.u32 ptrue, %8, %8;\n\t"
+      "setp.gt.u32 g1, %6, 1;\n\t"
+      "setp.gt.u32 g2, %6, 2;\n\t"
+      "setp.gt.u32 g3, %6, 3;\n\t"
+      "setp.ne.b32 h0, %7, 0;\n\t"
+      "and.pred h1, h0, g1;\n\t"
+      "and.pred h2, h0, g2;\n\t"
+      "and.pred h3, h0, g3;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %4, %8, pacc;\n\t"
+      "add.s64 a, %2, 2;\n\t"
+      "add.s64 b, %4, 2;\n\t"
+      "@g1 tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %8, ptrue;\n\t"
+      "add.s64 a, %2, 4;\n\t"
+      "add.s64 b, %4, 4;\n\t"
+      "@g2 tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %8, ptrue;\n\t"
+      "add.s64 a, %2, 6;\n\t"
+      "add.s64 b, %4, 6;\n\t"
+      "@g3 tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %8, ptrue;\n\t"
+      "@h0 tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %8, pacc;\n\t"
+      "add.s64 a, %3, 2;\n\t"
+      "add.s64 b, %4, 2;\n\t"
+      "@h1 tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %8, ptrue;\n\t"
+      "add.s64 a, %3, 4;\n\t"
+      "add.s64 b, %4, 4;\n\t"
+      "@h2 tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %8, ptrue;\n\t"
+      "add.s64 a, %3, 6;\n\t"
+      "add.s64 b, %4, 6;\n\t"
+      "@h3 tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %8, ptrue;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+      "}"
+      ::"r"(acc0), "r"(acc1), "l"(ad0), "l"(ad1), "l"(bd), "r"(accflag), "r"(ks), "r"(live1), "r"(idesc), "r"(empty_bar)
+      : "memory");
+}
+
 // One epilogue warp's share of a tile: TMEM lane = output position `m`, columns = output channels.
 //   raw = acc + bias (+ residual) -> optional bf16 store ; y = relu?(raw*scale + shift) -> bf16 store
 __device__ __forceinline__ void epilogue_rows(const ConvKernelParams& p, uint32_t taddr, int m, bool row_ok, int n0,
@@ -272,8 +327,8 @@ conv_umma_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap t
   const int num_kb = p.num_kb;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the ring, one elected lane issues) =====================
+    {
       int q = 0, pp = 0, z = 0, n = 0;
       if (tma_a) {
         int t = m0;
@@ -284,46 +339,51 @@ conv_umma_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap t
       const int cw = q * p.sW - p.pW, chh = pp * p.sH - p.pH, cd = z * p.sD - p.pD;
       int cb = 0, kx = 0, ky = 0, kz = 0;
       const uint32_t tx_bytes = b_stage_bytes + (tma_a ? a_stage_bytes : 0u);
+      uint32_t s = 0, ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (uint32_t)(kb / S) & 1u;
         mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
-        mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
-        tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
-        if (tma_a) {
-          if (p.nsp == 3)
-            tma_im2col_5d(sA + s * a_stage_bytes, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, cd, n,
-                          (uint16_t)kx, (uint16_t)ky, (uint16_t)kz);
-          else
-            tma_im2col_4d(sA + s * a_stage_bytes, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, n,
-                          (uint16_t)kx, (uint16_t)ky);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
+          tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
+          if (tma_a) {
+            if (p.nsp == 3)
+              tma_im2col_5d(sA + s * a_stage_bytes, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, cd, n,
+                            (uint16_t)kx, (uint16_t)ky, (uint16_t)kz);
+            else
+              tma_im2col_4d(sA + s * a_stage_bytes, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, n,
+                            (uint16_t)kx, (uint16_t)ky);
+          }
         }
         if (++cb == p.cblocks) {
           cb = 0;
           if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++kz; } }
         }
+        if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp walks the ring, one elected lane issues) =====================
+    {
       const uint32_t idesc = make_idesc(BN);
+      // the last channel block of a tap may hold fewer than 64 channels (Cin = 96: 64 + 32): its all-zero K steps are skipped
+      const uint32_t tail_k = (uint32_t)(((p.Cin & (kBlockK - 1)) + kUmmaK - 1) / kUmmaK);  // 0: every block is full
+      const uint64_t adesc0 = make_sw128_desc(sA), bdesc0 = make_sw128_desc(sB);
+      const uint32_t a_step = a_stage_bytes >> 4, b_step = b_stage_bytes >> 4;
+      uint32_t s = 0, ph = 0, cb = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (uint32_t)(kb / S) & 1u;
         mbar_wait(bar_full + 8 * s, ph, p.error_flag, 2);
         if (!tma_a) fence_proxy_async_smem();  // cp.async (generic proxy) writes -> async-proxy reads
         tc_fence_after();
-        const uint64_t adesc = make_sw128_desc(sA + s * a_stage_bytes);
-        const uint64_t bdesc = make_sw128_desc(sB + s * b_stage_bytes);
-#pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+        uint32_t ks = 4;
+        if (tail_k) {
+          if (++cb == (uint32_t)p.cblocks) { cb = 0; ks = tail_k; }
         }
-        umma_commit(bar_empty + 8 * s);  // frees the smem slot when these MMAs retire
+        if (elect_one())
+          mma_kblock(tmem_base, tmem_base, adesc0 + (uint64_t)(s * a_step), 0, bdesc0 + (uint64_t)(s * b_step),
+                     (uint32_t)(kb != 0), ks, 0u, idesc, bar_empty + 8 * s);
+        if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
       }
-      umma_commit(bar_tmem_full);        // accumulator complete
+      if (elect_one()) umma_commit(bar_tmem_full);  // accumulator complete
     }
   } else {
     // ===================== gather producers (A_GATHER) then epilogue =====================
@@ -650,9 +710,9 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   const int num_kb = p.num_kb;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t it = 0;  // running K-block counter across tiles
+    // ===================== TMA producer (whole warp walks the ring, one elected lane issues) =====================
+    {
+      uint32_t s = 0, ph = 0;  // ring position, running across tiles (no division in the per-block loop)
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n0 = (t % n_tiles_n) * BN;
         int cw[MT], chh[MT], cd[MT], cn[MT];
@@ -670,58 +730,63 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
           cw[h] = q * p.sW - p.pW; chh[h] = pp * p.sH - p.pH; cd[h] = z * p.sD - p.pD;
         }
         int cb = 0, kx = 0, ky = 0, kz = 0;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)S;
-          const uint32_t ph = (it / (uint32_t)S) & 1u;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
-          mbar_arrive_expect_tx(bar_full + 8 * s, tile_tx);
-          tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_full + 8 * s, tile_tx);
+            tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
 #pragma unroll
-          for (int h = 0; h < MT; ++h) {
-            if (!live[h]) continue;
-            const uint32_t dst = sA + s * a_stage_bytes + h * a_half_bytes;
-            if (p.nsp == 3)
-              tma_im2col_5d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cd[h], cn[h], (uint16_t)kx,
-                            (uint16_t)ky, (uint16_t)kz);
-            else
-              tma_im2col_4d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cn[h], (uint16_t)kx,
-                            (uint16_t)ky);
+            for (int h = 0; h < MT; ++h) {
+              if (!live[h]) continue;
+              const uint32_t dst = sA + s * a_stage_bytes + h * a_half_bytes;
+              if (p.nsp == 3)
+                tma_im2col_5d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cd[h], cn[h], (uint16_t)kx,
+                              (uint16_t)ky, (uint16_t)kz);
+              else
+                tma_im2col_4d(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw[h], chh[h], cn[h], (uint16_t)kx,
+                              (uint16_t)ky);
+            }
           }
           if (++cb == p.cblocks) {
             cb = 0;
             if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++kz; } }
           }
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp walks the ring, one elected lane issues) =====================
+    {
       const uint32_t idesc = make_idesc(BN);
-      uint32_t it = 0, tile_iter = 0;
+      const uint32_t tail_k = (uint32_t)(((p.Cin & (kBlockK - 1)) + kUmmaK - 1) / kUmmaK);  // 0: every block is full
+      const uint64_t adesc0 = make_sw128_desc(sA), bdesc0 = make_sw128_desc(sB);
+      const uint32_t a_step = a_stage_bytes >> 4, b_step = b_stage_bytes >> 4, a_half_step = a_half_bytes >> 4;
+      uint32_t s = 0, ph = 0, tile_iter = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
         const uint32_t buf = tile_iter & 1u;
         const uint32_t use = tile_iter >> 1;
         mbar_wait(bar_tmem_empty + 8 * buf, (use & 1u) ^ 1u, p.error_flag, 5);  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * acc_cols;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)S;
-          const uint32_t ph = (it / (uint32_t)S) & 1u;
+        // second 128-row half of the tile: dead when it starts beyond the last output position
+        const uint32_t live1 = (MT == 2 && (t / n_tiles_n) * TILE_M + kBlockM < p.M) ? 1u : 0u;
+        uint32_t cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full + 8 * s, ph, p.error_flag, 2);
           tc_fence_after();
-          const uint64_t bdesc = make_sw128_desc(sB + s * b_stage_bytes);
-#pragma unroll
-          for (int h = 0; h < MT; ++h) {
-            if ((t / n_tiles_n) * TILE_M + h * kBlockM >= p.M) continue;  // half beyond the last output position
-            const uint64_t adesc = make_sw128_desc(sA + s * a_stage_bytes + h * a_half_bytes);
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              umma_bf16(acc + (uint32_t)(h * BN), adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          uint32_t ks = 4;
+          if (tail_k) {
+            if (++cb == (uint32_t)p.cblocks) { cb = 0; ks = tail_k; }
           }
-          umma_commit(bar_empty + 8 * s);
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + (uint64_t)(s * a_step);
+            mma_kblock(acc, acc + (uint32_t)BN, ad, ad + a_half_step, bdesc0 + (uint64_t)(s * b_step), (uint32_t)(kb != 0), ks,
+                       live1, idesc, bar_empty + 8 * s);
+          }
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
-        umma_commit(bar_tmem_full + 8 * buf);
+        if (elect_one()) umma_commit(bar_tmem_full + 8 * buf);
       }
     }
   } else {
@@ -1030,6 +1095,297 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stem rows kernel (see StemRowsParams).  Replaces, for the first layer, conv_layer.cpp:28-43 +
+// bn_layer.cu:12-124 + relu_layer.cu:10-27 and (pool = 1) pooling_layer.cu:13-61 MAX.
+//   cell row Y of a frame = OW overlapping windows of 4 cells x 16 values (one 128-byte swizzle row per
+//   output column); output row y needs cell rows y..y+3 against the weight K blocks 0..3.
+//   warp 0: TMA producer (one cell row per stage), warp 1: MMA issuer -- every resident cell row is
+//   multiplied into the (up to) four accumulators it contributes to, warps 2-9: epilogue.
+constexpr int kStemThreads = 320;
+constexpr int kStemSlots = 8;  // accumulator ring: 8 x 64 fp32 columns = all 512 TMEM columns
+
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+__device__ __forceinline__ long long mbar_wait_timed(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return 0;
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, err, code);
+  return clock64() - t0;
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const int SA = p.a_stages;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + (uint32_t)SA * 16384u;
+  const uint32_t sRow = sB + 4u * 8192u;
+  const size_t row_bytes = POOL ? 2 * 16384 : 0;
+  float* s_scale = reinterpret_cast<float*>(smem + (size_t)SA * 16384 + 4 * 8192 + row_bytes);
+  float* s_shift = s_scale + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 64);
+  const uint32_t bar_a_full = smem_u32(bars);
+  const uint32_t bar_a_empty = bar_a_full + 8 * SA;
+  const uint32_t bar_b_full = bar_a_empty + 8 * SA;
+  const uint32_t bar_acc_full = bar_b_full + 8;
+  const uint32_t bar_acc_empty = bar_acc_full + 8 * kStemSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 1 + 2 * kStemSlots);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int units = p.F * p.strips;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(bar_a_full + 8 * s, 1); mbar_init(bar_a_empty + 8 * s, 1); }
+    mbar_init(bar_b_full, 1);
+    for (int s = 0; s < kStemSlots; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 64) {
+    const int i = threadIdx.x - 64;
+    if (i < 64) {
+      const float bi = p.bias ? p.bias[i] : 0.f;
+      const float sc = p.scale ? p.scale[i] : 1.f;
+      const float sh = p.scale ? p.shift[i] : 0.f;
+      s_scale[i] = sc;
+      s_shift[i] = fmaf(bi, sc, sh);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long t_start = clock64();
+
+  // rows [r0, r1) of frame f that work unit u produces
+  auto unit_rows = [&](int u, int& f, int& r0, int& r1, int& p0) {
+    f = u / p.strips;
+    const int s = u - f * p.strips;
+    if (POOL) {
+      p0 = s * p.strip;
+      const int p1 = min(p.PH, p0 + p.strip);
+      r0 = 2 * p0;
+      r1 = min(p.OH, 2 * p1 + 1);
+    } else {
+      p0 = 0;
+      r0 = s * p.strip;
+      r1 = min(p.OH, r0 + p.strip);
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp walks the ring, one elected lane issues) =====================
+    {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_b_full, 4u * 8192u);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sB + kb * 8192u, &tmB, bar_b_full, kb * kBlockK, 0);
+      }
+      uint32_t s = 0, ph = 0;
+      long long w_prod = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int f, r0, r1, p0;
+        unit_rows(u, f, r0, r1, p0);
+        for (int Y = r0; Y < r1 + 3; ++Y) {
+          w_prod += mbar_wait_timed(bar_a_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
+          if (elect_one()) {
+            if (p.debug_flags & 8) {
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a_full + 8 * s) : "memory");
+            } else {
+              mbar_arrive_expect_tx(bar_a_full + 8 * s, p.a_tx_bytes);
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                  ::"r"(sA + s * 16384u), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_a_full + 8 * s), "r"(0), "r"(0),
+                  "r"(Y), "r"(f)
+                  : "memory");
+            }
+          }
+          if (++s == (uint32_t)SA) { s = 0; ph ^= 1u; }
+        }
+      }
+      if ((p.debug_flags & 16) && blockIdx.x == 0 && lane == 0)
+        printf("stem_rows cta0: producer waited %lld cycles of %lld\n", w_prod, clock64() - t_start);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp walks the rings, one elected lane issues) =====================
+    {
+      const uint32_t idesc = make_idesc(64);
+      mbar_wait(bar_b_full, 0, p.error_flag, 7);
+      tc_fence_after();
+      const uint64_t adesc0 = make_sw128_desc(sA), bdesc0 = make_sw128_desc(sB);
+      uint32_t s = 0, ph = 0, ir = 0;
+      long long w_full = 0, w_acc = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int f, r0, r1, p0;
+        unit_rows(u, f, r0, r1, p0);
+        for (int Y = r0; Y < r1 + 3; ++Y) {
+          w_full += mbar_wait_timed(bar_a_full + 8 * s, ph, p.error_flag, 2);
+          if (Y < r1) {  // a new output row starts with this cell row: its accumulator slot must be drained
+            const uint32_t ridx = ir + (uint32_t)(Y - r0);
+            w_acc += mbar_wait_timed(bar_acc_empty + 8 * (ridx % (uint32_t)kStemSlots),
+                                     ((ridx / (uint32_t)kStemSlots) & 1u) ^ 1u, p.error_flag, 5);
+          }
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc = adesc0 + (uint64_t)(s * (16384u >> 4));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int y = Y - i;
+              if (y < r0 || y >= r1) continue;
+              const uint32_t slot = (ir + (uint32_t)(y - r0)) % (uint32_t)kStemSlots;
+              if (!(p.debug_flags & 4)) {
+                const uint64_t bdesc = bdesc0 + (uint64_t)(i * (8192 >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tmem_base + slot * 64u, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) ? 1u : 0u);
+              }
+              if (i == 3) umma_commit(bar_acc_full + 8 * slot);
+            }
+            umma_commit(bar_a_empty + 8 * s);
+          }
+          if (++s == (uint32_t)SA) { s = 0; ph ^= 1u; }
+        }
+        ir += (uint32_t)(r1 - r0);
+      }
+      if ((p.debug_flags & 16) && blockIdx.x == 0 && lane == 0)
+        printf("stem_rows cta0: mma waited %lld (tile loads) + %lld (accumulator slots) cycles of %lld\n", w_full, w_acc,
+               clock64() - t_start);
+    }
+  } else {
+    // ===================== epilogue warps (8): lane quarter x column half =====================
+    const int wq = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int x = wq * 32 + lane;  // output column of this thread
+    const bool x_ok = x < p.OW;
+    const int te = threadIdx.x - 64;
+    const float* sc = s_scale + half * 32;
+    const float* sh = s_shift + half * 32;
+    uint32_t ir = 0, em = 0;
+    long long w_epi = 0, w_bar = 0;
+    uint32_t cm[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cm[j] = 0u;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int f, r0, r1, p0;
+      unit_rows(u, f, r0, r1, p0);
+      // pooled row `pr` of this frame from the per-thread column maxima `w` (POOL only)
+      auto emit = [&](int pr, const uint32_t (&w)[16]) {
+        const uint32_t rowbuf = sRow + (em & 1u) * 16384u;
+        ++em;
+        if (x_ok) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t chunk = (uint32_t)(half * 4 + c) ^ (uint32_t)(x & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowbuf + (uint32_t)x * 128u + (chunk << 4)),
+                         "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
+          }
+        }
+        const long long tb = clock64();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        w_bar += clock64() - tb;
+        if (p.debug_flags & 1) return;
+        __nv_bfloat16* orow = p.out + ((long long)f * p.PH + pr) * p.PW * p.out_cs + p.out_coff;
+        for (int item = te; item < p.PW * 8; item += 256) {
+          const int q = item >> 3, g = item & 7;
+          const int x0 = 2 * q;
+          uint4 m;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w)
+                       : "r"(rowbuf + (uint32_t)x0 * 128u + ((uint32_t)(g ^ (x0 & 7)) << 4)));
+#pragma unroll
+          for (int d = 1; d < 3; ++d) {
+            const int xd = x0 + d;
+            if (xd < p.OW) {
+              uint4 t;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+                           : "r"(rowbuf + (uint32_t)xd * 128u + ((uint32_t)(g ^ (xd & 7)) << 4)));
+              m.x = hmax2_u32(m.x, t.x); m.y = hmax2_u32(m.y, t.y); m.z = hmax2_u32(m.z, t.z); m.w = hmax2_u32(m.w, t.w);
+            }
+          }
+          *reinterpret_cast<uint4*>(orow + (long long)q * p.out_cs + g * 8) = m;
+        }
+      };
+      for (int y = r0; y < r1; ++y) {
+        const uint32_t ridx = ir + (uint32_t)(y - r0);
+        const uint32_t slot = ridx % (uint32_t)kStemSlots;
+        w_epi += mbar_wait_timed(bar_acc_full + 8 * slot, (ridx / (uint32_t)kStemSlots) & 1u, p.error_flag, 4);
+        tc_fence_after();
+        uint32_t v[32];
+        if (!(p.debug_flags & 2)) {
+          tmem_ld32_nowait(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 64u + (uint32_t)(half * 32), v);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0x3f800000u;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acc_empty + 8 * slot) : "memory");
+        float fv[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = reinterpret_cast<const float4*>(sc)[j], b = reinterpret_cast<const float4*>(sh)[j];
+          fv[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), a.x, b.x);
+          fv[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y);
+          fv[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z);
+          fv[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) fv[j] = fmaxf(fv[j], 0.f);
+        }
+        if (!POOL) {
+          if (x_ok && !(p.debug_flags & 1)) {
+            __nv_bfloat16* dst = p.out + (((long long)f * p.OH + y) * p.OW + x) * p.out_cs + p.out_coff + half * 32;
+            store16_bf16(dst, *reinterpret_cast<const float (*)[16]>(&fv[0]), 16);
+            store16_bf16(dst + 16, *reinterpret_cast<const float (*)[16]>(&fv[16]), 16);
+          }
+        } else {
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(fv[2 * j], fv[2 * j + 1]);
+          if (((y - r0) & 1) == 0) {
+            if (y > r0) {
+              uint32_t t[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) t[j] = hmax2_u32(cm[j], w[j]);
+              emit(p0 + ((y - r0) >> 1) - 1, t);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cm[j] = w[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cm[j] = hmax2_u32(cm[j], w[j]);
+          }
+        }
+      }
+      if (POOL && ((r1 - r0) & 1) == 0 && r1 > r0) emit(p0 + ((r1 - r0) >> 1) - 1, cm);  // clipped last window
+      ir += (uint32_t)(r1 - r0);
+    }
+    if ((p.debug_flags & 16) && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9))
+      printf("stem_rows cta0 warp %d: epilogue waited %lld (accumulators) + %lld (row barrier) cycles of %lld\n", warp, w_epi,
+             w_bar, clock64() - t_start);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace
 
 cudaError_t conv_umma_configure() {
@@ -1041,7 +1397,20 @@ cudaError_t conv_umma_configure() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(stem_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(stem_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_stem_rows(const StemRowsParams& p, const CUtensorMap& tmX, const CUtensorMap& tmB, cudaStream_t stream) {
+  const int units = p.F * p.strips;
+  const int grid = units < p.num_sms ? units : p.num_sms;
+  const size_t smem = stem_rows_smem_bytes(p);
+  if (p.pool) stem_rows_kernel<true><<<grid, kStemThreads, smem, stream>>>(p, tmX, tmB);
+  else stem_rows_kernel<false><<<grid, kStemThreads, smem, stream>>>(p, tmX, tmB);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_conv_halo(const HaloKernelParams& p, int m_halves, const CUtensorMap& tmX, const CUtensorMap& tmB,

@@ -92,6 +92,32 @@ inline size_t halo_smem_bytes(const HaloKernelParams& p) {
 cudaError_t launch_conv_halo(const HaloKernelParams& p, int m_halves, const CUtensorMap& tmX, const CUtensorMap& tmB,
                              cudaStream_t stream);
 
+
+// ---- stem rows kernel: the 7x7/s2/p3 stem (Cin 3 -> 64) as a sliding window over rows of
+// space-to-depth cells.  One 14 KB tile (a cell row: OW windows x 64 values) is loaded ONCE and feeds
+// the four vertical filter taps of four different output rows, each with its own TMEM accumulator
+// (ring of 8 x 64 columns); optionally the 3x3/s2 max pooling that follows (pool1) is applied to the
+// rectified rows on chip, so the 64-channel full-resolution map never touches HBM. ----
+struct StemRowsParams {
+  int F;                     // frames
+  int OH, OW;                // conv output grid (OW <= 128)
+  int pool;                  // 1: emit MAX 3x3 / stride 2 / pad 0 (caffe ceil mode) of the conv output instead
+  int PH, PW;                // pooled grid
+  int strip, strips;         // output rows (pooled rows if pool) per work unit; units per frame
+  int a_stages;
+  uint32_t a_tx_bytes;       // OW * 128
+  int num_sms;
+  int debug_flags;           // development: 1 no stores, 2 no TMEM loads, 4 no MMAs, 8 no TMA loads, 16 print role wait cycles (CTA 0)
+  const float* bias; const float* scale; const float* shift;
+  int relu;
+  __nv_bfloat16* out; long long out_cs; int out_coff;   // [F, OH, OW, 64] or pooled [F, PH, PW, 64]
+  int* error_flag;
+};
+inline size_t stem_rows_smem_bytes(const StemRowsParams& p) {
+  return 1024 + (size_t)p.a_stages * 16384 + 4 * 8192 + (p.pool ? 2 * 16384 : 0) + 2 * 64 * sizeof(float) + 512;
+}
+cudaError_t launch_stem_rows(const StemRowsParams& p, const CUtensorMap& tmX, const CUtensorMap& tmB, cudaStream_t stream);
+
 // dynamic shared memory needed for (block_n, stages)
 inline size_t conv_epi_stage_bytes(int epi_group) { return epi_group ? (size_t)8 * 32 * ((size_t)epi_group * 32 + 16) : 0; }
 inline size_t conv_smem_bytes(int block_n, int stages, int m_halves = 1, size_t epi_stage = 0) {

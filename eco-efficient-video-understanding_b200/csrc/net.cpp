@@ -528,6 +528,7 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "persistent") persistent_ = v;  // 0 never, 1 auto (per layer), 2 always
   else if (key == "epi_staged") epi_staged_ = v != 0;
   else if (key == "halo") halo_ = v;
+  else if (key == "stem_rows") stem_rows_ = v;
   else if (key == "debug_flags") debug_flags_ = v;
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
   else ECO_CHECK(false, "unknown option '" << key << "'");
@@ -814,6 +815,52 @@ bool Net::plan_halo(ConvOp& c) {
   return true;
 }
 
+// Set up the stem rows kernel (conv_umma.cu: stem_rows_kernel) for a convolution plan_conv_group marked `rows`.
+void Net::plan_stem_rows(ConvOp& c) {
+  static EncodeTiledFn enc_tiled = (EncodeTiledFn)driver_fn("cuTensorMapEncodeTiled");
+  ECO_CHECK(c.stem && c.Cout == 64 && c.kp.block_n == 64 && c.O[2] <= 128, "stem rows kernel: unexpected geometry");
+  StemRowsParams& r = c.rp;
+  r = StemRowsParams{};
+  r.F = c.NB; r.OH = c.O[1]; r.OW = c.O[2];
+  r.pool = c.pool_tensor >= 0 ? 1 : 0;
+  const Tensor& y = tensors_[r.pool ? c.pool_tensor : c.out_tensor];
+  ECO_CHECK(y.dev && y.kind == Kind::CL && y.cs % 8 == 0 && y.coff % 8 == 0, "stem rows kernel: output " << y.name);
+  r.PH = r.pool ? y.shape[2] : 0;
+  r.PW = r.pool ? y.shape[3] : 0;
+  if (r.pool) ECO_CHECK(2 * (r.PH - 1) < r.OH && 2 * (r.PW - 1) < r.OW && 2 * r.PH + 1 >= r.OH && 2 * r.PW + 1 >= r.OW, "pool grid");
+  // work units: strips of rows per frame, balanced over the SMs (each unit re-reads a 3-row halo)
+  const int rows_out = r.pool ? r.PH : r.OH;
+  long long best = -1;
+  for (int s = 1; s <= 16 && s <= rows_out; ++s) {
+    const int strip = (rows_out + s - 1) / s;
+    const int strips = (rows_out + strip - 1) / strip;
+    const long long cell_rows = (r.pool ? 2 * strip + 1 : strip) + 3;
+    const long long cost = (((long long)r.F * strips + g_num_sms - 1) / g_num_sms) * cell_rows;
+    if (best < 0 || cost < best) { best = cost; r.strip = strip; r.strips = strips; }
+  }
+  r.a_stages = r.pool ? 6 : 8;
+  r.a_tx_bytes = (uint32_t)r.OW * 128u;
+  r.num_sms = g_num_sms;
+  r.debug_flags = debug_flags_;
+  r.bias = c.kp.bias; r.scale = c.kp.scale; r.shift = c.kp.shift; r.relu = c.kp.relu;
+  r.out = static_cast<__nv_bfloat16*>(y.dev); r.out_cs = y.cs; r.out_coff = y.coff;
+  r.error_flag = c.kp.error_flag;
+  // cell rows as [64-value window, OW windows (32 bytes apart), CH rows, F frames]
+  cuuint64_t dims[4] = {64, (cuuint64_t)r.OW, (cuuint64_t)c.stem_CH, (cuuint64_t)c.NB};
+  cuuint64_t strides[3] = {32, (cuuint64_t)c.stem_CW * 32, (cuuint64_t)c.stem_CH * c.stem_CW * 32};
+  cuuint32_t box[4] = {64, (cuuint32_t)r.OW, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult e = enc_tiled(&c.tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, c.stem_in, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ECO_CHECK(e == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stem cell rows) failed with " << (int)e
+                                   << "; set option stem_rows=0 to use the im2col kernel");
+  if (r.pool) {
+    const double px = (double)c.NB * r.PH * r.PW * 64;
+    c.bytes = 2.0 * ((double)c.NB * c.I[1] * c.I[2] * 3 + px + 64.0 * 147);
+  }
+}
+
 // =====================================================================================
 // planner
 static bool is_inplace_relu(const OrigLayer& L, int tensor) {
@@ -821,6 +868,19 @@ static bool is_inplace_relu(const OrigLayer& L, int tensor) {
   if (L.bottoms[0] != tensor || L.tops[0] != tensor) return false;
   const pt::Msg* p = L.msg ? L.msg->msg("relu_param") : nullptr;
   return !p || p->num("negative_slope", 0.0) == 0.0;
+}
+
+// 7x7 / stride 2 / pad 3 over a 3-channel fp32 net input (ECO's conv1/7x7_s2)
+bool Net::is_stem_conv(const OrigLayer& L) const {
+  if (L.type != "Convolution" || L.bottoms.empty()) return false;
+  const Tensor& x = tensors_[L.bottoms[0]];
+  if (x.kind != Kind::F32 || x.shape.size() != 4 || x.shape[1] != 3) return false;
+  const pt::Msg* p = L.msg->msg("convolution_param");
+  if (!p) return false;
+  auto k = nd_param(*p, "kernel_size", "kernel", 2, -1);
+  auto s = nd_param(*p, "stride", "stride", 2, 1);
+  auto pd = nd_param(*p, "pad", "pad", 2, 0);
+  return k[0] == 7 && k[1] == 7 && s[0] == 2 && s[1] == 2 && pd[0] == 3 && pd[1] == 3;
 }
 
 void Net::plan_conv_group(int li, std::vector<bool>& done) {
@@ -892,6 +952,39 @@ void Net::plan_conv_group(int li, std::vector<bool>& done) {
     }
   }
   done[li] = true;
+  // the 7x7/s2 stem: rows kernel when only the rectified output is wanted; the MAX 3x3/s2 pooling that
+  // is its sole reader (pool1) is folded into the same kernel unless every blob must be kept
+  if (stem_rows_ != 0 && is_stem_conv(L) && L.params[0].shape[0] == 64 && tensors_[T0].shape[3] <= 128 &&
+      c.out_tensor >= 0 && c.raw_tensor < 0 && c.res_tensor < 0) {
+    c.rows = true;
+    if (stem_rows_ == 1 && !keep_all_) {
+      int readers = 0, pool = -1;
+      for (int ci : tensors_[c.out_tensor].consumers) {
+        if (done[ci]) continue;  // the fused BN / in-place ReLU
+        ++readers;
+        pool = ci;
+      }
+      if (readers == 1 && layers_[pool].type == "Pooling" && tensors_[layers_[pool].tops[0]].kind == Kind::CL) {
+        const OrigLayer& PL = layers_[pool];
+        const pt::Msg* pp = PL.msg->msg("pooling_param");
+        bool ok = pp && !pp->boolean("global_pooling", false) && pp->str("pool", "MAX") == "MAX" && PL.tops.size() == 1;
+        if (ok) {
+          auto k = nd_param(*pp, "kernel_size", "kernel", 2, -1);
+          auto st = nd_param(*pp, "stride", "stride", 2, 1);
+          auto pd = nd_param(*pp, "pad", "pad", 2, 0);
+          ok = k[0] == 3 && k[1] == 3 && st[0] == 2 && st[1] == 2 && pd[0] == 0 && pd[1] == 0;
+        }
+        if (ok) {
+          c.pool_layer = pool;
+          c.pool_tensor = PL.tops[0];
+          c.out_tensor = -1;  // stays on chip
+          done[pool] = true;
+          last = std::max(last, pool);
+          tensors_[c.pool_tensor].materialized = true;
+        }
+      }
+    }
+  }
   if (c.out_tensor >= 0) tensors_[c.out_tensor].materialized = true;
   if (c.raw_tensor >= 0) tensors_[c.raw_tensor].materialized = true;
 
@@ -1377,9 +1470,8 @@ void Net::plan() {
         {
           const size_t per_stage = (size_t)kBlockM * 128 + (size_t)kp.block_n * 128;
           kp.persistent = (persistent_ && kp.a_mode == A_TMA_IM2COL) ? 1 : 0;
-          // measured A/B (tools/ab_bench.py, B=32): long-K layers with >= 128-wide tiles (the 3-D head) run
-          // 5-15% faster as one-tile CTAs, two per SM, than as a single persistent CTA per SM
-          if (persistent_ == 1 && kp.persistent && kp.num_kb >= 48 && kp.block_n >= 128) kp.persistent = 0;
+          // (until the MMA issue path was fixed -- elect.sync instead of lane 0, profiles/r01j -- long-K layers ran
+          // faster as one-tile CTAs, two per SM; since then the persistent kernel wins on every layer, ab21)
           kp.m_halves = 1;
           if (kp.persistent) {
             // one CTA per SM: deep ring, double-buffered accumulator (2 x m_halves x block_n TMEM columns).
@@ -1406,6 +1498,7 @@ void Net::plan() {
         const double taps = (double)c.K[0] * c.K[1] * c.K[2];
         c.flops = 2.0 * kp.M * c.Cout * taps * c.Cin;
         c.bytes = 2.0 * ((double)c.NB * c.I[0] * c.I[1] * c.I[2] * c.Cin + (double)kp.M * c.Cout + (double)c.Cout * taps * c.Cin);
+        if (c.rows) plan_stem_rows(c);
         op.flops = c.flops;
         op.bytes = c.bytes;
         op.launches = 1 + (c.stem_in ? 1 : 0);
@@ -1733,8 +1826,10 @@ void Net::run_op(Op& op, bool with_xform) {
     case Op::CONV: {
       ConvOp& c = convs_[op.conv];
       if (c.stem_in && with_xform) run_input_xform(c, nullptr);
-      if (c.halo) CUDA_OK(launch_conv_halo(c.hp, c.halo_mt, c.tmX, c.tmB, stream_));
+      if (c.rows) CUDA_OK(launch_stem_rows(c.rp, c.tmX, c.tmB, stream_));
+      else if (c.halo) CUDA_OK(launch_conv_halo(c.hp, c.halo_mt, c.tmX, c.tmB, stream_));
       else CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.tmB, stream_));
+      if (c.pool_tensor >= 0) mark_written(c.pool_tensor);
       if (c.out_tensor >= 0) mark_written(c.out_tensor);
       if (c.raw_tensor >= 0) mark_written(c.raw_tensor);
       break;

@@ -131,6 +131,10 @@ struct ConvOp {
   int halo_mt = 1;
   HaloKernelParams hp{};
   CUtensorMap tmX{};
+  bool rows = false;          // stem rows kernel (sliding window over cell rows, optional fused pool1)
+  int pool_layer = -1;        // Pooling layer folded into the rows kernel
+  int pool_tensor = -1;       // its top (the only tensor the fused op stores)
+  StemRowsParams rp{};
   double flops = 0, bytes = 0;
 };
 
@@ -204,6 +208,7 @@ class Net {
   int persistent_ = 1;
   int dual_m_ = 1;
   int halo_ = 0;  // 0 off (default: measured slower, profiles/r01h), 1 auto (resident weights only), 2 force two halves, 3 allow streamed weights
+  int stem_rows_ = 1;  // 0: stem as 4x1 im2col GEMM; 1: rows kernel, pool1 folded in when its input has no other reader; 2: rows kernel, never fold the pool
   int debug_flags_ = 0;
   bool epi_staged_ = false;
   bool user_stream_ = false;
@@ -248,6 +253,8 @@ class Net {
   void plan_conv_group(int li, std::vector<bool>& done);
   void make_tensor_maps(ConvOp& c);
   bool plan_halo(ConvOp& c);
+  void plan_stem_rows(ConvOp& c);
+  bool is_stem_conv(const OrigLayer& L) const;
   void download(Tensor& t);
   void upload(Tensor& t);
   ClView view(const Tensor& t) const;

@@ -75,6 +75,10 @@ def test_eco_lite_n4_fast_plan_matches(gpu, graph):
         assert rel_max(got, want) <= TOL_LOGITS, describe_mismatch(got, want, "fc8")
     with pytest.raises(RuntimeError):
         net.blobs["conv1_7x7_s2"].data  # fused away in the fast plan: loud, not stale
+    with pytest.raises(RuntimeError):
+        net.blobs["conv1_7x7_s2_bn"].data  # the stem rows kernel pools on chip: only pool1 is stored
+    full = ref.forward(x, bf16=True)
+    check_bf16_blob(net.blobs["pool1_3x3_s2"].data.copy(), full["pool1_3x3_s2"], "pool1_3x3_s2")
 
 
 def test_eco_full_n4(gpu):

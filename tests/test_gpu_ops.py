@@ -48,12 +48,14 @@ def two_conv_net(shape, cmid, cout, k, s, p):
 PLAIN = {"gp", "gp_r", "fc"}  # blobs that are plain fp32 on the device
 
 
-def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True, persistent=True, dual_m=1, halo=1):
+def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True, persistent=True, dual_m=1, halo=1,
+             stem_rows=None):
     ref = refnet.RefNet(txt).init_params(seed + 1)
     rng = np.random.default_rng(seed)
     x = rng.normal(size=shape).astype(np.float32)
     want = ref.forward(x, bf16=True)
-    net = make_net(txt, keep_all=keep_all, a_mode=a_mode, persistent=persistent, dual_m=dual_m, halo=halo)
+    net = make_net(txt, keep_all=keep_all, a_mode=a_mode, persistent=persistent, dual_m=dual_m, halo=halo,
+                   stem_rows=stem_rows)
     load_params(net, ref.params_dict())
     net.blobs["data"].data[...] = x
     net.forward()
@@ -163,6 +165,35 @@ def test_stem_7x7_s2(gpu, hw, mode):
     shape = (2, 3) + hw
     run_case(conv_net(shape, 64, [7, 7], [2, 2], [3, 3]), shape, 0 if mode == "gather" else 1, check=("c", "c_bn"),
              halo={"gather": 0, "im2col": 0, "halo": 1, "halo_mt2": 2}[mode])
+
+
+STEM_POOL = 'layer { name: "p1" type: "Pooling" bottom: "c_bn" top: "p1" pooling_param { pool: MAX kernel_size: 3 stride: 2 } }\n'
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 32, 32), (2, 3, 30, 34), (3, 3, 224, 224), (160, 3, 32, 32), (1, 3, 256, 250)],
+                         ids=["32x32", "30x34", "224", "160frames", "256x250"])
+@pytest.mark.parametrize("pool", [False, True], ids=["rows", "rows_pool"])
+def test_stem_rows_kernel(gpu, shape, pool):
+    # the production stem: sliding window over cell rows with a ring of TMEM accumulators; with `pool` the MAX
+    # 3x3/s2 pooling behind it (pool1) is applied on chip and the full-resolution map is never stored.
+    # 160 frames: more work units than SMs (several units per CTA, both rings wrap); odd / even output heights
+    # cover the clipped last pooling window of caffe's ceil mode.
+    txt = conv_net(shape, 64, [7, 7], [2, 2], [3, 3]) + (STEM_POOL if pool else "")
+    net, _ = run_case(txt, shape, 1, check=("p1",) if pool else ("c_bn",), keep_all=False, stem_rows=1)
+    with pytest.raises(RuntimeError):
+        net.blobs["c"].data  # never materialised by this kernel
+    if pool:
+        with pytest.raises(RuntimeError):
+            net.blobs["c_bn"].data
+
+
+def test_stem_rows_pool_not_folded_when_blob_has_other_readers(gpu):
+    # c_bn feeds the pooling AND a 1x1 conv: the pool must stay a separate op (c_bn is stored)
+    shape = (2, 3, 32, 32)
+    txt = conv_net(shape, 64, [7, 7], [2, 2], [3, 3]) + STEM_POOL
+    txt += ('layer { name: "d" type: "Convolution" bottom: "c_bn" top: "d" convolution_param { num_output: 32 '
+            'kernel_size: 1 } }\n')
+    run_case(txt, shape, 1, check=("c_bn", "p1", "d"), keep_all=False, stem_rows=1)
 
 
 @pytest.mark.parametrize("a_mode", [0, 1], ids=["gather", "im2col"])

@@ -46,14 +46,24 @@ for cfg in a.cfgs:
         names = [o["name"] for o in prof]
         kinds = [o["kind"] for o in prof]
         flops = [o["flops"] for o in prof]
-    results[label] = acc
+    results[label] = {"ms": acc, "names": names, "kinds": kinds, "flops": flops}
     del net
 labels = list(results)
+order = []
+for l in labels:  # union of op names, first appearance order (plans may fuse different ops)
+    for n in results[l]["names"]:
+        if n not in order:
+            order.append(n)
 print("%-34s" % "op" + "".join("%12s" % l for l in labels))
-for i, n in enumerate(names):
-    print("%-34s" % n[:34] + "".join("%12.1f" % (results[l][i] * 1e3) for l in labels))
-print("%-34s" % "TOTAL us" + "".join("%12.1f" % (results[l].sum() * 1e3) for l in labels))
-conv = [i for i, k in enumerate(kinds) if k == 0]
-tf = sum(flops[i] for i in conv)
-print("%-34s" % "conv TFLOP/s" + "".join("%12.1f" % (tf / results[l][conv].sum() / 1e9) for l in labels))
-print("%-34s" % "videos/s (sum of ops)" + "".join("%12.1f" % (B / results[l].sum() * 1e3) for l in labels))
+for n in order:
+    row = ""
+    for l in labels:
+        r = results[l]
+        row += "%12.1f" % (r["ms"][r["names"].index(n)] * 1e3) if n in r["names"] else "%12s" % "-"
+    print("%-34s" % n[:34] + row)
+print("%-34s" % "TOTAL us" + "".join("%12.1f" % (results[l]["ms"].sum() * 1e3) for l in labels))
+def conv_tf(r):
+    conv = [i for i, k in enumerate(r["kinds"]) if k == 0]
+    return sum(r["flops"][i] for i in conv) / r["ms"][conv].sum() / 1e9
+print("%-34s" % "conv TFLOP/s" + "".join("%12.1f" % conv_tf(results[l]) for l in labels))
+print("%-34s" % "videos/s (sum of ops)" + "".join("%12.1f" % (B / results[l]["ms"].sum() * 1e3) for l in labels))
