@@ -351,6 +351,14 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
         }
       } else {
         const int hcount = min(iy0 + 3, p.IH + p.pH) - iy0;  // pad-inclusive window rows (AVE divisor)
+        const bool affine = p.bias != nullptr || p.scale != nullptr;
+        float e_b[8], e_s[8], e_h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          e_b[j] = p.bias ? __ldg(p.bias + g * 8 + j) : 0.f;
+          e_s[j] = p.scale ? __ldg(p.scale + g * 8 + j) : 1.f;
+          e_h[j] = p.scale ? __ldg(p.shift + g * 8 + j) : 0.f;
+        }
         float c0[8], c1[8], c2[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) c0[j] = c1[j] = c2[j] = 0.f;
@@ -381,6 +389,14 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
               float o[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) o[j] = ((c0[j] + c1[j]) + c2[j]) * inv;
+              if (affine) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j] + e_b[j], e_s[j], e_h[j]);
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+              }
               *reinterpret_cast<uint4*>(p.y + (opix0 + ox) * p.y_cs + p.y_coff + g * 8) = pack8(o);
             }
           }
@@ -577,6 +593,7 @@ cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {
   const long long n = (long long)p.NB * p.OD * p.OH * p.OW * (p.C / 8);
   if (n == 0) return cudaSuccess;
   if (n >= (1LL << 31)) return cudaErrorInvalidValue;  // 32-bit index math in the kernel
+  const bool epilogue = p.bias || p.scale || p.relu;
   if (p.ID == 1 && p.KD == 1 && p.OD == 1 && p.x_cs == p.C && p.x_coff == 0) {
     // rows staged through shared memory by bulk copies
     const size_t row_bytes = (size_t)p.IW * p.C * 2;
@@ -590,11 +607,13 @@ cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {
         cudaFuncSetAttribute(pool2d_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         configured = true;
       }
+      if (epilogue && (p.is_max || p.KH != 3 || p.KW != 3 || p.sH != p.sW || p.sW > 2)) return cudaErrorNotSupported;
       dim3 grid((p.OH + rows_out - 1) / rows_out, p.NB, 1);
       pool2d_rows_kernel<<<grid, 256, smem, st>>>(p, rows_out);
       return cudaGetLastError();
     }
   }
+  if (epilogue) return cudaErrorNotSupported;  // only the row-staged AVE 3x3 path applies it
   if (p.ID == 1 && p.KD == 1 && p.KH == 3 && p.KW == 3 && p.sH == p.sW && (p.sH == 1 || p.sH == 2) && p.pH == p.pW &&
       p.pH <= 1) {
     constexpr int T = 4;

@@ -39,6 +39,9 @@ struct PoolParams {
   int ID, IH, IW, OD, OH, OW;
   int KD, KH, KW, sD, sH, sW, pD, pH, pW;
   int is_max;
+  // optional per-channel epilogue y = relu?((pool + bias) * scale + shift), AVE 3x3 on the row-staged kernel only:
+  // used when a 1x1 convolution behind an AVE pooling was moved in front of it (both are linear)
+  const float* bias; const float* scale; const float* shift; int relu;
 };
 // caffe pooling on channels-last bf16 (pooling_layer.cpp:199-262 semantics), C % 8 == 0
 cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st);

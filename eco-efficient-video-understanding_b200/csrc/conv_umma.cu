@@ -633,6 +633,17 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32
       f[4 * j + 3] = fmaf(f[4 * j + 3], a.w, b.w);
     }
   }
+  if (p.nseg > 1) {
+    // segmented output (fused sibling 1x1 convolutions): this 16-channel chunk lies inside one segment
+    int sg = 0;
+    while (sg < p.nseg - 1 && cg >= p.seg_end[sg]) ++sg;
+    if (p.seg_relu[sg]) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (row_ok && nvalid > 0) store16_bf16(p.seg_ptr[sg] + (long long)m * p.seg_cs[sg] + p.seg_coff[sg] + cg, f, nvalid);
+    return;
+  }
   if (p.relu) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -1192,7 +1203,8 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
     {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_b_full, 4u * 8192u);
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sB + kb * 8192u, &tmB, bar_b_full, kb * kBlockK, 0);
+        // weight K block i = vertical tap i; stacked in shared memory as tap 3, 2, 1, 0 (see the MMA issuer)
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sB + (3 - kb) * 8192u, &tmB, bar_b_full, kb * kBlockK, 0);
       }
       uint32_t s = 0, ph = 0;
       long long w_prod = 0;
@@ -1240,20 +1252,36 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
           }
           tc_fence_after();
           if (elect_one()) {
+            // taps ilo..ihi of this cell row land in output rows Y-ilo .. Y-ihi of the unit
             const uint64_t adesc = adesc0 + (uint64_t)(s * (16384u >> 4));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int y = Y - i;
-              if (y < r0 || y >= r1) continue;
-              const uint32_t slot = (ir + (uint32_t)(y - r0)) % (uint32_t)kStemSlots;
-              if (!(p.debug_flags & 4)) {
-                const uint64_t bdesc = bdesc0 + (uint64_t)(i * (8192 >> 4));
+            const int ilo = max(0, Y - r1 + 1), ihi = min(3, Y - r0);
+            if (!(p.debug_flags & 4)) {
+              if (ilo == 0) {
+                // newest row: first contribution, overwrites its accumulator (N = 64)
+                const uint32_t slot = (ir + (uint32_t)(Y - r0)) % (uint32_t)kStemSlots;
+                const uint64_t bdesc = bdesc0 + (uint64_t)(3 * (8192 >> 4));
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(tmem_base + slot * 64u, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) ? 1u : 0u);
+                  umma_bf16(tmem_base + slot * 64u, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
               }
-              if (i == 3) umma_commit(bar_acc_full + 8 * slot);
+              // taps >= 1: consecutive older rows = adjacent accumulator slots = ONE N = 64 x count MMA per K step
+              // against the weight tiles stacked tap 3, 2, 1 (split only where the slot ring wraps)
+              int tap = ihi;
+              int cnt = ihi - max(1, ilo) + 1;
+              while (cnt > 0) {
+                const uint32_t slot = (ir + (uint32_t)(Y - tap - r0)) % (uint32_t)kStemSlots;
+                const int c1 = min(cnt, kStemSlots - (int)slot);
+                const uint64_t bdesc = bdesc0 + (uint64_t)((3 - tap) * (8192 >> 4));
+                const uint32_t idesc_n = make_idesc(64 * c1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tmem_base + slot * 64u, adesc + 2 * k, bdesc + 2 * k, idesc_n, 1u);
+                tap -= c1;
+                cnt -= c1;
+              }
             }
+            if (ihi == 3 && ilo <= 3)  // row Y-3 just received its last tap
+              umma_commit(bar_acc_full + 8 * ((ir + (uint32_t)(Y - 3 - r0)) % (uint32_t)kStemSlots));
             umma_commit(bar_a_empty + 8 * s);
           }
           if (++s == (uint32_t)SA) { s = 0; ph ^= 1u; }

@@ -59,6 +59,16 @@ struct ConvKernelParams {
   __nv_bfloat16* raw;   long long raw_cs;  int raw_coff;   // raw (null -> not stored)
   const __nv_bfloat16* res; long long res_cs; int res_coff;  // residual added into raw (null -> none)
   int* error_flag;                   // set non-zero if an mbarrier wait times out
+  // ---- output segments (persistent kernel, out-only epilogue): sibling 1x1 convolutions that read the same
+  // tensor run as ONE GEMM whose N range is the concatenation of their output channels; segment g covers
+  // channels [seg_end[g-1], seg_end[g]) and goes to its own tensor (seg_coff already has the segment start
+  // subtracted) with its own ReLU flag.  nseg <= 1: `out` / `relu` above. ----
+  int nseg;
+  int seg_end[4];
+  __nv_bfloat16* seg_ptr[4];
+  long long seg_cs[4];
+  int seg_coff[4];
+  int seg_relu[4];
 };
 
 // ---- halo-resident 2-D convolution (stride 1): the input patch of a tile is loaded ONCE and every

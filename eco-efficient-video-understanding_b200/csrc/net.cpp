@@ -529,6 +529,8 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "epi_staged") epi_staged_ = v != 0;
   else if (key == "halo") halo_ = v;
   else if (key == "stem_rows") stem_rows_ = v;
+  else if (key == "pool_commute") pool_commute_ = v;
+  else if (key == "fuse_1x1") fuse_1x1_ = v;
   else if (key == "debug_flags") debug_flags_ = v;
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
   else ECO_CHECK(false, "unknown option '" << key << "'");
@@ -883,11 +885,157 @@ bool Net::is_stem_conv(const OrigLayer& L) const {
   return k[0] == 7 && k[1] == 7 && s[0] == 2 && s[1] == 2 && pd[0] == 3 && pd[1] == 3;
 }
 
-void Net::plan_conv_group(int li, std::vector<bool>& done) {
+// AVE pooling (3x3, stride 1, pad 1: every window divides by 9, padding counts as zeros) followed by a 1x1
+// convolution whose only input it is: both are linear, so conv1x1(pool(x)) == pool(conv1x1_nobias(x)) + bias exactly,
+// and the pooling then runs on Cout (32..128) channels instead of Cin (192..608).  Emits CONV (accumulator stored
+// as bf16 into an internal tensor) + POOL_CL (bias, BN, ReLU in its epilogue).  Only in the fast plan: the pooled
+// blob itself is never formed.  Rounding differs from the reference order by one bf16 rounding of the
+// intermediate, like every fused op; the logits tolerance of the whole-net tests covers it.
+bool Net::try_commute_pool_conv(int li, std::vector<bool>& done, std::vector<int>& view_of) {
+  if (keep_all_ || !pool_commute_) return false;
+  const OrigLayer& L = layers_[li];
+  const pt::Msg* pp = L.msg->msg("pooling_param");
+  if (!pp || pp->boolean("global_pooling", false) || pp->str("pool", "MAX") != "AVE") return false;
+  if (L.bottoms.size() != 1 || L.tops.size() != 1) return false;
+  const int xb = L.bottoms[0], top = L.tops[0];
+  if (tensors_[xb].kind != Kind::CL || tensors_[xb].shape.size() != 4 || tensors_[top].kind != Kind::CL) return false;
+  if (tensors_[xb].shape[0] > 65535) return false;
+  {
+    auto k = nd_param(*pp, "kernel_size", "kernel", 2, -1);
+    auto st = nd_param(*pp, "stride", "stride", 2, 1);
+    auto pd = nd_param(*pp, "pad", "pad", 2, 0);
+    if (k[0] != 3 || k[1] != 3 || st[0] != 1 || st[1] != 1 || pd[0] != 1 || pd[1] != 1) return false;
+  }
+  if (tensors_[top].consumers.size() != 1) return false;
+  const int cj = tensors_[top].consumers[0];
+  const OrigLayer& C = layers_[cj];
+  if (C.type != "Convolution" || done[cj] || C.bottoms.size() != 1 || C.bottoms[0] != top || C.tops.size() != 1) return false;
+  const pt::Msg* cp = C.msg->msg("convolution_param");
+  if (!cp || cp->integer("group", 1) != 1) return false;
+  {
+    auto k = nd_param(*cp, "kernel_size", "kernel", 2, -1);
+    auto st = nd_param(*cp, "stride", "stride", 2, 1);
+    auto pd = nd_param(*cp, "pad", "pad", 2, 0);
+    if (k[0] != 1 || k[1] != 1 || st[0] != 1 || st[1] != 1 || pd[0] != 0 || pd[1] != 0) return false;
+  }
+  // the conv group must reduce to "one stored output" (conv -> BN [-> in-place ReLU])
+  const int T0 = C.tops[0];
+  if (tensors_[T0].consumers.size() != 1) return false;
+  {
+    const OrigLayer& B = layers_[tensors_[T0].consumers[0]];
+    if (B.type != "BN" || B.tops[0] == T0 || done[tensors_[T0].consumers[0]]) return false;
+    const pt::Msg* bp = B.msg->msg("bn_param");
+    if (!(phase_ == ECO_PHASE_TEST || (bp && bp->boolean("frozen", false)))) return false;
+  }
+  const int T = add_tensor(C.name + "@prepool");
+  while ((int)view_of.size() <= T) view_of.push_back(-1);
+  tensors_[T].shape = tensors_[T0].shape;
+  tensors_[T].kind = Kind::CL;
+  tensors_[T].ch_axis = 1;
+  tensors_[T].producer = cj;
+  tensors_[T].consumers.assign(1, li);
+  tensors_[T].materialized = true;
+  plan_conv_group(cj, done, xb);
+  ConvOp& c = convs_.back();
+  Op& cop = ops_.back();
+  ECO_CHECK(c.out_tensor >= 0 && c.raw_tensor < 0 && c.res_tensor < 0 && !c.rows, "pool_commute: unexpected conv group for " << C.name);
+  const int final_t = c.out_tensor;
+  c.post_pool = true;
+  c.post_relu = c.relu;
+  c.relu = false;
+  c.raw_tensor = T;
+  c.out_tensor = -1;
+  cop.first_layer = std::min(cop.first_layer, li);
+  Op pop;
+  pop.type = Op::POOL_CL;
+  pop.name = L.name;
+  pop.layer = li;
+  pop.first_layer = li;
+  pop.last_layer = cop.last_layer;
+  pop.in0 = T;
+  pop.out = final_t;
+  pop.affine_conv = cop.conv;
+  ops_.push_back(pop);
+  done[li] = true;
+  return true;
+}
+
+// 1x1 / stride 1 convolutions that read the same channels-last tensor (an inception module's 1x1, 3x3_reduce,
+// double_3x3_reduce and -- after pool_commute -- pool_proj) become ONE GEMM over the concatenated output
+// channels: the input is read from HBM once instead of once per branch.  Each member keeps its own folded
+// BN / ReLU (per-channel constants, per-segment ReLU flag) and its own destination (concat slice or tensor).
+// Per-channel results are bit-identical to the unfused plan (same K order per output channel).
+void Net::fuse_sibling_1x1() {
+  if (!fuse_1x1_ || keep_all_ || persistent_ == 0 || a_mode_ == A_GATHER) return;
+  auto member_cout = [&](const Op& op) { return layers_[convs_[op.conv].conv_layer].params[0].shape[0]; };
+  auto eligible = [&](const Op& op) -> bool {
+    if (op.type != Op::CONV) return false;
+    const ConvOp& c = convs_[op.conv];
+    if (!c.members.empty() || c.rows || c.res_tensor >= 0 || c.elt_layer >= 0) return false;
+    if ((c.out_tensor >= 0) == (c.raw_tensor >= 0)) return false;  // exactly one stored tensor
+    const OrigLayer& L = layers_[c.conv_layer];
+    const Tensor& x = tensors_[c.in_tensor];
+    if (x.kind != Kind::CL || x.shape.size() != 4) return false;
+    const pt::Msg* cp = L.msg->msg("convolution_param");
+    if (!cp || cp->integer("group", 1) != 1) return false;
+    auto k = nd_param(*cp, "kernel_size", "kernel", 2, -1);
+    auto st = nd_param(*cp, "stride", "stride", 2, 1);
+    auto pd = nd_param(*cp, "pad", "pad", 2, 0);
+    if (k[0] != 1 || k[1] != 1 || st[0] != 1 || st[1] != 1 || pd[0] != 0 || pd[1] != 0) return false;
+    return L.params[0].shape[0] % 16 == 0;
+  };
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    if (!eligible(ops_[i])) continue;
+    std::vector<size_t> grp(1, i);
+    int total = member_cout(ops_[i]);
+    for (size_t j = i + 1; j < ops_.size() && grp.size() < 4; ++j) {
+      if (!eligible(ops_[j]) || convs_[ops_[j].conv].in_tensor != convs_[ops_[i].conv].in_tensor) continue;
+      if (total + member_cout(ops_[j]) > 256) continue;
+      grp.push_back(j);
+      total += member_cout(ops_[j]);
+    }
+    if (grp.size() < 2) continue;
+    ConvOp g = convs_[ops_[grp[0]].conv];  // geometry / input of the first member
+    g.out_tensor = g.raw_tensor = -1;
+    g.bn_layer = -1;
+    g.relu = false;
+    g.post_pool = false;
+    Op gop = ops_[grp[0]];
+    gop.name.clear();
+    int off = 0;
+    const int gidx = (int)convs_.size();
+    for (size_t q : grp) {
+      const ConvOp& c = convs_[ops_[q].conv];
+      ConvMember m;
+      m.conv_layer = c.conv_layer;
+      m.bn_layer = c.bn_layer;
+      m.relu = c.post_pool ? false : c.relu;
+      m.post_pool = c.post_pool;
+      m.cout = member_cout(ops_[q]);
+      m.off = off;
+      m.tensor = c.out_tensor >= 0 ? c.out_tensor : c.raw_tensor;
+      g.members.push_back(m);
+      g.group_scale |= (c.bn_layer >= 0 && !c.post_pool);
+      gop.name += (gop.name.empty() ? "" : "+") + layers_[c.conv_layer].name;
+      gop.first_layer = std::min(gop.first_layer, ops_[q].first_layer);
+      gop.last_layer = std::max(gop.last_layer, ops_[q].last_layer);
+      // a pooling op that applies this member's bias / BN now finds them in the group
+      for (auto& o : ops_)
+        if (o.type == Op::POOL_CL && o.affine_conv == ops_[q].conv) { o.affine_conv = gidx; o.affine_off = off; }
+      off += m.cout;
+    }
+    gop.conv = gidx;
+    convs_.push_back(g);
+    ops_[grp[0]] = gop;
+    for (size_t q = grp.size(); q-- > 1;) ops_.erase(ops_.begin() + (long)grp[q]);
+  }
+}
+
+void Net::plan_conv_group(int li, std::vector<bool>& done, int in_override) {
   OrigLayer& L = layers_[li];
   ConvOp c;
   c.conv_layer = li;
-  c.in_tensor = L.bottoms[0];
+  c.in_tensor = in_override >= 0 ? in_override : L.bottoms[0];
   const int T0 = L.tops[0];
   int last = li;
   int pre = T0;
@@ -1152,6 +1300,8 @@ void Net::plan() {
       tensors_[op.out].materialized = true;
       done[li] = true;
       ops_.push_back(op);
+    } else if (t == "Pooling" && try_commute_pool_conv(li, done, view_of)) {
+      // emitted as conv + pooling-with-epilogue
     } else if (t == "Pooling") {
       Tensor& x = tensors_[L.bottoms[0]];
       Tensor& y = tensors_[L.tops[0]];
@@ -1210,6 +1360,8 @@ void Net::plan() {
       ECO_CHECK(false, "layer type " << t << " (" << L.name << ") has no device implementation in this round");
     }
   }
+
+  fuse_sibling_1x1();
 
   // ---- 3. storage: views, zero-copy concat, allocation ----
   for (size_t i = 0; i < tensors_.size(); ++i) tensors_[i].root = (int)i;
@@ -1369,6 +1521,10 @@ void Net::plan() {
         c.NB = x.shape[0];
         c.Cin = x.shape[1];
         c.Cout = L.params[0].shape[0];
+        if (!c.members.empty()) {
+          c.Cout = 0;
+          for (const ConvMember& m : c.members) c.Cout += m.cout;
+        }
         for (int i = 0; i < nsp; ++i) {
           const int a = 3 - nsp + i;
           c.K[a] = k[i]; c.S[a] = s[i]; c.P[a] = pd[i];
@@ -1429,7 +1585,7 @@ void Net::plan() {
         kp.Cout = c.Cout;
         const int ntiles = (c.Cout + 255) / 256;
         kp.block_n = round_up((c.Cout + ntiles - 1) / ntiles, 16);
-        if (kp.block_n >= 192 && (kp.block_n / 2) % 16 == 0) {
+        if (kp.block_n >= 192 && (kp.block_n / 2) % 16 == 0 && c.members.empty()) {
           // wave quantisation on the persistent grid: halve the N tile when that lowers
           // ceil(tiles / SMs) * tile_cost (e.g. res5 at batch 64: 196 tiles of 256 -> 392 tiles of 128)
           auto cost = [&](int bn) {
@@ -1445,13 +1601,22 @@ void Net::plan() {
         kp.relu = c.relu ? 1 : 0;
         c.w_dev = static_cast<__nv_bfloat16*>(dalloc((size_t)c.Cout_pad * c.Ktotal * 2, true));
         c.bias_dev = static_cast<float*>(dalloc((size_t)c.Cout * 4, true));
-        if (c.bn_layer >= 0) {
+        if (c.bn_layer >= 0 || c.group_scale) {
           c.scale_dev = static_cast<float*>(dalloc((size_t)c.Cout * 4, true));
           c.shift_dev = static_cast<float*>(dalloc((size_t)c.Cout * 4, true));
         }
+        for (const ConvMember& m : c.members)
+          if (m.post_pool && !c.post_bias_dev) {
+            c.post_bias_dev = static_cast<float*>(dalloc((size_t)c.Cout * 4, true));
+            c.post_scale_dev = static_cast<float*>(dalloc((size_t)c.Cout * 4, true));
+            c.post_shift_dev = static_cast<float*>(dalloc((size_t)c.Cout * 4, true));
+          }
         kp.bias = c.bias_dev;
         kp.scale = c.scale_dev;
         kp.shift = c.shift_dev;
+        if (c.post_pool) {  // the pooling op behind this conv applies them
+          kp.bias = nullptr; kp.scale = nullptr; kp.shift = nullptr; kp.relu = 0;
+        }
         auto bind = [&](int tid, __nv_bfloat16*& ptr, long long& cs, int& coff) {
           if (tid < 0) { ptr = nullptr; cs = 0; coff = 0; return; }
           Tensor& t = tensors_[tid];
@@ -1461,6 +1626,23 @@ void Net::plan() {
           cs = t.cs;
           coff = t.coff;
         };
+        if (!c.members.empty()) {
+          ECO_CHECK(c.members.size() <= 4, "fused 1x1 group too large");
+          kp.nseg = (int)c.members.size();
+          for (size_t q = 0; q < c.members.size(); ++q) {
+            const ConvMember& m = c.members[q];
+            long long cs = 0;
+            int coff = 0;
+            bind(m.tensor, kp.seg_ptr[q], cs, coff);
+            kp.seg_cs[q] = cs;
+            kp.seg_coff[q] = coff - m.off;
+            kp.seg_end[q] = m.off + m.cout;
+            kp.seg_relu[q] = m.relu ? 1 : 0;
+          }
+          kp.out = kp.seg_ptr[0];
+          kp.out_cs = kp.seg_cs[0];
+          kp.out_coff = kp.seg_coff[0];
+        } else
         bind(c.out_tensor, kp.out, kp.out_cs, kp.out_coff);
         bind(c.raw_tensor, kp.raw, kp.raw_cs, kp.raw_coff);
         __nv_bfloat16* rp = nullptr;
@@ -1494,6 +1676,7 @@ void Net::plan() {
             kp.tmem_cols = pow2_at_least(kp.block_n);
           }
         }
+        ECO_CHECK(c.members.empty() || kp.persistent, "fused 1x1 group " << op.name << " needs the persistent im2col kernel");
         plan_halo(c);
         const double taps = (double)c.K[0] * c.K[1] * c.K[2];
         c.flops = 2.0 * kp.M * c.Cout * taps * c.Cin;
@@ -1531,6 +1714,22 @@ void Net::plan() {
         q.KD = K[0]; q.KH = K[1]; q.KW = K[2]; q.sD = S[0]; q.sH = S[1]; q.sW = S[2];
         q.pD = P[0]; q.pH = P[1]; q.pW = P[2];
         q.is_max = method == "MAX";
+        if (op.affine_conv >= 0) {
+          const ConvOp& ac = convs_[op.affine_conv];
+          q.bias = ac.bias_dev; q.scale = ac.scale_dev; q.shift = ac.shift_dev; q.relu = ac.post_relu ? 1 : 0;
+          if (op.affine_off >= 0) {  // member of a fused 1x1 group: its constants live in the group's post arrays
+            q.bias = ac.post_bias_dev + op.affine_off;
+            q.scale = q.shift = nullptr;
+            q.relu = 0;
+            for (const ConvMember& m : ac.members)
+              if (m.off == op.affine_off) {
+                if (m.bn_layer >= 0) { q.scale = ac.post_scale_dev + m.off; q.shift = ac.post_shift_dev + m.off; }
+                // the member's own ConvOp recorded whether a ReLU follows
+                for (const ConvOp& oc : convs_)
+                  if (oc.members.empty() && oc.conv_layer == m.conv_layer) q.relu = oc.post_relu ? 1 : 0;
+              }
+          }
+        }
         op.bytes = 2.0 * ((double)x.count() + (double)y.count());
         break;
       }
@@ -1630,6 +1829,49 @@ void Net::upload_params() {
     if (op.type == Op::CONV) {
       ConvOp& c = convs_[op.conv];
       OrigLayer& L = layers_[c.conv_layer];
+      if (!c.members.empty()) {
+        bool dirty = false;
+        for (const ConvMember& m : c.members)
+          dirty |= layers_[m.conv_layer].params_dirty || (m.bn_layer >= 0 && layers_[m.bn_layer].params_dirty);
+        if (!dirty) continue;
+        const ConvKernelParams& kp = c.kp;
+        std::vector<uint16_t> wp((size_t)c.Cout_pad * c.Ktotal, 0);
+        std::vector<float> bias(c.Cout, 0.f), scale(c.Cout, 1.f), shift(c.Cout, 0.f);
+        std::vector<float> pbias(c.Cout, 0.f), pscale(c.Cout, 1.f), pshift(c.Cout, 0.f);
+        for (const ConvMember& m : c.members) {
+          const OrigLayer& ML = layers_[m.conv_layer];
+          const std::vector<float>& w = ML.params[0].data;
+          for (int o = 0; o < m.cout; ++o)
+            for (int ch = 0; ch < c.Cin; ++ch) {
+              const size_t kidx = ((size_t)(ch / kBlockK)) * kBlockK + ch % kBlockK;  // 1x1: one tap
+              wp[(size_t)(m.off + o) * c.Ktotal + kidx] = f2bf(w[(size_t)o * c.Cin + ch]);
+            }
+          std::vector<float> sc, sh;
+          if (m.bn_layer >= 0) bn_fold(layers_[m.bn_layer], sc, sh);
+          for (int o = 0; o < m.cout; ++o) {
+            const float b = ML.params.size() > 1 ? ML.params[1].data[o] : 0.f;
+            float* B = m.post_pool ? pbias.data() : bias.data();
+            float* S = m.post_pool ? pscale.data() : scale.data();
+            float* H = m.post_pool ? pshift.data() : shift.data();
+            B[m.off + o] = b;
+            if (m.bn_layer >= 0) { S[m.off + o] = sc[o]; H[m.off + o] = sh[o]; }
+          }
+        }
+        (void)kp;
+        CUDA_OK(cudaMemcpyAsync(c.w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice, stream_));
+        CUDA_OK(cudaMemcpyAsync(c.bias_dev, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, stream_));
+        if (c.scale_dev) {
+          CUDA_OK(cudaMemcpyAsync(c.scale_dev, scale.data(), scale.size() * 4, cudaMemcpyHostToDevice, stream_));
+          CUDA_OK(cudaMemcpyAsync(c.shift_dev, shift.data(), shift.size() * 4, cudaMemcpyHostToDevice, stream_));
+        }
+        if (c.post_bias_dev) {
+          CUDA_OK(cudaMemcpyAsync(c.post_bias_dev, pbias.data(), pbias.size() * 4, cudaMemcpyHostToDevice, stream_));
+          CUDA_OK(cudaMemcpyAsync(c.post_scale_dev, pscale.data(), pscale.size() * 4, cudaMemcpyHostToDevice, stream_));
+          CUDA_OK(cudaMemcpyAsync(c.post_shift_dev, pshift.data(), pshift.size() * 4, cudaMemcpyHostToDevice, stream_));
+        }
+        CUDA_OK(cudaStreamSynchronize(stream_));  // host vectors are temporaries
+        continue;
+      }
       const bool bn_dirty = c.bn_layer >= 0 && layers_[c.bn_layer].params_dirty;
       if (L.params_dirty) {
         const ConvKernelParams& kp = c.kp;
@@ -1830,6 +2072,7 @@ void Net::run_op(Op& op, bool with_xform) {
       else if (c.halo) CUDA_OK(launch_conv_halo(c.hp, c.halo_mt, c.tmX, c.tmB, stream_));
       else CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.tmB, stream_));
       if (c.pool_tensor >= 0) mark_written(c.pool_tensor);
+      for (const ConvMember& m : c.members) mark_written(m.tensor);
       if (c.out_tensor >= 0) mark_written(c.out_tensor);
       if (c.raw_tensor >= 0) mark_written(c.raw_tensor);
       break;

@@ -105,6 +105,14 @@ struct VisBlob {
   int tensor = -1;
 };
 
+// one of several 1x1 convolutions on the same input that run as a single GEMM (ConvOp::members)
+struct ConvMember {
+  int conv_layer = -1, bn_layer = -1;
+  bool relu = false, post_pool = false;
+  int cout = 0, off = 0;   // channels, first channel inside the fused N range
+  int tensor = -1;         // the tensor this member stores
+};
+
 struct ConvOp {
   int conv_layer = -1, bn_layer = -1, elt_layer = -1;
   bool relu = false;
@@ -135,6 +143,11 @@ struct ConvOp {
   int pool_layer = -1;        // Pooling layer folded into the rows kernel
   int pool_tensor = -1;       // its top (the only tensor the fused op stores)
   StemRowsParams rp{};
+  std::vector<ConvMember> members;  // non-empty: fused sibling 1x1 convolutions (fuse_1x1), Cout = sum of theirs
+  bool group_scale = false;         //   some member has a folded BN
+  float *post_bias_dev = nullptr, *post_scale_dev = nullptr, *post_shift_dev = nullptr;  // for pooling ops behind post_pool members
+  bool post_pool = false;     // 1x1 conv moved in front of the AVE pooling that fed it: stores acc only (no bias / BN / ReLU);
+  bool post_relu = false;     //   the pooling op behind it applies bias, BN and ReLU (pool_commute)
   double flops = 0, bytes = 0;
 };
 
@@ -144,6 +157,8 @@ struct Op {
   std::string name;
   int first_layer = 0, last_layer = 0;  // orig layer range covered
   int conv = -1;                        // index into convs_
+  int affine_conv = -1;                 // POOL_CL: conv whose bias / BN / ReLU this pooling applies (pool_commute)
+  int affine_off = -1;                  //   >= 0: that conv is member of a fused group, first channel inside it
   // generic payload
   int in0 = -1, in1 = -1, out = -1;     // tensor ids
   int layer = -1;                       // orig layer (params, pooling geometry)
@@ -208,6 +223,8 @@ class Net {
   int persistent_ = 1;
   int dual_m_ = 1;
   int halo_ = 0;  // 0 off (default: measured slower, profiles/r01h), 1 auto (resident weights only), 2 force two halves, 3 allow streamed weights
+  int fuse_1x1_ = 1;  // 1: 1x1 convolutions reading the same tensor run as one GEMM with segmented output (fast plan only)
+  int pool_commute_ = 1;  // 1: AVE 3x3/s1 pooling -> 1x1 conv (+BN+ReLU) runs as conv -> pooling(+bias+BN+ReLU) when nothing else reads the pooled blob
   int stem_rows_ = 1;  // 0: stem as 4x1 im2col GEMM; 1: rows kernel, pool1 folded in when its input has no other reader; 2: rows kernel, never fold the pool
   int debug_flags_ = 0;
   bool epi_staged_ = false;
@@ -250,7 +267,9 @@ class Net {
   void* dalloc(size_t bytes, bool zero);
   Tensor& T(int i) { return tensors_[i]; }
   int add_tensor(const std::string& name);
-  void plan_conv_group(int li, std::vector<bool>& done);
+  void plan_conv_group(int li, std::vector<bool>& done, int in_override = -1);
+  void fuse_sibling_1x1();
+  bool try_commute_pool_conv(int li, std::vector<bool>& done, std::vector<int>& view_of);
   void make_tensor_maps(ConvOp& c);
   bool plan_halo(ConvOp& c);
   void plan_stem_rows(ConvOp& c);

@@ -283,6 +283,49 @@ def test_inception_block_concat_alias(gpu, a_mode):
     run_case(INCEPTION, (2, 8, 14, 14), a_mode, check=("b1_bn", "b2_bn", "pl", "pp_bn", "mp", "out", "down", "nx_bn"))
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 14, 14), (5, 8, 28, 28), (3, 8, 9, 11)], ids=["14", "28", "9x11"])
+def test_inception_pool_conv_commuted_in_fast_plan(gpu, shape):
+    # fast plan: AVE 3x3/s1/p1 pooling -> 1x1 conv -> BN -> ReLU runs as conv (64 -> 32 channels, no bias) -> pooling
+    # with bias + BN + ReLU in its epilogue (exact by linearity; one bf16 rounding moves from the pooled blob to the
+    # conv output).  The pooled blob is never formed; the concat slice must match the oracle to bf16 noise.
+    from eco_testlib import rel_l2
+    txt = INCEPTION.replace("input_dim: 2 input_dim: 8 input_dim: 14 input_dim: 14",
+                            " ".join("input_dim: %d" % d for d in shape))
+    ref = refnet.RefNet(txt).init_params(5)
+    x = np.random.default_rng(3).normal(size=shape).astype(np.float32)
+    want = ref.forward(x, bf16=True)
+    got = {}
+    for commute in (1, 0):
+        net = make_net(txt, keep_all=False, a_mode=1)
+        net.set_option("pool_commute", commute)
+        load_params(net, ref.params_dict())
+        net.blobs["data"].data[...] = x
+        net.forward()
+        got[commute] = {k: net.blobs[k].data.copy() for k in ("pp_bn", "out", "nx_bn")}
+        if commute:
+            with pytest.raises(RuntimeError):
+                net.blobs["pl"].data  # never formed
+        else:
+            assert net.blobs["pl"].data.shape == want["pl"].shape
+    for k in ("pp_bn", "out", "nx_bn"):
+        e1, e0 = rel_l2(got[1][k], want[k]), rel_l2(got[0][k], want[k])
+        assert e1 <= 6e-3 and e0 <= 6e-3, (k, e1, e0)
+        scale = np.abs(want[k]).max()
+        assert np.abs(got[1][k] - want[k]).max() <= 2e-2 * scale, k
+    # sibling 1x1 fusion (b1 + b2r + the commuted pp run as one GEMM with three output segments) changes no bit
+    net = make_net(txt, keep_all=False, a_mode=1)
+    net.set_option("fuse_1x1", 0)
+    load_params(net, ref.params_dict())
+    net.blobs["data"].data[...] = x
+    net.forward()
+    for k in ("pp_bn", "out", "nx_bn"):
+        assert np.array_equal(net.blobs[k].data, got[1][k]), k
+    # the other branches are untouched by the rewrite: bit-identical between the two plans
+    c32 = 32 + 96
+    assert np.array_equal(got[1]["out"][:, :c32], got[0]["out"][:, :c32])
+    assert np.array_equal(got[1]["out"][:, c32 + 32:], got[0]["out"][:, c32 + 32:])
+
+
 POOLS = """name: "pools"
 input: "data" input_dim: 3 input_dim: 8 input_dim: %d input_dim: %d
 layer { name: "f" type: "Convolution" bottom: "data" top: "f" convolution_param { num_output: 24 kernel_size: 1 } }
