@@ -1113,7 +1113,9 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
 //   output column); output row y needs cell rows y..y+3 against the weight K blocks 0..3.
 //   warp 0: TMA producer (one cell row per stage), warp 1: MMA issuer -- every resident cell row is
 //   multiplied into the (up to) four accumulators it contributes to, warps 2-9: epilogue.
-constexpr int kStemThreads = 320;
+constexpr int kStemThreads = 320;        // warp 0 TMA, 1 MMA, 2-9 epilogue
+constexpr int kStemThreadsDirect = 448;  // + warps 10-13: window gather from raw frames (src_mode 1 / 2)
+constexpr int kStemRawStagesMax = 8;
 constexpr int kStemSlots = 8;  // accumulator ring: 8 x 64 fp32 columns = all 512 TMEM columns
 
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
@@ -1128,8 +1130,8 @@ __device__ __forceinline__ long long mbar_wait_timed(uint32_t bar, uint32_t pari
   return clock64() - t0;
 }
 
-template <bool POOL>
-__global__ void __launch_bounds__(kStemThreads, 1)
+template <bool POOL, int SRC>
+__global__ void __launch_bounds__(kStemThreadsDirect, 1)
 stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ uint8_t smem_raw[];
@@ -1141,7 +1143,11 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
   const uint32_t sB = sA + (uint32_t)SA * 16384u;
   const uint32_t sRow = sB + 4u * 8192u;
   const size_t row_bytes = POOL ? 2 * 16384 : 0;
-  float* s_scale = reinterpret_cast<float*>(smem + (size_t)SA * 16384 + 4 * 8192 + row_bytes);
+  const int RS = SRC ? p.raw_stages : 0;
+  const size_t raw_off = (size_t)SA * 16384 + 4 * 8192 + row_bytes;
+  const uint32_t sRaw = base + (uint32_t)raw_off;
+  const size_t raw_bytes = (size_t)RS * p.raw_stage_bytes;
+  float* s_scale = reinterpret_cast<float*>(smem + raw_off + raw_bytes);
   float* s_shift = s_scale + 64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 64);
   const uint32_t bar_a_full = smem_u32(bars);
@@ -1149,7 +1155,9 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
   const uint32_t bar_b_full = bar_a_empty + 8 * SA;
   const uint32_t bar_acc_full = bar_b_full + 8;
   const uint32_t bar_acc_empty = bar_acc_full + 8 * kStemSlots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 1 + 2 * kStemSlots);
+  const uint32_t bar_raw_full = bar_acc_empty + 8 * kStemSlots;
+  const uint32_t bar_raw_empty = bar_raw_full + 8 * kStemRawStagesMax;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 1 + 2 * kStemSlots + 2 * kStemRawStagesMax);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1159,6 +1167,7 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
     for (int s = 0; s < SA; ++s) { mbar_init(bar_a_full + 8 * s, 1); mbar_init(bar_a_empty + 8 * s, 1); }
     mbar_init(bar_b_full, 1);
     for (int s = 0; s < kStemSlots; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 8); }
+    for (int s = 0; s < RS; ++s) { mbar_init(bar_raw_full + 8 * s, 1); mbar_init(bar_raw_empty + 8 * s, 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -1208,6 +1217,38 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
       }
       uint32_t s = 0, ph = 0;
       long long w_prod = 0;
+      if constexpr (SRC != 0) {
+        // raw frames: the two image rows (x 3 channels) a cell row is made of, bulk-copied into the raw ring
+        const uint32_t esz = SRC == 1 ? 4u : 1u;
+        const uint32_t rowb = (uint32_t)p.W * esz;
+        const uint8_t* srcb = static_cast<const uint8_t*>(p.src);
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+          int f, r0, r1, p0;
+          unit_rows(u, f, r0, r1, p0);
+          for (int Y = r0; Y < r1 + 3; ++Y) {
+            w_prod += mbar_wait_timed(bar_raw_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
+            if (elect_one()) {
+              uint32_t nrows = 0;
+#pragma unroll
+              for (int dy = 0; dy < 2; ++dy) nrows += ((unsigned)(2 * Y - 3 + dy) < (unsigned)p.H) ? 3u : 0u;
+              mbar_arrive_expect_tx(bar_raw_full + 8 * s, nrows * rowb);
+#pragma unroll
+              for (int dy = 0; dy < 2; ++dy) {
+                const int y = 2 * Y - 3 + dy;
+                if ((unsigned)y >= (unsigned)p.H) continue;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  const uint8_t* g = srcb + (((size_t)f * 3 + c) * p.H + y) * (size_t)rowb;
+                  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                               ::"r"(sRaw + s * p.raw_stage_bytes + (uint32_t)(dy * 3 + c) * rowb), "l"(g), "r"(rowb),
+                               "r"(bar_raw_full + 8 * s) : "memory");
+                }
+              }
+            }
+            if (++s == (uint32_t)RS) { s = 0; ph ^= 1u; }
+          }
+        }
+      } else
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         int f, r0, r1, p0;
         unit_rows(u, f, r0, r1, p0);
@@ -1250,6 +1291,7 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
             w_acc += mbar_wait_timed(bar_acc_empty + 8 * (ridx % (uint32_t)kStemSlots),
                                      ((ridx / (uint32_t)kStemSlots) & 1u) ^ 1u, p.error_flag, 5);
           }
+          if (SRC) fence_proxy_async_smem();  // windows were written with st.shared (generic proxy)
           tc_fence_after();
           if (elect_one()) {
             // taps ilo..ihi of this cell row land in output rows Y-ilo .. Y-ihi of the unit
@@ -1291,6 +1333,77 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
       if ((p.debug_flags & 16) && blockIdx.x == 0 && lane == 0)
         printf("stem_rows cta0: mma waited %lld (tile loads) + %lld (accumulator slots) cycles of %lld\n", w_full, w_acc,
                clock64() - t_start);
+    }
+  } else if (warp >= 10) {
+    // ===================== window gather (src_mode 1 / 2): warp gw builds every 4th cell row =====================
+    // cell (Y, X) = 2x2 pixels x 3 channels (+4 zeros) of the zero-padded frame; window x of the tile = cells
+    // x..x+3 = one 128-byte row in the 128B-swizzled K-major layout the MMA descriptors expect
+    if constexpr (SRC != 0) {
+      const int gw = warp - 10;
+      const int CW = p.OW + 3;
+      const float mean[3] = {p.mean0, p.mean1, p.mean2};
+      uint32_t i = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int f, r0, r1, p0;
+        unit_rows(u, f, r0, r1, p0);
+        for (int Y = r0; Y < r1 + 3; ++Y, ++i) {
+          if ((int)(i & 3u) != gw) continue;
+          const uint32_t rs = i % (uint32_t)RS, rph = (i / (uint32_t)RS) & 1u;
+          const uint32_t as = i % (uint32_t)SA, aph = (i / (uint32_t)SA) & 1u;
+          mbar_wait(bar_raw_full + 8 * rs, rph, p.error_flag, 8);
+          mbar_wait(bar_a_empty + 8 * as, aph ^ 1u, p.error_flag, 9);
+          const uint32_t raw = sRaw + rs * p.raw_stage_bytes;
+          const uint32_t tile = sA + as * 16384u;
+          const bool yok0 = (unsigned)(2 * Y - 3) < (unsigned)p.H, yok1 = (unsigned)(2 * Y - 2) < (unsigned)p.H;
+          for (int X = lane; X < CW; X += 32) {
+            float v[12];
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx) {
+                const int x = 2 * X - 3 + dx;
+                const bool ok = (dy ? yok1 : yok0) && (unsigned)x < (unsigned)p.W;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  float t = 0.f;
+                  if (ok) {
+                    const uint32_t a = raw + (uint32_t)((dy * 3 + c) * p.W + x) * (SRC == 1 ? 4u : 1u);
+                    if (SRC == 1) {
+                      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(a));
+                    } else {
+                      uint32_t b;
+                      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(a));
+                      t = (float)b - mean[c];
+                    }
+                  }
+                  v[(dy * 2 + dx) * 3 + c] = t;
+                }
+              }
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            w[6] = 0u; w[7] = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int x = X - j;  // window that sees this cell as its j-th
+              if (x >= 0 && x < p.OW) {
+                const uint32_t rowa = tile + (uint32_t)x * 128u;
+                const uint32_t sw = (uint32_t)(x & 7);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((((uint32_t)(2 * j)) ^ sw) << 4)), "r"(w[0]),
+                             "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((((uint32_t)(2 * j + 1)) ^ sw) << 4)),
+                             "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a_full + 8 * as) : "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_raw_empty + 8 * rs) : "memory");
+          }
+        }
+      }
     }
   } else {
     // ===================== epilogue warps (8): lane quarter x column half =====================
@@ -1425,10 +1538,12 @@ cudaError_t conv_umma_configure() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(stem_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#define ECO_STEM_ATTR(P, S)                                                                                         \
+  e = cudaFuncSetAttribute(stem_rows_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(stem_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return e;
+  ECO_STEM_ATTR(true, 0) ECO_STEM_ATTR(true, 1) ECO_STEM_ATTR(true, 2)
+  ECO_STEM_ATTR(false, 0) ECO_STEM_ATTR(false, 1) ECO_STEM_ATTR(false, 2)
+#undef ECO_STEM_ATTR
   return cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
@@ -1436,8 +1551,16 @@ cudaError_t launch_stem_rows(const StemRowsParams& p, const CUtensorMap& tmX, co
   const int units = p.F * p.strips;
   const int grid = units < p.num_sms ? units : p.num_sms;
   const size_t smem = stem_rows_smem_bytes(p);
-  if (p.pool) stem_rows_kernel<true><<<grid, kStemThreads, smem, stream>>>(p, tmX, tmB);
-  else stem_rows_kernel<false><<<grid, kStemThreads, smem, stream>>>(p, tmX, tmB);
+  const int threads = p.src_mode ? kStemThreadsDirect : kStemThreads;
+  if (p.pool) {
+    if (p.src_mode == 0) stem_rows_kernel<true, 0><<<grid, threads, smem, stream>>>(p, tmX, tmB);
+    else if (p.src_mode == 1) stem_rows_kernel<true, 1><<<grid, threads, smem, stream>>>(p, tmX, tmB);
+    else stem_rows_kernel<true, 2><<<grid, threads, smem, stream>>>(p, tmX, tmB);
+  } else {
+    if (p.src_mode == 0) stem_rows_kernel<false, 0><<<grid, threads, smem, stream>>>(p, tmX, tmB);
+    else if (p.src_mode == 1) stem_rows_kernel<false, 1><<<grid, threads, smem, stream>>>(p, tmX, tmB);
+    else stem_rows_kernel<false, 2><<<grid, threads, smem, stream>>>(p, tmX, tmB);
+  }
   return cudaGetLastError();
 }
 

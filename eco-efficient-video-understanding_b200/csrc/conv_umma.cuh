@@ -117,6 +117,16 @@ struct StemRowsParams {
   int a_stages;
   uint32_t a_tx_bytes;       // OW * 128
   int num_sms;
+  // source of the cell rows: 0 = bf16 cells written by the stem transform kernel (tiled TMA), 1 = the net's fp32
+  // NCHW frames, 2 = raw uint8 NCHW frames with the per-channel mean subtracted: image rows are bulk-copied
+  // into a shared-memory ring and four gather warps build the overlapping windows on chip, so the transform
+  // kernel, its 217 MB of cells per step and their re-read disappear
+  int src_mode;
+  const void* src;           // frames (src_mode 1 / 2)
+  int H, W;                  // frame size
+  float mean0, mean1, mean2; // src_mode 2
+  int raw_stages;            // ring of raw image-row pairs (src_mode 1 / 2)
+  uint32_t raw_stage_bytes;  // 6 rows (2 image rows x 3 channels) x W x element size, 128-byte padded
   int debug_flags;           // development: 1 no stores, 2 no TMEM loads, 4 no MMAs, 8 no TMA loads, 16 print role wait cycles (CTA 0)
   const float* bias; const float* scale; const float* shift;
   int relu;
@@ -124,7 +134,8 @@ struct StemRowsParams {
   int* error_flag;
 };
 inline size_t stem_rows_smem_bytes(const StemRowsParams& p) {
-  return 1024 + (size_t)p.a_stages * 16384 + 4 * 8192 + (p.pool ? 2 * 16384 : 0) + 2 * 64 * sizeof(float) + 512;
+  return 1024 + (size_t)p.a_stages * 16384 + 4 * 8192 + (p.pool ? 2 * 16384 : 0) +
+         (p.src_mode ? (size_t)p.raw_stages * p.raw_stage_bytes : 0) + 2 * 64 * sizeof(float) + 1024;
 }
 cudaError_t launch_stem_rows(const StemRowsParams& p, const CUtensorMap& tmX, const CUtensorMap& tmB, cudaStream_t stream);
 

@@ -530,6 +530,7 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "halo") halo_ = v;
   else if (key == "stem_rows") stem_rows_ = v;
   else if (key == "pool_commute") pool_commute_ = v;
+  else if (key == "stem_direct") stem_direct_ = v;
   else if (key == "fuse_1x1") fuse_1x1_ = v;
   else if (key == "debug_flags") debug_flags_ = v;
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
@@ -842,11 +843,24 @@ void Net::plan_stem_rows(ConvOp& c) {
   }
   r.a_stages = r.pool ? 6 : 8;
   r.a_tx_bytes = (uint32_t)r.OW * 128u;
+  r.H = c.I[1]; r.W = c.I[2];
+  if (c.direct_in) {
+    // ring of raw image-row pairs (2 rows x 3 channels, sized for fp32) in what is left of the 227 KB
+    r.raw_stage_bytes = (uint32_t)round_up(6 * r.W * 4, 128);
+    const size_t used = 1024 + (size_t)r.a_stages * 16384 + 4 * 8192 + (r.pool ? 2 * 16384 : 0) + 2048;
+    const size_t left = (size_t)227 * 1024 - used;
+    r.raw_stages = (int)std::min<size_t>(8, left / r.raw_stage_bytes);
+    if (r.raw_stages < 3) { r.a_stages -= 2; r.raw_stages = (int)std::min<size_t>(8, (left + 2 * 16384) / r.raw_stage_bytes); }
+    ECO_CHECK(r.raw_stages >= 2, "stem rows kernel: frame rows of " << r.W << " pixels do not fit the raw ring; set stem_direct=0");
+  }
   r.num_sms = g_num_sms;
   r.debug_flags = debug_flags_;
   r.bias = c.kp.bias; r.scale = c.kp.scale; r.shift = c.kp.shift; r.relu = c.kp.relu;
   r.out = static_cast<__nv_bfloat16*>(y.dev); r.out_cs = y.cs; r.out_coff = y.coff;
   r.error_flag = c.kp.error_flag;
+  if (c.direct_in) {
+    std::memset(&c.tmX, 0, sizeof(c.tmX));  // unused: the kernel gathers from the frames
+  } else {
   // cell rows as [64-value window, OW windows (32 bytes apart), CH rows, F frames]
   cuuint64_t dims[4] = {64, (cuuint64_t)r.OW, (cuuint64_t)c.stem_CH, (cuuint64_t)c.NB};
   cuuint64_t strides[3] = {32, (cuuint64_t)c.stem_CW * 32, (cuuint64_t)c.stem_CH * c.stem_CW * 32};
@@ -857,6 +871,7 @@ void Net::plan_stem_rows(ConvOp& c) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ECO_CHECK(e == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stem cell rows) failed with " << (int)e
                                    << "; set option stem_rows=0 to use the im2col kernel");
+  }
   if (r.pool) {
     const double px = (double)c.NB * r.PH * r.PW * 64;
     c.bytes = 2.0 * ((double)c.NB * c.I[1] * c.I[2] * 3 + px + 64.0 * 147);
@@ -1544,7 +1559,8 @@ void Net::plan() {
           // conv is presented to the GEMM as a 4(h) x 1(w) kernel over 64 "channels" with pixel stride 16.
           c.stem_CH = c.O[1] + 3;
           c.stem_CW = c.O[2] + 3;
-          c.stem_bytes = (size_t)c.NB * c.stem_CH * c.stem_CW * 16 * 2 + 256;
+          c.direct_in = c.rows && stem_direct_ && (c.I[2] % 16 == 0);
+          c.stem_bytes = c.direct_in ? 256 : (size_t)c.NB * c.stem_CH * c.stem_CW * 16 * 2 + 256;
           c.stem_in = static_cast<__nv_bfloat16*>(dalloc(c.stem_bytes, true));
           kp.x = c.stem_in;
           kp.x_sW = 16; kp.x_sH = (long long)c.stem_CW * 16; kp.x_sD = 0;
@@ -1684,7 +1700,7 @@ void Net::plan() {
         if (c.rows) plan_stem_rows(c);
         op.flops = c.flops;
         op.bytes = c.bytes;
-        op.launches = 1 + (c.stem_in ? 1 : 0);
+        op.launches = 1 + ((c.stem_in && !c.direct_in) ? 1 : 0);
         break;
       }
       case Op::POOL_CL: {
@@ -2036,6 +2052,18 @@ void Net::sync() {
 // forward reads straight from a staging slot).
 void Net::run_input_xform(ConvOp& c, const float* src) {
   Tensor& x = tensors_[c.in_tensor];
+  if (c.direct_in) {
+    // no transform kernel: the stem rows kernel reads the frames (this launch IS the convolution)
+    StemRowsParams r = c.rp;
+    if (u8_src_) {
+      r.src_mode = 2; r.src = u8_src_;
+      r.mean0 = u8_mean_[0]; r.mean1 = u8_mean_[1]; r.mean2 = u8_mean_[2];
+    } else {
+      r.src_mode = 1; r.src = src ? src : static_cast<const float*>(x.dev);
+    }
+    CUDA_OK(launch_stem_rows(r, c.tmX, c.tmB, stream_));
+    return;
+  }
   if (u8_src_) {
     // raw uint8 frames: mean subtraction fused into the transform (stem) or into a conversion pass
     const unsigned char* u8 = static_cast<const unsigned char*>(u8_src_);
@@ -2068,7 +2096,8 @@ void Net::run_op(Op& op, bool with_xform) {
     case Op::CONV: {
       ConvOp& c = convs_[op.conv];
       if (c.stem_in && with_xform) run_input_xform(c, nullptr);
-      if (c.rows) CUDA_OK(launch_stem_rows(c.rp, c.tmX, c.tmB, stream_));
+      if (c.direct_in) {}  // launched by run_input_xform (outside the CUDA graph: its source pointer changes per call)
+      else if (c.rows) CUDA_OK(launch_stem_rows(c.rp, c.tmX, c.tmB, stream_));
       else if (c.halo) CUDA_OK(launch_conv_halo(c.hp, c.halo_mt, c.tmX, c.tmB, stream_));
       else CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.tmB, stream_));
       if (c.pool_tensor >= 0) mark_written(c.pool_tensor);

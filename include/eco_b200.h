@@ -48,7 +48,7 @@ int eco_device_count(int* count);        /* 0 devices is not an error here */
 int eco_net_create(const char* prototxt_path, int phase, eco_net** out);
 int eco_net_create_from_string(const char* prototxt_text, int phase, eco_net** out);
 int eco_net_destroy(eco_net* net);
-/* options, set before the first forward/reshape:  "keep_all_blobs" (0/1: also store blobs the
+/* options, set before the first forward/reshape (full list: INTEGRATION.md section 4):  "keep_all_blobs" (0/1: also store blobs the
  * fused plan would keep on chip, e.g. a conv output that only feeds its BN), "a_mode"
  * (0 cp.async gather, 1 TMA im2col, -1 auto), "use_graph" (0/1 CUDA-graph replay of full forwards) */
 int eco_net_set_option(eco_net* net, const char* key, int value);

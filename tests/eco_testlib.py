@@ -21,12 +21,13 @@ TOL_NET_FULL = 1e-1  # ECO-Full is 69 convs deep on the 2-D stream: oracle self-
 TOL_LOGITS = 2e-2 # free-running whole net, logits max|a-b| / max|b| (oracle self-noise: 4.2e-3)
 
 
-def make_net(text, keep_all=True, a_mode=None, graph=False, persistent=True, dual_m=1, halo=0, stem_rows=None):
+def make_net(text, keep_all=True, a_mode=None, graph=False, persistent=True, dual_m=1, halo=0, stem_rows=None, **extra):
     import caffe
     opts = {"keep_all_blobs": 1 if keep_all else 0, "use_graph": 1 if graph else 0, "halo": halo,
             "persistent": 2 if persistent else 0, "dual_m": dual_m}
     if stem_rows is not None:
         opts["stem_rows"] = stem_rows
+    opts.update(extra)
     if a_mode is not None:
         opts["a_mode"] = a_mode
     return caffe.Net.from_string(text, caffe.TEST, **opts)

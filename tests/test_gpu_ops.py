@@ -49,13 +49,13 @@ PLAIN = {"gp", "gp_r", "fc"}  # blobs that are plain fp32 on the device
 
 
 def run_case(txt, shape, a_mode, check=("c_bn",), seed=0, keep_all=True, persistent=True, dual_m=1, halo=1,
-             stem_rows=None):
+             stem_rows=None, **extra):
     ref = refnet.RefNet(txt).init_params(seed + 1)
     rng = np.random.default_rng(seed)
     x = rng.normal(size=shape).astype(np.float32)
     want = ref.forward(x, bf16=True)
     net = make_net(txt, keep_all=keep_all, a_mode=a_mode, persistent=persistent, dual_m=dual_m, halo=halo,
-                   stem_rows=stem_rows)
+                   stem_rows=stem_rows, **extra)
     load_params(net, ref.params_dict())
     net.blobs["data"].data[...] = x
     net.forward()
@@ -172,14 +172,17 @@ STEM_POOL = 'layer { name: "p1" type: "Pooling" bottom: "c_bn" top: "p1" pooling
 
 @pytest.mark.parametrize("shape", [(2, 3, 32, 32), (2, 3, 30, 34), (3, 3, 224, 224), (160, 3, 32, 32), (1, 3, 256, 250)],
                          ids=["32x32", "30x34", "224", "160frames", "256x250"])
+@pytest.mark.parametrize("direct", [1, 0], ids=["frames", "cells"])
 @pytest.mark.parametrize("pool", [False, True], ids=["rows", "rows_pool"])
-def test_stem_rows_kernel(gpu, shape, pool):
+def test_stem_rows_kernel(gpu, shape, pool, direct):
     # the production stem: sliding window over cell rows with a ring of TMEM accumulators; with `pool` the MAX
     # 3x3/s2 pooling behind it (pool1) is applied on chip and the full-resolution map is never stored.
     # 160 frames: more work units than SMs (several units per CTA, both rings wrap); odd / even output heights
     # cover the clipped last pooling window of caffe's ceil mode.
     txt = conv_net(shape, 64, [7, 7], [2, 2], [3, 3]) + (STEM_POOL if pool else "")
-    net, _ = run_case(txt, shape, 1, check=("p1",) if pool else ("c_bn",), keep_all=False, stem_rows=1)
+    # frames: the kernel bulk-copies raw image rows and builds the windows on chip (widths that are a multiple of 16;
+    # other widths and `stem_direct=0` go through the cell buffer written by the transform kernel + tiled TMA)
+    net, _ = run_case(txt, shape, 1, check=("p1",) if pool else ("c_bn",), keep_all=False, stem_rows=1, stem_direct=direct)
     with pytest.raises(RuntimeError):
         net.blobs["c"].data  # never materialised by this kernel
     if pool:
