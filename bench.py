@@ -322,9 +322,19 @@ def main():
                 other_ms += op["ms"]
     pk = peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (all %d launches/step)" % (conv_n // prof_iters),
+    # dram bytes of the same launches from the committed ncu --set full capture (only valid for the captured workload)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_final_ncu_dram_bytes.json")))
+        if tj["model"] == a.model and tj["batch"] == B and tj["segments"] == N:
+            traffic, traffic_src = tj["conv_dram_bytes_per_step"], "profiles/r01_final_ncu_dram_bytes.json"
+    except (OSError, KeyError, ValueError):
+        pass
+    roofline = {"bound": "tensor",
+                "kernel": "conv_umma_persistent_kernel + stem_rows_kernel (all %d conv launches/step)" % (conv_n // prof_iters),
                 "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                "peak_source": pk["src"], "traffic": None,
+                "peak_source": pk["src"], "traffic": traffic, "traffic_unit": "bytes/step (dram read+write, all conv launches)",
+                "traffic_source": traffic_src,
                 "conv_ms_per_step": conv_ms / prof_iters, "other_ms_per_step": other_ms / prof_iters,
                 "share_of_step": conv_ms / max(conv_ms + other_ms, 1e-9)}
 

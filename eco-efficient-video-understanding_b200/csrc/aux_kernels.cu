@@ -291,7 +291,9 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
   }
   const int cg = p.C >> 3;
   const unsigned long long magic_cg = (1ULL << 32) / (unsigned)cg + 1ULL;  // i / cg == (i * magic) >> 32 for i < 2^16
-  if (p.KH == 3 && p.KW == 3 && p.sH == p.sW && (p.sW == 1 || p.sW == 2)) {
+  // (narrow maps, C <= 64: the strips of neighbouring threads start a multiple of 128 bytes apart -> 4- to 7-way
+  //  bank conflicts on every load, measured 39 us for a 51 MB pool; they take the window-per-thread path below)
+  if (p.KH == 3 && p.KW == 3 && p.sH == p.sW && (p.sW == 1 || p.sW == 2) && p.C > 64) {
     // 3x3 windows: a thread owns a strip of T outputs along x and slides over the input columns once
     constexpr int T = 4;
     const int S = p.sW;
@@ -441,8 +443,22 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
       }
     }
     if (!p.is_max) {
+      const float inv = __frcp_rn(div);  // same rounding as the strip path (div is a small integer)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = acc[j] / div;
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] * inv;
+      if (p.bias || p.scale) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float b = p.bias ? __ldg(p.bias + g * 8 + j) : 0.f;
+          const float sc = p.scale ? __ldg(p.scale + g * 8 + j) : 1.f;
+          const float sh = p.scale ? __ldg(p.shift + g * 8 + j) : 0.f;
+          acc[j] = fmaf(acc[j] + b, sc, sh);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+      }
     }
     const long long opix = ((long long)n * p.OH + oy) * p.OW + ox;
     *reinterpret_cast<uint4*>(p.y + opix * p.y_cs + p.y_coff + g * 8) = pack8(acc);

@@ -1601,14 +1601,22 @@ void Net::plan() {
         kp.Cout = c.Cout;
         const int ntiles = (c.Cout + 255) / 256;
         kp.block_n = round_up((c.Cout + ntiles - 1) / ntiles, 16);
-        if (kp.block_n >= 192 && (kp.block_n / 2) % 16 == 0 && c.members.empty()) {
-          // wave quantisation on the persistent grid: halve the N tile when that lowers
-          // ceil(tiles / SMs) * tile_cost (e.g. res5 at batch 64: 196 tiles of 256 -> 392 tiles of 128)
+        if (c.members.empty()) {
+          // wave quantisation on the persistent grid: more, narrower N tiles when that lowers
+          // ceil(tiles / SMs) x tile cost.  Tile cost ~ shared-memory bytes moved per K block (the bound of
+          // cta_group::1 kernels): MMA operand reads 4 x (4096 + 32 N) + TMA writes 16384 + 128 N.
+          // e.g. res5 (M = 6272, Cout = 512) at batch 32: 98 tiles of 256 on 148 SMs -> 147 tiles of 176.
           auto cost = [&](int bn) {
             const long long tiles = ((long long)kp.M + kBlockM - 1) / kBlockM * ((c.Cout + bn - 1) / bn);
-            return ((tiles + g_num_sms - 1) / g_num_sms) * (long long)bn;
+            return ((tiles + g_num_sms - 1) / g_num_sms) * (32768LL + 256LL * bn);
           };
-          if (cost(kp.block_n / 2) < cost(kp.block_n)) kp.block_n /= 2;
+          int best = kp.block_n;
+          for (int nt = ntiles + 1; nt <= ntiles + 3; ++nt) {
+            const int bn = round_up((c.Cout + nt - 1) / nt, 16);
+            if (bn < 96) break;
+            if (cost(bn) < cost(best)) best = bn;
+          }
+          kp.block_n = best;
         }
         c.Cout_pad = round_up(c.Cout, kp.block_n);
         kp.a_mode = a_mode_ < 0 ? A_TMA_IM2COL : a_mode_;
