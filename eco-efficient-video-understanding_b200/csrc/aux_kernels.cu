@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(256) pool2d_k3_strip_kernel(const PoolParams p
 // contiguous in a dense channels-last map, so a handful of 10-20 KB bulk copies put >= 64 KB per SM in
 // flight (three CTAs per SM), which plain 16-byte loads could not; every input row is fetched once per
 // band.  Same caffe semantics as pool_cl_kernel (pooling_layer.cpp:199-262).
+template <int SS>  // 3x3 window stride known at compile time (1 / 2: the strip loops unroll fully), 0: generic
 __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, int rows_out) {
   extern __shared__ __align__(128) uint8_t pool_smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -280,7 +281,9 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
                    : "memory");
     }
   }
-  {
+  // one thread polls the mbarrier; everybody else parks at the CTA barrier (256 spinning threads per CTA took
+  // a large share of the SM's issue slots from the CTAs that were already computing: ncu, r01 final)
+  if (threadIdx.x == 0) {
     uint32_t ok = 0;
     const long long t0 = clock64();
     while (!ok) {
@@ -289,14 +292,13 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
       if (!ok && clock64() - t0 > 4000000000LL) __trap();
     }
   }
+  __syncthreads();
   const int cg = p.C >> 3;
   const unsigned long long magic_cg = (1ULL << 32) / (unsigned)cg + 1ULL;  // i / cg == (i * magic) >> 32 for i < 2^16
-  // (narrow maps, C <= 64: the strips of neighbouring threads start a multiple of 128 bytes apart -> 4- to 7-way
-  //  bank conflicts on every load, measured 39 us for a 51 MB pool; they take the window-per-thread path below)
-  if (p.KH == 3 && p.KW == 3 && p.sH == p.sW && (p.sW == 1 || p.sW == 2) && p.C > 64) {
+  if (SS != 0) {
     // 3x3 windows: a thread owns a strip of T outputs along x and slides over the input columns once
     constexpr int T = 4;
-    const int S = p.sW;
+    constexpr int S = SS ? SS : 1;
     const int strips = (p.OW + T - 1) / T;
     const int items = (oy1 - oy0) * strips * cg;
     for (int i = threadIdx.x; i < items; i += blockDim.x) {
@@ -317,13 +319,14 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
         rows[rr] = pool_smem + (size_t)(rok[rr] ? y - vy_lo : 0) * row_bytes + (size_t)g * 16;
       }
       const long long opix0 = ((long long)n * p.OH + oy) * p.OW;
-      const int ncols = (T - 1) * S + 3;
+      constexpr int ncols = (T - 1) * S + 3;
       if (p.is_max) {
         // max of bf16 values is exact in packed bf16 arithmetic: no fp32 unpacking
         const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
         __nv_bfloat162 c0[4], c1[4], c2[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) c0[j] = c1[j] = c2[j] = ninf;
+#pragma unroll
         for (int col = 0; col < ncols; ++col) {
           const int ix = ix0 + col;
           __nv_bfloat162 cv[4] = {ninf, ninf, ninf, ninf};
@@ -364,6 +367,7 @@ __global__ void __launch_bounds__(256) pool2d_rows_kernel(const PoolParams p, in
         float c0[8], c1[8], c2[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) c0[j] = c1[j] = c2[j] = 0.f;
+#pragma unroll
         for (int col = 0; col < ncols; ++col) {
           const int ix = ix0 + col;
           float cv[8];
@@ -620,12 +624,17 @@ cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {
     if (smem <= 200 * 1024 && row_bytes % 16 == 0 && p.NB <= 65535) {
       static bool configured = false;
       if (!configured) {
-        cudaFuncSetAttribute(pool2d_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(pool2d_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(pool2d_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(pool2d_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         configured = true;
       }
-      if (epilogue && (p.is_max || p.KH != 3 || p.KW != 3 || p.sH != p.sW || p.sW > 2)) return cudaErrorNotSupported;
+      const bool k3 = p.KH == 3 && p.KW == 3 && p.sH == p.sW && (p.sW == 1 || p.sW == 2);
+      if (epilogue && (p.is_max || !k3)) return cudaErrorNotSupported;
       dim3 grid((p.OH + rows_out - 1) / rows_out, p.NB, 1);
-      pool2d_rows_kernel<<<grid, 256, smem, st>>>(p, rows_out);
+      if (k3 && p.sW == 1) pool2d_rows_kernel<1><<<grid, 256, smem, st>>>(p, rows_out);
+      else if (k3) pool2d_rows_kernel<2><<<grid, 256, smem, st>>>(p, rows_out);
+      else pool2d_rows_kernel<0><<<grid, 256, smem, st>>>(p, rows_out);
       return cudaGetLastError();
     }
   }
