@@ -887,6 +887,258 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
 
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant of the persistent kernel (cta_group::2): two CTAs of a cluster (one TPC) compute ONE
+// 256 x block_n tile.  Each CTA loads the im2col rows of ITS 128 output positions and HALF of the weight tile
+// (block_n / 2 rows); the leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256), which reads
+// A and the B half from the shared memory of both SMs, and each SM accumulates its 128 rows x block_n in its own
+// TMEM.  Per SM and K block the shared-memory traffic drops from 16 KB + 128 B x block_n (twice: TMA write + MMA
+// read) to 16 KB + 64 B x block_n -- the bound of the cta_group::1 kernels.
+//   barriers: full[s] lives on the leader (its expect_tx covers the bytes of both CTAs; the peer's TMA loads
+//   signal it through the peer-bit-cleared address), empty[s] / tmem_full[b] exist in both CTAs and are signalled
+//   by multicast tcgen05.commit, tmem_empty[b] lives on the leader and collects 16 epilogue-warp arrivals.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address -> same offset in CTA rank 0 of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_cta(uint32_t local_bar, uint32_t cta) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+               "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_im2col_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h,
+                                                  int n, uint16_t ow, uint16_t oh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow),
+      "h"(oh) : "memory");
+}
+__device__ __forceinline__ void tma_im2col_5d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h,
+                                                  int d, int n, uint16_t ow, uint16_t oh, uint16_t od) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n),
+      "h"(ow), "h"(oh), "h"(od) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// K block of the pair kernel: up to 4 K steps of M = 256 MMAs, then the multicast commit that frees the stage in both CTAs
+__device__ __forceinline__ void mma_kblock_pair(uint32_t acc, uint64_t ad, uint64_t bd, uint32_t accflag, uint32_t ks,
+                                                uint32_t idesc, uint32_t empty_bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, ptrue, g1, g2, g3;\n\t"
+      ".reg .b64 a, b;\n\t"
+      "setp.ne.b32 pacc, %3, 0;\n\t"
+      "setp.eq.u32 ptrue, %5, %5;\n\t"
+      "setp.gt.u32 g1, %4, 1;\n\t"
+      "setp.gt.u32 g2, %4, 2;\n\t"
+      "setp.gt.u32 g3, %4, 3;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %5, pacc;\n\t"
+      "add.s64 a, %1, 2;\n\t"
+      "add.s64 b, %2, 2;\n\t"
+      "@g1 tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, ptrue;\n\t"
+      "add.s64 a, %1, 4;\n\t"
+      "add.s64 b, %2, 4;\n\t"
+      "@g2 tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, ptrue;\n\t"
+      "add.s64 a, %1, 6;\n\t"
+      "add.s64 b, %2, 6;\n\t"
+      "@g3 tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, ptrue;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %7;\n\t"
+      "}"
+      ::"r"(acc), "l"(ad), "l"(bd), "r"(accflag), "r"(ks), "r"(idesc), "r"(empty_bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1)
+conv_umma_pair_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap tmA,
+                      const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  constexpr int TILE_M = 2 * kBlockM;
+  const int S = p.stages;
+  const int BN = p.block_n;
+  const uint32_t a_stage_bytes = kBlockM * 128;
+  const uint32_t b_stage_bytes = (uint32_t)(BN / 2) * 128;  // this CTA's half of the weight tile
+  const uint32_t sA = base;
+  const uint32_t sB = sA + S * a_stage_bytes;
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)S * a_stage_bytes + (size_t)S * b_stage_bytes);
+  float* s_scale = s_bias + 256;
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  const uint32_t bar_full = smem_u32(bars);              // [S]  used on the leader
+  const uint32_t bar_empty = bar_full + 8 * S;           // [S]  both CTAs (multicast commit)
+  const uint32_t bar_tmem_full = bar_empty + 8 * S;      // [2]  both CTAs (multicast commit)
+  const uint32_t bar_tmem_empty = bar_tmem_full + 16;    // [2]  used on the leader: 16 epilogue warps arrive
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int n_tiles_n = (p.Cout + BN - 1) / BN;
+  const int n_tiles_m = (p.M + TILE_M - 1) / TILE_M;
+  const int total_tiles = n_tiles_n * n_tiles_m;
+  const uint32_t acc_cols = (uint32_t)BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tmem_full + 8 * b, 1);
+      mbar_init(bar_tmem_empty + 8 * b, 16);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_kb = p.num_kb;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; all loads signal the leader's full barrier) =====================
+    uint32_t s = 0, ph = 0;
+    for (int t = pair_id; t < total_tiles; t += npairs) {
+      const int n0 = (t % n_tiles_n) * BN + (int)rank * (BN / 2);
+      const int mt0 = (t / n_tiles_n) * TILE_M;
+      int r = mt0 + (int)rank * kBlockM;
+      const bool live = r < p.M;
+      const bool peer_live = mt0 + kBlockM < p.M;
+      const uint32_t tile_tx = 2u * b_stage_bytes + a_stage_bytes + (peer_live ? a_stage_bytes : 0u);  // leader's expectation
+      const int q = r % p.OW; r /= p.OW;
+      const int pp = r % p.OH; r /= p.OH;
+      const int z = r % p.OD;
+      const int cn = r / p.OD;
+      const int cw = q * p.sW - p.pW, chh = pp * p.sH - p.pH, cd = z * p.sD - p.pD;
+      int cb = 0, kx = 0, ky = 0, kz = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, tile_tx);
+          tma_load_2d_2sm(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
+          if (live) {
+            const uint32_t dst = sA + s * a_stage_bytes;
+            if (p.nsp == 3)
+              tma_im2col_5d_2sm(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, cd, cn, (uint16_t)kx, (uint16_t)ky,
+                                (uint16_t)kz);
+            else
+              tma_im2col_4d_2sm(dst, &tmA, bar_full + 8 * s, cb * kBlockK, cw, chh, cn, (uint16_t)kx, (uint16_t)ky);
+          }
+        }
+        if (++cb == p.cblocks) {
+          cb = 0;
+          if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++kz; } }
+        }
+        if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: leader CTA only =====================
+    if (leader) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      const uint32_t tail_k = (uint32_t)(((p.Cin & (kBlockK - 1)) + kUmmaK - 1) / kUmmaK);
+      const uint64_t adesc0 = make_sw128_desc(sA), bdesc0 = make_sw128_desc(sB);
+      const uint32_t a_step = a_stage_bytes >> 4, b_step = b_stage_bytes >> 4;
+      uint32_t s = 0, ph = 0, tile_iter = 0;
+      for (int t = pair_id; t < total_tiles; t += npairs, ++tile_iter) {
+        const uint32_t buf = tile_iter & 1u;
+        const uint32_t use = tile_iter >> 1;
+        mbar_wait(bar_tmem_empty + 8 * buf, (use & 1u) ^ 1u, p.error_flag, 5);  // both CTAs drained this buffer
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * acc_cols;
+        uint32_t cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph, p.error_flag, 2);
+          tc_fence_after();
+          uint32_t ks = 4;
+          if (tail_k) {
+            if (++cb == (uint32_t)p.cblocks) { cb = 0; ks = tail_k; }
+          }
+          if (elect_one())
+            mma_kblock_pair(acc, adesc0 + (uint64_t)(s * a_step), bdesc0 + (uint64_t)(s * b_step), (uint32_t)(kb != 0), ks,
+                            idesc, bar_empty + 8 * s);
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+        }
+        if (elect_one()) umma_commit_pair(bar_tmem_full + 8 * buf);
+      }
+    }
+  } else {
+    // ===================== epilogue warps (8 per CTA): this CTA's 128 rows x all block_n columns =====================
+    const int wq = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int chunks = BN >> 4;
+    const bool simple = (p.res == nullptr) && (p.raw == nullptr) && (p.out != nullptr);
+    uint32_t tile_iter = 0;
+    int loaded_n0 = -1;
+    for (int t = pair_id; t < total_tiles; t += npairs, ++tile_iter) {
+      const int n0 = (t % n_tiles_n) * BN;
+      const int m0 = (t / n_tiles_n) * TILE_M + (int)rank * kBlockM;
+      if (n0 != loaded_n0) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = threadIdx.x - 64; i < BN; i += 256) {
+          const int c = n0 + i;
+          const bool ok = c < p.Cout;
+          const float bi = (ok && p.bias) ? p.bias[c] : 0.f;
+          const float sc = (ok && p.scale) ? p.scale[c] : 1.f;
+          const float sh = (ok && p.scale) ? p.shift[c] : 0.f;
+          s_bias[i] = bi;
+          s_scale[i] = sc;
+          s_shift[i] = simple ? fmaf(bi, sc, sh) : sh;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        loaded_n0 = n0;
+      }
+      const uint32_t buf = tile_iter & 1u;
+      const uint32_t use = tile_iter >> 1;
+      mbar_wait(bar_tmem_full + 8 * buf, use & 1u, p.error_flag, 4);
+      tc_fence_after();
+      const int m = m0 + wq * 32 + lane;
+      const bool row_ok = m < p.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols;
+      const int c_begin = half ? (chunks + 1) / 2 : 0;
+      const int c_end = half ? chunks : (chunks + 1) / 2;
+      for (int c = c_begin; c < c_end; ++c)
+        epilogue_chunk(p, taddr + (uint32_t)(c * 16), m, row_ok, n0 + c * 16, c * 16, s_bias, s_scale, s_shift, simple, 0u);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on_cta(bar_tmem_empty + 8 * buf, 0u);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's shared memory / TMEM must outlive every MMA that reads it
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Halo-resident 2-D convolution, stride 1 (3x3 / 4x4 / ... filters).
 //   tile   = R output rows x OW columns of one image, enumerated on the padded-width grid
 //            (position i = r*pw + c, pw = OW + KW - 1; columns c >= OW are discarded in the epilogue),
@@ -1534,6 +1786,8 @@ cudaError_t conv_umma_configure() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_umma_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1571,6 +1825,15 @@ cudaError_t launch_conv_halo(const HaloKernelParams& p, int m_halves, const CUte
   const size_t smem = halo_smem_bytes(p);
   if (m_halves == 2) conv_halo_kernel<2><<<grid, kHaloThreads, smem, stream>>>(p, tmX, tmB);
   else conv_halo_kernel<1><<<grid, kHaloThreads, smem, stream>>>(p, tmX, tmB);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_pair(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmBhalf,
+                             cudaStream_t stream) {
+  const size_t smem = 1024 + (size_t)p.stages * (kBlockM * 128 + (size_t)(p.block_n / 2) * 128) + 3 * 256 * sizeof(float) + 64 * 8;
+  const int tiles = ((p.M + 2 * kBlockM - 1) / (2 * kBlockM)) * ((p.Cout + p.block_n - 1) / p.block_n);
+  const int pairs = tiles < p.num_sms / 2 ? tiles : p.num_sms / 2;
+  conv_umma_pair_kernel<<<2 * pairs, kPersistThreads, smem, stream>>>(p, tmA, tmBhalf);  // __cluster_dims__(2,1,1)
   return cudaGetLastError();
 }
 

@@ -151,6 +151,9 @@ inline size_t conv_smem_bytes(int block_n, int stages, int m_halves = 1, size_t 
 
 cudaError_t launch_conv_umma(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                              cudaStream_t stream);
+// CTA-pair (cta_group::2) variant: p.stages / p.tmem_cols sized for it, tmBhalf has box rows = block_n / 2
+cudaError_t launch_conv_pair(const ConvKernelParams& p, const CUtensorMap& tmA, const CUtensorMap& tmBhalf,
+                             cudaStream_t stream);
 cudaError_t conv_umma_configure();  // sets max dynamic smem attribute once
 
 }  // namespace eco

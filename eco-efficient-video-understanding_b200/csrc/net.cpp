@@ -531,6 +531,7 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "stem_rows") stem_rows_ = v;
   else if (key == "pool_commute") pool_commute_ = v;
   else if (key == "stem_direct") stem_direct_ = v;
+  else if (key == "pair") pair_ = v;
   else if (key == "fuse_1x1") fuse_1x1_ = v;
   else if (key == "debug_flags") debug_flags_ = v;
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
@@ -1618,6 +1619,14 @@ void Net::plan() {
           }
           kp.block_n = best;
         }
+        // CTA-pair kernel (cta_group::2, 256-row tiles on two SMs, each CTA loads half of the weight tile).
+        // Measured (profiles/r01l): a cta_group::2 MMA has an issue interval of ~150-165 cycles whatever N, so the
+        // pair only pays for 256-wide tiles (res4: -6..15 %) and loses for N <= 192; auto mode uses it there only.
+        c.pair = false;
+        if (pair_ && persistent_ && !c.stem && (a_mode_ < 0 || a_mode_ == A_TMA_IM2COL)) {
+          const long long t256 = ((long long)kp.M + 2 * kBlockM - 1) / (2 * kBlockM) * ((c.Cout + kp.block_n - 1) / kp.block_n);
+          if (pair_ == 2 || (kp.block_n == 256 && t256 >= 2LL * (g_num_sms / 2))) c.pair = true;
+        }
         c.Cout_pad = round_up(c.Cout, kp.block_n);
         kp.a_mode = a_mode_ < 0 ? A_TMA_IM2COL : a_mode_;
         kp.num_sms = g_num_sms;
@@ -1706,6 +1715,24 @@ void Net::plan() {
         c.flops = 2.0 * kp.M * c.Cout * taps * c.Cin;
         c.bytes = 2.0 * ((double)c.NB * c.I[0] * c.I[1] * c.I[2] * c.Cin + (double)kp.M * c.Cout + (double)c.Cout * taps * c.Cin);
         if (c.rows) plan_stem_rows(c);
+        if (c.pair && (kp.a_mode != A_TMA_IM2COL || !kp.persistent)) c.pair = false;
+        if (c.pair) {
+          static EncodeTiledFn enc_tiled = (EncodeTiledFn)driver_fn("cuTensorMapEncodeTiled");
+          c.kpp = kp;
+          c.kpp.m_halves = 1;
+          const size_t stage = (size_t)kBlockM * 128 + (size_t)(kp.block_n / 2) * 128;
+          const size_t avail = (size_t)227 * 1024 - 1024 - 3 * 1024 - 512;
+          c.kpp.stages = (int)std::max<size_t>(2, std::min<size_t>(8, avail / stage));
+          c.kpp.tmem_cols = pow2_at_least(2 * kp.block_n);
+          cuuint64_t dims[2] = {(cuuint64_t)c.Ktotal, (cuuint64_t)c.Cout_pad};
+          cuuint64_t strides[1] = {(cuuint64_t)c.Ktotal * 2};
+          cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(kp.block_n / 2)};
+          cuuint32_t es[2] = {1, 1};
+          CUresult r = enc_tiled(&c.tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.w_dev, dims, strides, box, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r != CUDA_SUCCESS) c.pair = false;
+        }
         op.flops = c.flops;
         op.bytes = c.bytes;
         op.launches = 1 + ((c.stem_in && !c.direct_in) ? 1 : 0);
@@ -2106,6 +2133,7 @@ void Net::run_op(Op& op, bool with_xform) {
       if (c.stem_in && with_xform) run_input_xform(c, nullptr);
       if (c.direct_in) {}  // launched by run_input_xform (outside the CUDA graph: its source pointer changes per call)
       else if (c.rows) CUDA_OK(launch_stem_rows(c.rp, c.tmX, c.tmB, stream_));
+      else if (c.pair) CUDA_OK(launch_conv_pair(c.kpp, c.tmA, c.tmBh, stream_));
       else if (c.halo) CUDA_OK(launch_conv_halo(c.hp, c.halo_mt, c.tmX, c.tmB, stream_));
       else CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.tmB, stream_));
       if (c.pool_tensor >= 0) mark_written(c.pool_tensor);

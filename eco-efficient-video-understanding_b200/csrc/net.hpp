@@ -139,6 +139,9 @@ struct ConvOp {
   int halo_mt = 1;
   HaloKernelParams hp{};
   CUtensorMap tmX{};
+  bool pair = false;          // CTA-pair (cta_group::2) kernel
+  ConvKernelParams kpp{};     //   its parameters (stages / TMEM sized for half weight tiles)
+  CUtensorMap tmBh{};         //   weight map with box rows = block_n / 2
   bool direct_in = false;     // rows kernel reads the fp32 / uint8 frames itself (no transform kernel, no cell buffer)
   bool rows = false;          // stem rows kernel (sliding window over cell rows, optional fused pool1)
   int pool_layer = -1;        // Pooling layer folded into the rows kernel
@@ -225,6 +228,7 @@ class Net {
   int dual_m_ = 1;
   int halo_ = 0;  // 0 off (default: measured slower, profiles/r01h), 1 auto (resident weights only), 2 force two halves, 3 allow streamed weights
   int fuse_1x1_ = 1;  // 1: 1x1 convolutions reading the same tensor run as one GEMM with segmented output (fast plan only)
+  int pair_ = 1;  // CTA-pair (cta_group::2) kernel: 0 off, 1 for 256-wide tiles with >= 2 tiles per SM pair, 2 wherever possible
   int stem_direct_ = 1;  // 1: the stem rows kernel gathers its windows from the raw frames (frame width % 16 == 0)
   int pool_commute_ = 1;  // 1: AVE 3x3/s1 pooling -> 1x1 conv (+BN+ReLU) runs as conv -> pooling(+bias+BN+ReLU) when nothing else reads the pooled blob
   int stem_rows_ = 1;  // 0: stem as 4x1 im2col GEMM; 1: rows kernel, pool1 folded in when its input has no other reader; 2: rows kernel, never fold the pool

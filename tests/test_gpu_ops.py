@@ -146,6 +146,26 @@ def test_conv2d_dual_m_tiles(gpu, case):
     run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 1, check=("a_bn", "c", "c_bn"), dual_m=2)
 
 
+@pytest.mark.parametrize("case", [CONV2D[0], CONV2D[1], CONV2D[3], CONV2D[5]], ids=["c0", "c1", "c3", "c5"])
+def test_conv2d_cta_pair_kernel(gpu, case):
+    # cta_group::2: two CTAs of a cluster share one 256-row tile, each loads half of the weight tile (forced; the
+    # cost model only picks it for layers with at least a tile per SM pair)
+    shape, cmid, cout, k, s, p = case
+    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 1, check=("a_bn", "c", "c_bn"), pair=2)
+
+
+@pytest.mark.parametrize("case", CONV3D, ids=["d%d" % i for i in range(len(CONV3D))])
+def test_conv3d_cta_pair_kernel(gpu, case):
+    shape, cmid, cout, k, s, p = case
+    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 1, check=("a_bn", "c", "c_bn"), pair=2)
+
+
+def test_cta_pair_residual_and_many_tiles(gpu):
+    run_case(RES_NET, (2, 8, 4, 6, 6), 1, check=("ra", "ra_bn", "rb_bn", "rc_bn", "fc"), pair=2)
+    shape = (8, 8, 8, 14, 14)  # more 256-row tiles than SM pairs, two N tiles: both TMEM buffers, ring wrap
+    run_case(two_conv_net(shape, 128, 512, [3, 3, 3], [1, 1, 1], [1, 1, 1]), shape, 1, check=("c", "c_bn"), pair=2)
+
+
 def test_conv3d_dual_m_residual(gpu):
     run_case(RES_NET, (2, 8, 4, 6, 6), 1, check=("ra", "ra_bn", "rb_bn", "rc_bn", "fc"), dual_m=2)
 
