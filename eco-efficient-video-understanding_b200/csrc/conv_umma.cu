@@ -743,7 +743,9 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
         int cb = 0, kx = 0, ky = 0, kz = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
-          if (elect_one()) {
+          if (p.debug_flags & 8) {  // development: no TMA traffic at all, the MMAs read whatever the stage holds
+            if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(bar_full + 8 * s, tile_tx);
             tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
 #pragma unroll

@@ -46,7 +46,7 @@ struct ConvKernelParams {
   int persistent;                    // 1: conv_umma_persistent_kernel (needs a_mode == A_TMA_IM2COL)
   int m_halves;                      // persistent only: 1 or 2 128-row halves per tile sharing the weight tile
   int epi_group;                     // persistent only: 16-column chunks staged per copy-out (2 or 4)
-  int debug_flags;                   // development only: 1 = skip global stores, 2 = skip TMEM loads, 4 = skip MMAs
+  int debug_flags;                   // development only: 1 = skip global stores, 2 = skip TMEM loads, 4 = skip MMAs, 8 = skip TMA loads
   int epi_staged;                    // persistent only: 1 = row-contiguous copy-out through smem, 0 = direct 32-byte stores
   int num_sms;
   // ---- epilogue:  raw = acc + bias (+ res);  y = relu?(raw * scale + shift) ----
