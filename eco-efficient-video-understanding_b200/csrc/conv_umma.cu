@@ -189,11 +189,70 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// weight-tile half, multicast to both CTAs of a cluster pair (lands at the same offset in each, signals the mbarrier
+// at the same offset in each)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+
 // One K block of the main loop (call from the elected lane): up to 4 K steps into accumulator 0 and, if `live1`,
 // into accumulator 1 (second 128-row half sharing the weight tile), then tcgen05.commit -> `empty_bar`.
+template <bool MC = false>  // MC: the commit frees the stage in BOTH CTAs of the cluster pair (multicast weight tiles)
 __device__ __forceinline__ void mma_kblock(uint32_t acc0, uint32_t acc1, uint64_t ad0, uint64_t ad1, uint64_t bd,
                                            uint32_t accflag, uint32_t ks, uint32_t live1, uint32_t idesc,
                                            uint32_t empty_bar) {
+  if (MC) {
+    asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, ptrue, g1, g2, g3, h0, h1, h2, h3;\n\t"
+      ".reg .b64 a, b;\n\t"
+      ".reg .b16 m;\n\t"
+      "setp.ne.b32 pacc, %5, 0;\n\t"
+      "setp.eq.u32 ptrue, %8, %8;\n\t"
+      "setp.gt.u32 g1, %6, 1;\n\t"
+      "setp.gt.u32 g2, %6, 2;\n\t"
+      "setp.gt.u32 g3, %6, 3;\n\t"
+      "setp.ne.b32 h0, %7, 0;\n\t"
+      "and.pred h1, h0, g1;\n\t"
+      "and.pred h2, h0, g2;\n\t"
+      "and.pred h3, h0, g3;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %4, %8, pacc;\n\t"
+      "add.s64 a, %2, 2;\n\t"
+      "add.s64 b, %4, 2;\n\t"
+      "@g1 tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %8, ptrue;\n\t"
+      "add.s64 a, %2, 4;\n\t"
+      "add.s64 b, %4, 4;\n\t"
+      "@g2 tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %8, ptrue;\n\t"
+      "add.s64 a, %2, 6;\n\t"
+      "add.s64 b, %4, 6;\n\t"
+      "@g3 tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %8, ptrue;\n\t"
+      "@h0 tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %8, pacc;\n\t"
+      "add.s64 a, %3, 2;\n\t"
+      "add.s64 b, %4, 2;\n\t"
+      "@h1 tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %8, ptrue;\n\t"
+      "add.s64 a, %3, 4;\n\t"
+      "add.s64 b, %4, 4;\n\t"
+      "@h2 tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %8, ptrue;\n\t"
+      "add.s64 a, %3, 6;\n\t"
+      "add.s64 b, %4, 6;\n\t"
+      "@h3 tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %8, ptrue;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%9], m;\n\t"
+      "}"
+      ::"r"(acc0), "r"(acc1), "l"(ad0), "l"(ad1), "l"(bd), "r"(accflag), "r"(ks), "r"(live1), "r"(idesc), "r"(empty_bar)
+      : "memory");
+    return;
+  }
   asm volatile(
       "{\n\t"
       ".reg .pred pacc, ptrue, g1, g2, g3, h0, h1, h2, h3;\n\t"
@@ -660,7 +719,11 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32
                : "memory");
 }
 
-template <int MT>
+// MC = true: launched as clusters of 2 CTAs that work on two different M tiles of the SAME N tile; each CTA loads half
+// of the weight tile and multicasts it into both shared memories (tmB then has box rows = block_n / 2), which
+// removes a quarter to a third of the L2->SM bytes -- the co-limiter next to the UMMA operand reads
+// (profiles/r01m: with the MMAs switched off the layers take the same time, 15-17.5 TB/s of TMA traffic).
+template <int MT, bool MC>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CUtensorMap tmA,
                             const __grid_constant__ CUtensorMap tmB) {
@@ -694,13 +757,20 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   const int lane = threadIdx.x & 31;
   const int n_tiles_n = (p.Cout + BN - 1) / BN;
   const int n_tiles_m = (p.M + TILE_M - 1) / TILE_M;
-  const int total_tiles = n_tiles_n * n_tiles_m;
   const uint32_t acc_cols = (uint32_t)(MT * BN);  // TMEM columns of one accumulator buffer
+  // work list: plain = tile t -> (m tile t / n_tiles_n, n tile t % n_tiles_n), CTA b takes t = b, b + grid, ...;
+  // MC = cluster c takes "super tiles" u = c, c + clusters, ...: n tile u % n_tiles_n, m tiles 2 (u / n_tiles_n) + rank
+  // (an odd last m tile leaves rank 1 with a dead tile: it still loads and multicasts its weight half)
+  const uint32_t rank = MC ? cluster_ctarank() : 0u;
+  const int total_tiles = MC ? n_tiles_n * ((n_tiles_m + 1) / 2) : n_tiles_n * n_tiles_m;
+  const int t_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_m_index = [&](int t) { return MC ? 2 * (t / n_tiles_n) + (int)rank : t / n_tiles_n; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, MC ? 2 : 1);  // MC: both CTAs of the pair must have released the stage
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tmem_full + 8 * b, 1);
@@ -715,7 +785,8 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (MC) cluster_sync_all();  // the peer multicasts into this CTA's shared memory and barriers
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_kb = p.num_kb;
@@ -724,14 +795,14 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
     // ===================== TMA producer (whole warp walks the ring, one elected lane issues) =====================
     {
       uint32_t s = 0, ph = 0;  // ring position, running across tiles (no division in the per-block loop)
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_step) {
         const int n0 = (t % n_tiles_n) * BN;
         int cw[MT], chh[MT], cd[MT], cn[MT];
         bool live[MT];  // a half that starts beyond the last output position is never loaded
         uint32_t tile_tx = b_stage_bytes;
 #pragma unroll
         for (int h = 0; h < MT; ++h) {
-          int r = (t / n_tiles_n) * TILE_M + h * kBlockM;
+          int r = tile_m_index(t) * TILE_M + h * kBlockM;
           live[h] = r < p.M;
           if (live[h]) tile_tx += a_half_bytes;
           const int q = r % p.OW; r /= p.OW;
@@ -747,7 +818,11 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
             if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
           } else if (elect_one()) {
             mbar_arrive_expect_tx(bar_full + 8 * s, tile_tx);
-            tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
+            if (MC)
+              tma_load_2d_mc(sB + s * b_stage_bytes + rank * (b_stage_bytes >> 1), &tmB, bar_full + 8 * s, kb * kBlockK,
+                             n0 + (int)rank * (BN >> 1), (uint16_t)3);
+            else
+              tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_full + 8 * s, kb * kBlockK, n0);
 #pragma unroll
             for (int h = 0; h < MT; ++h) {
               if (!live[h]) continue;
@@ -776,14 +851,14 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
       const uint64_t adesc0 = make_sw128_desc(sA), bdesc0 = make_sw128_desc(sB);
       const uint32_t a_step = a_stage_bytes >> 4, b_step = b_stage_bytes >> 4, a_half_step = a_half_bytes >> 4;
       uint32_t s = 0, ph = 0, tile_iter = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+      for (int t = t_first; t < total_tiles; t += t_step, ++tile_iter) {
         const uint32_t buf = tile_iter & 1u;
         const uint32_t use = tile_iter >> 1;
         mbar_wait(bar_tmem_empty + 8 * buf, (use & 1u) ^ 1u, p.error_flag, 5);  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * acc_cols;
         // second 128-row half of the tile: dead when it starts beyond the last output position
-        const uint32_t live1 = (MT == 2 && (t / n_tiles_n) * TILE_M + kBlockM < p.M) ? 1u : 0u;
+        const uint32_t live1 = (MT == 2 && tile_m_index(t) * TILE_M + kBlockM < p.M) ? 1u : 0u;
         uint32_t cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full + 8 * s, ph, p.error_flag, 2);
@@ -794,8 +869,8 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
           }
           if (elect_one()) {
             const uint64_t ad = adesc0 + (uint64_t)(s * a_step);
-            mma_kblock(acc, acc + (uint32_t)BN, ad, ad + a_half_step, bdesc0 + (uint64_t)(s * b_step), (uint32_t)(kb != 0), ks,
-                       live1, idesc, bar_empty + 8 * s);
+            mma_kblock<MC>(acc, acc + (uint32_t)BN, ad, ad + a_half_step, bdesc0 + (uint64_t)(s * b_step), (uint32_t)(kb != 0), ks,
+                           live1, idesc, bar_empty + 8 * s);
           }
           if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
@@ -810,9 +885,9 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
     const bool simple = (p.res == nullptr) && (p.raw == nullptr) && (p.out != nullptr);
     uint32_t tile_iter = 0;
     int loaded_n0 = -1;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+    for (int t = t_first; t < total_tiles; t += t_step, ++tile_iter) {
       const int n0 = (t % n_tiles_n) * BN;
-      const int m0 = (t / n_tiles_n) * TILE_M;
+      const int m0 = tile_m_index(t) * TILE_M;
       if (n0 != loaded_n0) {  // uniform across the eight epilogue warps
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int i = threadIdx.x - 64; i < BN; i += 256) {
@@ -880,7 +955,8 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (MC) cluster_sync_all();  // no multicast write or commit may still be in flight towards an exited CTA
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                  : "memory");
@@ -900,14 +976,6 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
 //   by multicast tcgen05.commit, tmem_empty[b] lives on the leader and collects 16 epilogue-warp arrivals.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address -> same offset in CTA rank 0 of the pair
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive_on_cta(uint32_t local_bar, uint32_t cta) {
   asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
                "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_bar), "r"(cta) : "memory");
@@ -1202,8 +1270,8 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
 
   if (warp == 0) {
     // ===================== TMA producer: input patches (+ the resident weights, once) =====================
-    if (lane == 0) {
-      if (p.b_resident) {
+    {
+      if (p.b_resident && elect_one()) {
         // b_full[0] doubles as the "weights resident" barrier: armed once, completes once
         mbar_arrive_expect_tx(bar_b_full, (uint32_t)p.b_kblocks * b_stage_bytes);
         for (int kbk = 0; kbk < p.b_kblocks; ++kbk)
@@ -1217,19 +1285,21 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
         for (int cb = 0; cb < p.cblocks; ++cb, ++ia) {
           const uint32_t s = ia % (uint32_t)SA, ph = (ia / (uint32_t)SA) & 1u;
           mbar_wait(bar_a_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
-          mbar_arrive_expect_tx(bar_a_full + 8 * s, p.a_tx_bytes);
-          asm volatile(
-              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-              ::"r"(sA + s * p.a_stage_bytes), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_a_full + 8 * s),
-              "r"(cb * kBlockK), "r"(-p.pW), "r"(y0 - p.pH), "r"(n)
-              : "memory");
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_a_full + 8 * s, p.a_tx_bytes);
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(sA + s * p.a_stage_bytes), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_a_full + 8 * s),
+                "r"(cb * kBlockK), "r"(-p.pW), "r"(y0 - p.pH), "r"(n)
+                : "memory");
+          }
         }
       }
     }
   } else if (warp >= 10) {
     // ===================== TMA producers: weight tiles, two threads interleaved =====================
     const uint32_t me = (uint32_t)(warp - 10);
-    if (lane == 0 && !p.b_resident) {
+    if (!p.b_resident) {
       uint32_t ib = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n0 = (t % n_tiles_n) * BN;
@@ -1238,15 +1308,17 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
             if ((ib & 1u) != me) continue;
             const uint32_t s = ib % (uint32_t)SB, ph = (ib / (uint32_t)SB) & 1u;
             mbar_wait(bar_b_empty + 8 * s, ph ^ 1u, p.error_flag, 6);
-            mbar_arrive_expect_tx(bar_b_full + 8 * s, b_stage_bytes);
-            tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_b_full + 8 * s, (tap * p.cblocks + cb) * kBlockK, n0);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar_b_full + 8 * s, b_stage_bytes);
+              tma_load_2d(sB + s * b_stage_bytes, &tmB, bar_b_full + 8 * s, (tap * p.cblocks + cb) * kBlockK, n0);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp walks the rings, one elected lane issues) =====================
+    {
       const uint32_t idesc = make_idesc(BN);
       const uint32_t rb = (uint32_t)p.row_bytes;
       const bool sw32 = p.row_bytes == 32;
@@ -1284,22 +1356,24 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
               btile = sB + sb * b_stage_bytes;
               ++ib;
             }
-            const uint64_t bdesc = make_sw128_desc(btile) + (uint64_t)((bk_elem % kBlockK) * 2 / 16);
-            const uint32_t a0 = patch + (uint32_t)(ky * p.pw + kx) * rb;  // tap = row shift of the patch
+            if (elect_one()) {
+              const uint64_t bdesc = make_sw128_desc(btile) + (uint64_t)((bk_elem % kBlockK) * 2 / 16);
+              const uint32_t a0 = patch + (uint32_t)(ky * p.pw + kx) * rb;  // tap = row shift of the patch
 #pragma unroll
-            for (int h = 0; h < MT; ++h) {
-              const uint32_t ah = a0 + (uint32_t)h * (kBlockM * rb);
-              const uint64_t adesc = sw32 ? make_sw32_desc(ah) : make_sw128_desc(ah);
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(acc + (uint32_t)(h * BN), adesc + 2 * k, bdesc + 2 * k, idesc, first ? (uint32_t)(k != 0) : 1u);
+              for (int h = 0; h < MT; ++h) {
+                const uint32_t ah = a0 + (uint32_t)h * (kBlockM * rb);
+                const uint64_t adesc = sw32 ? make_sw32_desc(ah) : make_sw128_desc(ah);
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16(acc + (uint32_t)(h * BN), adesc + 2 * k, bdesc + 2 * k, idesc, first ? (uint32_t)(k != 0) : 1u);
+              }
+              if (!p.b_resident) umma_commit(bar_b_empty + 8 * sb);
             }
             first = 0;
-            if (!p.b_resident) umma_commit(bar_b_empty + 8 * sb);
             if (++kx == p.KW) { kx = 0; ++ky; }
           }
-          umma_commit(bar_a_empty + 8 * sa);
+          if (elect_one()) umma_commit(bar_a_empty + 8 * sa);
         }
-        umma_commit(bar_tmem_full + 8 * buf);
+        if (elect_one()) umma_commit(bar_tmem_full + 8 * buf);
       }
     }
   } else {
@@ -1784,9 +1858,13 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
 }  // namespace
 
 cudaError_t conv_umma_configure() {
-  cudaError_t e = cudaFuncSetAttribute(conv_umma_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_persistent_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_umma_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(conv_umma_persistent_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_umma_persistent_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_umma_persistent_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
@@ -1847,10 +1925,27 @@ cudaError_t launch_conv_umma(const ConvKernelParams& p, const CUtensorMap& tmA, 
     const int tile_m = kBlockM * p.m_halves;
     const int tiles = ((p.M + tile_m - 1) / tile_m) * ((p.Cout + p.block_n - 1) / p.block_n);
     const int grid = tiles < p.num_sms ? tiles : p.num_sms;
+    if (p.multicast) {
+      // clusters of two CTAs (launch attribute): tmB must be the half-tile map (box rows = block_n / 2)
+      const int supers = ((((p.M + tile_m - 1) / tile_m) + 1) / 2) * ((p.Cout + p.block_n - 1) / p.block_n);
+      const int clusters = supers < p.num_sms / 2 ? supers : p.num_sms / 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * clusters, 1, 1);
+      cfg.blockDim = dim3(kPersistThreads, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (p.m_halves == 2) return cudaLaunchKernelEx(&cfg, conv_umma_persistent_kernel<2, true>, p, tmA, tmB);
+      return cudaLaunchKernelEx(&cfg, conv_umma_persistent_kernel<1, true>, p, tmA, tmB);
+    }
     if (p.m_halves == 2)
-      conv_umma_persistent_kernel<2><<<grid, kPersistThreads, smem, stream>>>(p, tmA, tmB);
+      conv_umma_persistent_kernel<2, false><<<grid, kPersistThreads, smem, stream>>>(p, tmA, tmB);
     else
-      conv_umma_persistent_kernel<1><<<grid, kPersistThreads, smem, stream>>>(p, tmA, tmB);
+      conv_umma_persistent_kernel<1, false><<<grid, kPersistThreads, smem, stream>>>(p, tmA, tmB);
     return cudaGetLastError();
   }
   dim3 grid((p.M + kBlockM - 1) / kBlockM, (p.Cout + p.block_n - 1) / p.block_n, 1);

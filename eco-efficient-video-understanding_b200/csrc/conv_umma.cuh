@@ -49,6 +49,7 @@ struct ConvKernelParams {
   int debug_flags;                   // development only: 1 = skip global stores, 2 = skip TMEM loads, 4 = skip MMAs, 8 = skip TMA loads
   int epi_staged;                    // persistent only: 1 = row-contiguous copy-out through smem, 0 = direct 32-byte stores
   int num_sms;
+  int multicast;                     // persistent only: clusters of 2 CTAs share each weight tile (TMA multicast of halves)
   // ---- epilogue:  raw = acc + bias (+ res);  y = relu?(raw * scale + shift) ----
   int Cout;
   const float* bias;                 // [Cout] or null

@@ -532,6 +532,7 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "pool_commute") pool_commute_ = v;
   else if (key == "stem_direct") stem_direct_ = v;
   else if (key == "pair") pair_ = v;
+  else if (key == "multicast") multicast_ = v;
   else if (key == "fuse_1x1") fuse_1x1_ = v;
   else if (key == "debug_flags") debug_flags_ = v;
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
@@ -1716,9 +1717,16 @@ void Net::plan() {
         c.bytes = 2.0 * ((double)c.NB * c.I[0] * c.I[1] * c.I[2] * c.Cin + (double)kp.M * c.Cout + (double)c.Cout * taps * c.Cin);
         if (c.rows) plan_stem_rows(c);
         if (c.pair && (kp.a_mode != A_TMA_IM2COL || !kp.persistent)) c.pair = false;
-        if (c.pair) {
+        kp.multicast = 0;
+        if (multicast_ && kp.persistent && !c.pair && !c.rows && !c.halo) {
+          const long long tile_m = (long long)kBlockM * kp.m_halves;
+          const long long tiles = (kp.M + tile_m - 1) / tile_m * ((c.Cout + kp.block_n - 1) / kp.block_n);
+          if (multicast_ == 2 || tiles >= 2LL * g_num_sms) kp.multicast = 1;
+        }
+        if (c.pair || kp.multicast) {
           static EncodeTiledFn enc_tiled = (EncodeTiledFn)driver_fn("cuTensorMapEncodeTiled");
           c.kpp = kp;
+          c.kpp.multicast = 0;
           c.kpp.m_halves = 1;
           const size_t stage = (size_t)kBlockM * 128 + (size_t)(kp.block_n / 2) * 128;
           const size_t avail = (size_t)227 * 1024 - 1024 - 3 * 1024 - 512;
@@ -1731,7 +1739,7 @@ void Net::plan() {
           CUresult r = enc_tiled(&c.tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.w_dev, dims, strides, box, es,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-          if (r != CUDA_SUCCESS) c.pair = false;
+          if (r != CUDA_SUCCESS) { c.pair = false; kp.multicast = 0; }
         }
         op.flops = c.flops;
         op.bytes = c.bytes;
@@ -2135,7 +2143,7 @@ void Net::run_op(Op& op, bool with_xform) {
       else if (c.rows) CUDA_OK(launch_stem_rows(c.rp, c.tmX, c.tmB, stream_));
       else if (c.pair) CUDA_OK(launch_conv_pair(c.kpp, c.tmA, c.tmBh, stream_));
       else if (c.halo) CUDA_OK(launch_conv_halo(c.hp, c.halo_mt, c.tmX, c.tmB, stream_));
-      else CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.tmB, stream_));
+      else CUDA_OK(launch_conv_umma(c.kp, c.tmA, c.kp.multicast ? c.tmBh : c.tmB, stream_));
       if (c.pool_tensor >= 0) mark_written(c.pool_tensor);
       for (const ConvMember& m : c.members) mark_written(m.tensor);
       if (c.out_tensor >= 0) mark_written(c.out_tensor);

@@ -166,6 +166,24 @@ def test_cta_pair_residual_and_many_tiles(gpu):
     run_case(two_conv_net(shape, 128, 512, [3, 3, 3], [1, 1, 1], [1, 1, 1]), shape, 1, check=("c", "c_bn"), pair=2)
 
 
+@pytest.mark.parametrize("dual_m", [1, 2], ids=["mt1", "mt2"])
+@pytest.mark.parametrize("case", [CONV2D[0], CONV2D[1], CONV2D[5], CONV3D[0], CONV3D[2], CONV3D[3]],
+                         ids=["c0", "c1", "c5", "d0", "d2", "d3"])
+def test_conv_multicast_clusters(gpu, case, dual_m):
+    # persistent kernel in clusters of two CTAs: different M tiles of the same N tile, each CTA loads half of the
+    # weight tile and multicasts it into both shared memories (forced; auto needs >= 2 tiles per SM).  Odd tile
+    # counts leave one CTA of the last cluster with a dead tile that still feeds its weight half to the peer.
+    shape, cmid, cout, k, s, p = case
+    run_case(two_conv_net(shape, cmid, cout, k, s, p), shape, 1, check=("a_bn", "c", "c_bn"), multicast=2, dual_m=dual_m, pair=0)
+
+
+def test_multicast_clusters_residual_and_many_tiles(gpu):
+    run_case(RES_NET, (2, 8, 4, 6, 6), 1, check=("ra", "ra_bn", "rb_bn", "rc_bn", "fc"), multicast=2, pair=0)
+    shape = (8, 8, 8, 14, 14)
+    run_case(two_conv_net(shape, 128, 512, [3, 3, 3], [1, 1, 1], [1, 1, 1]), shape, 1, check=("c", "c_bn"), multicast=2, pair=0)
+    run_case(INCEPTION, (2, 8, 14, 14), 1, check=("b1_bn", "b2_bn", "nx_bn"), keep_all=False, multicast=2, pool_commute=0)
+
+
 def test_conv3d_dual_m_residual(gpu):
     run_case(RES_NET, (2, 8, 4, 6, 6), 1, check=("ra", "ra_bn", "rb_bn", "rc_bn", "fc"), dual_m=2)
 
