@@ -50,6 +50,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+// (development counters) mbarrier.try_wait may block for a hardware-defined time before it returns, so the probe
+// that decides "did we have to wait" is the non-blocking test_wait
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ long long mbar_wait_timed(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_test_wait(bar, parity)) return 0;
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, err, code);
+  return clock64() - t0;
+}
+
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -653,7 +673,13 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32
                                                int c0, const float* s_bias, const float* s_scale,
                                                const float* s_shift, bool simple, uint32_t stage_dst) {
   uint32_t v[16];
-  tmem_ld16(taddr, v);
+  if (p.debug_flags & 2) {  // development: no TMEM traffic
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0x3f800000u;
+  } else {
+    tmem_ld16(taddr, v);
+  }
+  if (p.debug_flags & 1) row_ok = false;  // development: compute, never store
   const int nvalid = p.Cout - cg;
   float f[16];
   const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
@@ -717,6 +743,67 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, uint32
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_dst + 16), "r"(w4), "r"(w5), "r"(w6), "r"(w7)
                : "memory");
+}
+
+// Out-only epilogue of one 16-column chunk with everything it needs in registers (destination pointer already at
+// this row and column, ReLU flag, valid-column count): y = relu?(acc * scale + shift') -> one 32-byte bf16 store.
+// The generic epilogue_chunk re-reads its parameters (and, for fused sibling 1x1 convolutions, walks the segment
+// table with dynamically indexed constant loads) for EVERY chunk; on the short-K 1x1 layers that made the
+// epilogue the critical path (in-kernel counters: the MMA warp waited 70 % of the time for a free accumulator).
+__device__ __forceinline__ void epilogue_chunk_simple(uint32_t taddr, __nv_bfloat16* dst, int nvalid, bool relu, bool store,
+                                                      const float* sc, const float* sh, int dbg) {
+  uint32_t v[16];
+  if (dbg & 2) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0x3f800000u;
+  } else {
+    tmem_ld16(taddr, v);
+  }
+  float f[16];
+  const float4* sc4 = reinterpret_cast<const float4*>(sc);
+  const float4* sh4 = reinterpret_cast<const float4*>(sh);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 a = sc4[j], b = sh4[j];
+    f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), a.x, b.x);
+    f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y);
+    f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z);
+    f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w);
+  }
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (store && nvalid > 0) store16_bf16(dst, f, nvalid);
+}
+
+// This warp's chunk range [c_begin, c_end) of one 128-row accumulator, out-only epilogue, one or several output segments
+__device__ __forceinline__ void epilogue_simple_range(const ConvKernelParams& p, uint32_t taddr, long long m, bool row_ok,
+                                                      int n0, int c_begin, int c_end, const float* s_scale,
+                                                      const float* s_shift) {
+  const int dbg = p.debug_flags;
+  const bool store = row_ok && !(dbg & 1);
+  const int cout = p.Cout;
+  if (p.nseg <= 1) {
+    __nv_bfloat16* dst = p.out + m * p.out_cs + p.out_coff + n0;
+    const bool relu = p.relu != 0;
+    for (int c = c_begin; c < c_end; ++c)
+      epilogue_chunk_simple(taddr + (uint32_t)(c * 16), dst + c * 16, cout - (n0 + c * 16), relu, store, s_scale + c * 16,
+                            s_shift + c * 16, dbg);
+    return;
+  }
+  int seg_lo = 0;
+  for (int sg = 0; sg < p.nseg; ++sg) {
+    const int seg_hi = p.seg_end[sg];
+    const int a = max(c_begin, (seg_lo - n0) >> 4), b = min(c_end, (seg_hi - n0) >> 4);
+    seg_lo = seg_hi;
+    if (a >= b) continue;
+    __nv_bfloat16* dst = p.seg_ptr[sg] + m * p.seg_cs[sg] + p.seg_coff[sg] + n0;
+    const bool relu = p.seg_relu[sg] != 0;
+    for (int c = a; c < b; ++c)
+      epilogue_chunk_simple(taddr + (uint32_t)(c * 16), dst + c * 16, cout - (n0 + c * 16), relu, store, s_scale + c * 16,
+                            s_shift + c * 16, dbg);
+  }
 }
 
 // MC = true: launched as clusters of 2 CTAs that work on two different M tiles of the SAME N tile; each CTA loads half
@@ -790,11 +877,13 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_kb = p.num_kb;
+  const long long t_start = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the ring, one elected lane issues) =====================
     {
       uint32_t s = 0, ph = 0;  // ring position, running across tiles (no division in the per-block loop)
+      long long w_a = 0;
       for (int t = t_first; t < total_tiles; t += t_step) {
         const int n0 = (t % n_tiles_n) * BN;
         int cw[MT], chh[MT], cd[MT], cn[MT];
@@ -813,7 +902,7 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
         }
         int cb = 0, kx = 0, ky = 0, kz = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
+          w_a += mbar_wait_timed(bar_empty + 8 * s, ph ^ 1u, p.error_flag, 1);
           if (p.debug_flags & 8) {  // development: no TMA traffic at all, the MMAs read whatever the stage holds
             if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
           } else if (elect_one()) {
@@ -842,6 +931,8 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
           if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
       }
+      if ((p.debug_flags & 16) && blockIdx.x == 0 && lane == 0)
+        printf("persistent cta0: producer waited %lld cycles (stage free) of %lld\n", w_a, clock64() - t_start);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp walks the ring, one elected lane issues) =====================
@@ -851,17 +942,18 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
       const uint64_t adesc0 = make_sw128_desc(sA), bdesc0 = make_sw128_desc(sB);
       const uint32_t a_step = a_stage_bytes >> 4, b_step = b_stage_bytes >> 4, a_half_step = a_half_bytes >> 4;
       uint32_t s = 0, ph = 0, tile_iter = 0;
+      long long w_a = 0, w_b = 0;
       for (int t = t_first; t < total_tiles; t += t_step, ++tile_iter) {
         const uint32_t buf = tile_iter & 1u;
         const uint32_t use = tile_iter >> 1;
-        mbar_wait(bar_tmem_empty + 8 * buf, (use & 1u) ^ 1u, p.error_flag, 5);  // epilogue drained this buffer
+        w_b += mbar_wait_timed(bar_tmem_empty + 8 * buf, (use & 1u) ^ 1u, p.error_flag, 5);  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * acc_cols;
         // second 128-row half of the tile: dead when it starts beyond the last output position
         const uint32_t live1 = (MT == 2 && tile_m_index(t) * TILE_M + kBlockM < p.M) ? 1u : 0u;
         uint32_t cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(bar_full + 8 * s, ph, p.error_flag, 2);
+          w_a += mbar_wait_timed(bar_full + 8 * s, ph, p.error_flag, 2);
           tc_fence_after();
           uint32_t ks = 4;
           if (tail_k) {
@@ -876,6 +968,9 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
         }
         if (elect_one()) umma_commit(bar_tmem_full + 8 * buf);
       }
+      if ((p.debug_flags & 16) && blockIdx.x == 0 && lane == 0)
+        printf("persistent cta0 [M=%d Cout=%d bn=%d kb=%d MT=%d]: mma waited %lld (stage full) + %lld (accumulator free) cycles of %lld, %u tiles\n",
+               p.M, p.Cout, BN, num_kb, MT, w_a, w_b, clock64() - t_start, tile_iter);
     }
   } else {
     // ===================== epilogue warps (8) =====================
@@ -884,6 +979,7 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
     const int chunks = BN >> 4;
     const bool simple = (p.res == nullptr) && (p.raw == nullptr) && (p.out != nullptr);
     uint32_t tile_iter = 0;
+    long long w_e = 0;
     int loaded_n0 = -1;
     for (int t = t_first; t < total_tiles; t += t_step, ++tile_iter) {
       const int n0 = (t % n_tiles_n) * BN;
@@ -905,7 +1001,7 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
       }
       const uint32_t buf = tile_iter & 1u;
       const uint32_t use = tile_iter >> 1;
-      mbar_wait(bar_tmem_full + 8 * buf, use & 1u, p.error_flag, 4);
+      w_e += mbar_wait_timed(bar_tmem_full + 8 * buf, use & 1u, p.error_flag, 4);
       tc_fence_after();
 #pragma unroll
       for (int h = 0; h < MT; ++h) {
@@ -917,6 +1013,10 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
         const int c_begin = half ? (chunks + 1) / 2 : 0;
         const int c_end = half ? chunks : (chunks + 1) / 2;
         const uint32_t my_stage = stage_base + (uint32_t)(warp - 2) * 32u * stage_pitch;
+        if (simple && !p.epi_staged) {
+          epilogue_simple_range(p, taddr, (long long)m, row_ok, n0, c_begin, c_end, s_scale, s_shift);
+          continue;
+        }
         for (int cgrp = c_begin; cgrp < c_end; cgrp += p.epi_group) {
           const int gcount = min(p.epi_group, c_end - cgrp);
           for (int k = 0; k < gcount; ++k) {
@@ -952,6 +1052,8 @@ conv_umma_persistent_kernel(const ConvKernelParams p, const __grid_constant__ CU
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tmem_empty + 8 * buf) : "memory");
       }
     }
+    if ((p.debug_flags & 16) && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9))
+      printf("persistent cta0 warp %d: epilogue waited %lld cycles (accumulator full) of %lld\n", warp, w_e, clock64() - t_start);
   }
 
   tc_fence_before();
@@ -1192,8 +1294,12 @@ conv_umma_pair_kernel(const ConvKernelParams p, const __grid_constant__ CUtensor
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * acc_cols;
       const int c_begin = half ? (chunks + 1) / 2 : 0;
       const int c_end = half ? chunks : (chunks + 1) / 2;
-      for (int c = c_begin; c < c_end; ++c)
-        epilogue_chunk(p, taddr + (uint32_t)(c * 16), m, row_ok, n0 + c * 16, c * 16, s_bias, s_scale, s_shift, simple, 0u);
+      if (simple && !p.epi_staged) {
+        epilogue_simple_range(p, taddr, (long long)m, row_ok, n0, c_begin, c_end, s_scale, s_shift);
+      } else {
+        for (int c = c_begin; c < c_end; ++c)
+          epilogue_chunk(p, taddr + (uint32_t)(c * 16), m, row_ok, n0 + c * 16, c * 16, s_bias, s_scale, s_shift, simple, 0u);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_on_cta(bar_tmem_empty + 8 * buf, 0u);
@@ -1449,13 +1555,6 @@ constexpr int kStemSlots = 8;  // accumulator ring: 8 x 64 fp32 columns = all 51
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
   const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<const uint32_t*>(&r);
-}
-
-__device__ __forceinline__ long long mbar_wait_timed(uint32_t bar, uint32_t parity, int* err, int code) {
-  if (mbar_try_wait(bar, parity)) return 0;
-  const long long t0 = clock64();
-  mbar_wait(bar, parity, err, code);
-  return clock64() - t0;
 }
 
 template <bool POOL, int SRC>

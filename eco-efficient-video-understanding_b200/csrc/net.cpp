@@ -1626,7 +1626,8 @@ void Net::plan() {
         c.pair = false;
         if (pair_ && persistent_ && !c.stem && (a_mode_ < 0 || a_mode_ == A_TMA_IM2COL)) {
           const long long t256 = ((long long)kp.M + 2 * kBlockM - 1) / (2 * kBlockM) * ((c.Cout + kp.block_n - 1) / kp.block_n);
-          if (pair_ == 2 || (kp.block_n == 256 && t256 >= 2LL * (g_num_sms / 2))) c.pair = true;
+          // (short-K 256-wide GEMMs -- the fused 1x1 groups -- are epilogue-bound and run better on single CTAs)
+          if (pair_ == 2 || (kp.block_n == 256 && kp.num_kb >= 16 && t256 >= 2LL * (g_num_sms / 2))) c.pair = true;
         }
         c.Cout_pad = round_up(c.Cout, kp.block_n);
         kp.a_mode = a_mode_ < 0 ? A_TMA_IM2COL : a_mode_;
