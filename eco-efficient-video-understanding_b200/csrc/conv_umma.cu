@@ -1548,7 +1548,7 @@ conv_halo_kernel(const HaloKernelParams p, const __grid_constant__ CUtensorMap t
 //   warp 0: TMA producer (one cell row per stage), warp 1: MMA issuer -- every resident cell row is
 //   multiplied into the (up to) four accumulators it contributes to, warps 2-9: epilogue.
 constexpr int kStemThreads = 320;        // warp 0 TMA, 1 MMA, 2-9 epilogue
-constexpr int kStemThreadsDirect = 448;  // + warps 10-13: window gather from raw frames (src_mode 1 / 2)
+constexpr int kStemThreadsDirect = 512;  // + warps 10-15 (4..6 used): window gather from raw frames (src_mode 1 / 2)
 constexpr int kStemRawStagesMax = 8;
 constexpr int kStemSlots = 8;  // accumulator ring: 8 x 64 fp32 columns = all 512 TMEM columns
 
@@ -1766,7 +1766,7 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
     // cell (Y, X) = 2x2 pixels x 3 channels (+4 zeros) of the zero-padded frame; window x of the tile = cells
     // x..x+3 = one 128-byte row in the 128B-swizzled K-major layout the MMA descriptors expect
     if constexpr (SRC != 0) {
-      const int gw = warp - 10;
+      const int gw = warp - 10;  // blockDim = 320 + 32 * gather_warps
       const int CW = p.OW + 3;
       const float mean[3] = {p.mean0, p.mean1, p.mean2};
       uint32_t i = 0;
@@ -1774,7 +1774,7 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
         int f, r0, r1, p0;
         unit_rows(u, f, r0, r1, p0);
         for (int Y = r0; Y < r1 + 3; ++Y, ++i) {
-          if ((int)(i & 3u) != gw) continue;
+          if ((int)(i % (uint32_t)p.gather_warps) != gw) continue;
           const uint32_t rs = i % (uint32_t)RS, rph = (i / (uint32_t)RS) & 1u;
           const uint32_t as = i % (uint32_t)SA, aph = (i / (uint32_t)SA) & 1u;
           mbar_wait(bar_raw_full + 8 * rs, rph, p.error_flag, 8);
@@ -1984,7 +1984,7 @@ cudaError_t launch_stem_rows(const StemRowsParams& p, const CUtensorMap& tmX, co
   const int units = p.F * p.strips;
   const int grid = units < p.num_sms ? units : p.num_sms;
   const size_t smem = stem_rows_smem_bytes(p);
-  const int threads = p.src_mode ? kStemThreadsDirect : kStemThreads;
+  const int threads = p.src_mode ? kStemThreads + 32 * p.gather_warps : kStemThreads;
   if (p.pool) {
     if (p.src_mode == 0) stem_rows_kernel<true, 0><<<grid, threads, smem, stream>>>(p, tmX, tmB);
     else if (p.src_mode == 1) stem_rows_kernel<true, 1><<<grid, threads, smem, stream>>>(p, tmX, tmB);

@@ -126,6 +126,7 @@ struct StemRowsParams {
   const void* src;           // frames (src_mode 1 / 2)
   int H, W;                  // frame size
   float mean0, mean1, mean2; // src_mode 2
+  int gather_warps;          // 4..6 warps building the windows (src_mode 1 / 2)
   int raw_stages;            // ring of raw image-row pairs (src_mode 1 / 2)
   uint32_t raw_stage_bytes;  // 6 rows (2 image rows x 3 channels) x W x element size, 128-byte padded
   int debug_flags;           // development: 1 no stores, 2 no TMEM loads, 4 no MMAs, 8 no TMA loads, 16 print role wait cycles (CTA 0)

@@ -531,6 +531,7 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "stem_rows") stem_rows_ = v;
   else if (key == "pool_commute") pool_commute_ = v;
   else if (key == "stem_direct") stem_direct_ = v;
+  else if (key == "stem_gather_warps") stem_gather_warps_ = std::max(1, std::min(6, v));
   else if (key == "pair") pair_ = v;
   else if (key == "multicast") multicast_ = v;
   else if (key == "fuse_1x1") fuse_1x1_ = v;
@@ -846,6 +847,7 @@ void Net::plan_stem_rows(ConvOp& c) {
   r.a_stages = r.pool ? 6 : 8;
   r.a_tx_bytes = (uint32_t)r.OW * 128u;
   r.H = c.I[1]; r.W = c.I[2];
+  r.gather_warps = stem_gather_warps_;
   if (c.direct_in) {
     // ring of raw image-row pairs (2 rows x 3 channels, sized for fp32) in what is left of the 227 KB
     r.raw_stage_bytes = (uint32_t)round_up(6 * r.W * 4, 128);

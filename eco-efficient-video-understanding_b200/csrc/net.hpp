@@ -230,6 +230,7 @@ class Net {
   int fuse_1x1_ = 1;  // 1: 1x1 convolutions reading the same tensor run as one GEMM with segmented output (fast plan only)
   int multicast_ = 0;  // persistent kernel in clusters of 2 sharing each weight tile by TMA multicast: 0 off (default: measured no gain -- the limit is the per-SM TMA ingest, not L2; profiles/r01m), 1 layers with >= 2 tiles per SM, 2 always
   int pair_ = 1;  // CTA-pair (cta_group::2) kernel: 0 off, 1 for 256-wide tiles with >= 2 tiles per SM pair, 2 wherever possible
+  int stem_gather_warps_ = 4;  // window-gather warps of the direct stem kernel (4..6)
   int stem_direct_ = 1;  // 1: the stem rows kernel gathers its windows from the raw frames (frame width % 16 == 0)
   int pool_commute_ = 1;  // 1: AVE 3x3/s1 pooling -> 1x1 conv (+BN+ReLU) runs as conv -> pooling(+bias+BN+ReLU) when nothing else reads the pooled blob
   int stem_rows_ = 1;  // 0: stem as 4x1 im2col GEMM; 1: rows kernel, pool1 folded in when its input has no other reader; 2: rows kernel, never fold the pool

@@ -228,6 +228,14 @@ def test_stem_rows_kernel(gpu, shape, pool, direct):
             net.blobs["c_bn"].data
 
 
+@pytest.mark.parametrize("warps", [5, 6])
+def test_stem_rows_kernel_gather_warps(gpu, warps):
+    # the window-gather role of the direct stem kernel with 5 / 6 warps (default 4): rows are dealt round-robin
+    shape = (5, 3, 224, 224)
+    txt = conv_net(shape, 64, [7, 7], [2, 2], [3, 3]) + STEM_POOL
+    run_case(txt, shape, 1, check=("p1",), keep_all=False, stem_rows=1, stem_direct=1, stem_gather_warps=warps)
+
+
 def test_stem_rows_pool_not_folded_when_blob_has_other_readers(gpu):
     # c_bn feeds the pooling AND a 1x1 conv: the pool must stay a separate op (c_bn is stored)
     shape = (2, 3, 32, 32)
