@@ -1,0 +1,93 @@
+"""CPU checks of the algebra behind the device plan's rewrites, done with the oracle's own operators
+(oracle/ref_cpu.c through oracle.refnet), independent of any GPU:
+
+* the 7x7/stride-2/pad-3 stem == a 4x4/stride-1 convolution over 2x2 space-to-depth cells (what `stem_rows_kernel`
+  computes), with exactly the weight packing `Net::upload_params` uses, and == the sum over the 4 vertical taps of
+  "cell row y+i times weight K block i" (the sliding-row accumulation into the TMEM ring);
+* `pool_commute`: AVE 3x3/s1/p1 pooling followed by a 1x1 convolution == the 1x1 convolution without bias followed by
+  the pooling plus bias (caffe's AVE divides every window by 9 here and padding contributes zeros);
+* `fuse_1x1`: sibling 1x1 convolutions as one GEMM over concatenated output channels.
+"""
+import numpy as np
+
+from oracle import refnet
+
+
+def cells_of(x):
+    """[F,3,H,W] -> space-to-depth cells [F, CH, CW, 16] as csrc/aux_kernels.cu:stem_s2d_kernel lays them out:
+    cell (Y,X), value (dy*2+dx)*3+c = x[c, 2Y+dy-3, 2X+dx-3], zero outside the frame, values 12..15 zero."""
+    F, C, H, W = x.shape
+    OH, OW = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    CH, CW = OH + 3, OW + 3
+    xp = np.zeros((F, C, 2 * CH + 3, 2 * CW + 3), np.float32)
+    xp[:, :, 3:3 + H, 3:3 + W] = x  # xp[..., y+3, x+3] = x[..., y, x]
+    cells = np.zeros((F, CH, CW, 16), np.float32)
+    for dy in range(2):
+        for dx in range(2):
+            for c in range(3):
+                cells[..., (dy * 2 + dx) * 3 + c] = xp[:, c, dy:dy + 2 * CH:2, dx:dx + 2 * CW:2]
+    return cells, OH, OW
+
+
+def pack_stem_weights(w):
+    """[Cout,3,7,7] -> [Cout, 4 vertical taps, 64] with K index tx*16 + (dy*2+dx)*3 + c  (net.cpp: upload_params)"""
+    cout = w.shape[0]
+    wp = np.zeros((cout, 4, 64), np.float32)
+    for ty in range(4):
+        for tx in range(4):
+            for dy in range(2):
+                for dx in range(2):
+                    ky, kx = 2 * ty + dy, 2 * tx + dx
+                    if ky < 7 and kx < 7:
+                        for c in range(3):
+                            wp[:, ty, tx * 16 + (dy * 2 + dx) * 3 + c] = w[:, c, ky, kx]
+    return wp
+
+
+def test_stem_is_a_sliding_window_over_cell_rows():
+    rng = np.random.default_rng(0)
+    for hw in ((32, 32), (30, 34), (17, 23)):
+        x = rng.normal(size=(2, 3) + hw).astype(np.float32)
+        w = rng.normal(size=(8, 3, 7, 7)).astype(np.float32)
+        b = rng.normal(size=(8,)).astype(np.float32)
+        want = refnet.conv_forward(x, w, b, [7, 7], [2, 2], [3, 3])
+        cells, OH, OW = cells_of(x)
+        wp = pack_stem_weights(w)
+        got = np.zeros((2, 8, OH, OW), np.float32)
+        for y in range(OH):           # output row y = sum over the 4 cell rows y..y+3 (vertical taps)
+            for i in range(4):
+                row = cells[:, y + i]  # [F, CW, 16]
+                # window x = cells x..x+3 of this row = 64 consecutive values (what one 128-byte tile row holds)
+                win = np.stack([row[:, xx:xx + 4].reshape(2, 64) for xx in range(OW)], axis=1)  # [F, OW, 64]
+                got[:, :, y, :] += np.einsum("fxk,ok->fox", win, wp[:, i])
+        got += b[None, :, None, None]
+        assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max(), hw
+
+
+def test_ave_pool_then_1x1_conv_commutes():
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(3, 24, 9, 11)).astype(np.float32)
+    w = rng.normal(size=(16, 24, 1, 1)).astype(np.float32)
+    b = rng.normal(size=(16,)).astype(np.float32)
+    pooled = refnet.pool_forward(x, [3, 3], [1, 1], [1, 1], "AVE")
+    want = refnet.conv_forward(pooled, w, b, [1, 1], [1, 1], [0, 0])
+    nobias = refnet.conv_forward(x, w, np.zeros_like(b), [1, 1], [1, 1], [0, 0])
+    got = refnet.pool_forward(nobias, [3, 3], [1, 1], [1, 1], "AVE") + b[None, :, None, None]
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    # with a bias inside the conv the two orders differ at the border (padding is zero, not bias): the rewrite must
+    # keep the bias behind the pooling
+    wrong = refnet.pool_forward(refnet.conv_forward(x, w, b, [1, 1], [1, 1], [0, 0]), [3, 3], [1, 1], [1, 1], "AVE")
+    assert np.abs(wrong - want).max() > 1e-2 * np.abs(want).max()
+
+
+def test_sibling_1x1_convs_as_one_gemm():
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(2, 32, 6, 7)).astype(np.float32)
+    ws = [rng.normal(size=(n, 32, 1, 1)).astype(np.float32) for n in (16, 32, 16)]
+    bs = [rng.normal(size=(w.shape[0],)).astype(np.float32) for w in ws]
+    fused = refnet.conv_forward(x, np.concatenate(ws), np.concatenate(bs), [1, 1], [1, 1], [0, 0])
+    off = 0
+    for w, b in zip(ws, bs):
+        one = refnet.conv_forward(x, w, b, [1, 1], [1, 1], [0, 0])
+        assert np.array_equal(fused[:, off:off + w.shape[0]], one)  # same K order per output channel: bit-identical
+        off += w.shape[0]
