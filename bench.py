@@ -14,7 +14,13 @@ sharded across ranks with no data-path collective ("scaling": "weak").
   roofline: all launches of the implicit-GEMM conv kernel (the dominant kernel): algorithmic FLOPs
             (2*M*N*K per conv, SURVEY.md 8(d): 92.97 GFLOP/video) / their summed CUDA-event time
   cpu_baseline: the oracle (a port of caffe_3d's CPU algorithm: per-image im2col + SGEMM + separate
-            BN/ReLU/pool passes) on this box's host cores, bounded sample
+            BN/ReLU/pool passes) on this box's host cores, bounded sample; `strong` = the same clip through
+            torch-CPU fp32 (oneDNN), SURVEY.md 8(d)'s "strong CPU" line
+  parity  : the device logits of clip 0 of step 0 against the oracle run on that clip with the SAME weights
+            (read back from the product), outside every timed region: oracle = checker, never the thing measured
+
+The GPU arm generates its weights with tools/harness.py (numpy + the product's own surface); the oracle is only
+imported by the CPU legs (cpu_baseline / parity on rank 0, --impl reference).
 """
 from __future__ import annotations
 
@@ -31,6 +37,9 @@ for p in (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "eco-efficient-v
           os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
+
+os.environ.setdefault("OMP_PROC_BIND", "close")   # CPU legs: one thread per physical core, pinned
+os.environ.setdefault("OMP_PLACES", "cores")
 
 import numpy as np
 
@@ -102,41 +111,78 @@ class ClockSampler(threading.Thread):
                     samples=len(sm))
 
 
-def cpu_reference_forward(model, segments, steps, warmup, threads=None):
-    """The reference arm / cpu_baseline: oracle fp32 forward (caffe_3d's CPU algorithm), one clip per step."""
+def physical_cores():
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_reference_forward(model, segments, steps, warmup, threads=None, params=None, x=None, classes=None):
+    """The reference arm / cpu_baseline: oracle fp32 forward (caffe_3d's CPU algorithm), one clip per step.
+    `params` (the product's weights) and `x` (one clip) make it the parity checker as well; returns
+    (videos/s, ms/step, threads, logits fp32, logits bf16-mirror or None)."""
     import gen_eco_prototxt as gen
     from oracle import refnet
-    if not threads:
-        # all the host *cores* it can use: one OpenMP thread per physical core (SMT siblings only add
-        # contention to the SGEMM: 128 logical CPUs ran 50x slower than 64 threads on the GPU box's host)
-        try:
-            import psutil
-            threads = psutil.cpu_count(logical=False) or os.cpu_count()
-        except Exception:
-            threads = max(1, (os.cpu_count() or 2) // 2)
-        try:
-            threads = min(threads, len(os.sched_getaffinity(0)))
-        except Exception:
-            pass
-    if threads:
-        refnet.lib().ref_set_num_threads(int(threads))
+    threads = int(threads or physical_cores())  # one OpenMP thread per physical core (SMT siblings only add noise)
+    refnet.lib().ref_set_num_threads(threads)
     cores = int(refnet.lib().ref_num_threads())
-    txt = (gen.eco_full_deploy if model == "full" else gen.eco_lite_deploy)(segments=segments, batch=1)
-    net = refnet.RefNet(txt).init_params(4321)
-    x = refnet.eco_input(1, segments)
+    kw = dict(segments=segments, batch=1)
+    if classes:
+        kw["classes"] = classes
+    txt = (gen.eco_full_deploy if model == "full" else gen.eco_lite_deploy)(**kw)
+    net = refnet.RefNet(txt)
+    if params is not None:
+        net.set_params(params)
+    else:
+        net.init_params(4321)
+    if x is None:
+        x = refnet.eco_input(1, segments)
     for _ in range(warmup):
         net.forward(x)
     t0 = time.perf_counter()
     for _ in range(steps):
-        net.forward(x)
+        out = net.forward(x)
     dt = time.perf_counter() - t0
-    return steps / dt, dt / steps * 1e3, cores
+    mirror = net.forward(x, bf16=True)["fc8"] if params is not None else None
+    return steps / dt, dt / steps * 1e3, cores, out["fc8"], mirror
+
+
+def cpu_strong_forward(params, x, segments, steps=3, warmup=1, threads=None):
+    """torch-CPU fp32 (oneDNN / MKL) functional ECO-Lite on the same clip and weights: the strong CPU line."""
+    import torch
+    from oracle.torch_ref import torch_eco_lite, t
+    threads = int(threads or physical_cores())
+    torch.set_num_threads(threads)
+    xt = t(x)
+    with torch.no_grad():
+        for _ in range(warmup):
+            torch_eco_lite(params, xt, segments)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fc8, _ = torch_eco_lite(params, xt, segments)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3, threads, fc8
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="lite", choices=["lite", "full"])
@@ -156,12 +202,16 @@ def main():
         if rank != 0:
             return
         steps = max(1, min(a.steps, 10))
-        vps, ms, cores = cpu_reference_forward(a.model, a.segments, steps, min(a.warmup, 1))
+        vps, ms, cores, _, _ = cpu_reference_forward(a.model, a.segments, steps, min(a.warmup, 1))
         line = {"impl": "reference", "metric": "ECO-Lite-16 forward videos/sec", "value": vps, "unit": "videos/s",
                 "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 1), "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "note": "reference CPU algorithm (oracle port of caffe_3d), 1 clip per step"},
-                "cpu_baseline": {"value": vps, "unit": "videos/s", "cores": cores, "kind": "port",
+                "config": {"workload": workload,
+                           "note": "reference CPU algorithm (oracle port of caffe_3d: per-image im2col + SGEMM), bounded sample: "
+                                   "ONE clip per step and at most 10 steps, whatever --batch/--steps say (a CPU arm at batch 32 "
+                                   "would take minutes per step); videos/s is per clip, so it compares with the GPU arm's videos/s"},
+                "cpu_baseline": {"value": vps, "unit": "videos/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+                                 "threads": "one OpenMP thread per physical core, OMP_PROC_BIND=close",
                                  "sample": "%d single-clip N=%d forwards" % (steps, a.segments)},
                 "e2e": {"value": vps, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -171,8 +221,7 @@ def main():
     import torch
     import caffe
     import gen_eco_prototxt as gen
-    from oracle import refnet
-    from eco_testlib import load_params
+    import harness
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
@@ -186,10 +235,14 @@ def main():
     classes = CLASSES if a.model == "lite" else 400
     txt = (gen.eco_full_deploy if a.model == "full" else gen.eco_lite_deploy)(segments=N, classes=classes, batch=B)
     net = caffe.Net.from_string(txt, caffe.TEST, keep_all_blobs=0, use_graph=0 if a.no_graph else 1)
-    # harness weights (random init of the right architecture; values do not affect timing)
-    ref = refnet.RefNet((gen.eco_full_deploy if a.model == "full" else gen.eco_lite_deploy)(segments=4, classes=classes, batch=1))
-    ref.init_params(4321)
-    load_params(net, ref.params_dict())
+    # harness weights: random init of the right architecture, BN statistics calibrated on the device with a small
+    # every-blob net (N=4, one clip) so activations stay O(1) like a trained net's and the parity check below means something
+    make = gen.eco_full_deploy if a.model == "full" else gen.eco_lite_deploy
+    small = caffe.Net.from_string(make(segments=4, classes=classes, batch=1), caffe.TEST, keep_all_blobs=1)
+    harness.init_params(small, 4321)
+    harness.calibrate_bn_on_device(small, harness.synthetic_frames(1, 4))
+    harness.copy_params(net, small)
+    del small
     stream = torch.cuda.Stream()          # a real (non-legacy) stream: the events below are recorded on it
     net.set_stream(stream.cuda_stream)
 
@@ -225,6 +278,9 @@ def main():
     launches = net.last_launch_count() * a.steps
     ms_step = ms_total / a.steps
     value = world * B * a.steps / (ms_total / 1e3)
+    # logits of clip 0 from this plan (graph replay, production options), checked against the oracle further down
+    dev_logits0 = np.array(net.blobs["fc8"].data[0:1], np.float32, copy=True)
+    clip0 = frames[:N].cpu().numpy()
 
     # ---------------- e2e: host buffers in, logits out, copies inside the timed region ----------------
     host_in = net.blobs["data"].data  # pinned host mirror of the input blob (what caffe's data layer fills)
@@ -321,38 +377,76 @@ def main():
             else:
                 other_ms += op["ms"]
     pk = peaks()
-    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    # The per-launch CUDA-event profile runs eagerly (no graph) and carries event / launch gaps, so its sum exceeds the
+    # graph-replayed step; the conv launches' SHARE of it is what carries over (it agrees with the ncu launch list in
+    # profiles/).  conv time inside the timed step = share x ms_per_step; achieved = algorithmic conv FLOPs / that.
+    eager_conv_ms, eager_other_ms = conv_ms / prof_iters, other_ms / prof_iters
+    share = eager_conv_ms / max(eager_conv_ms + eager_other_ms, 1e-9)
+    conv_ms_step = share * ms_step
+    flops_step = conv_flops / prof_iters
+    achieved = flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
+    burst = None
+    try:
+        burst = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops")
+    except (OSError, ValueError):
+        pass
     # dram bytes of the same launches from the committed ncu --set full capture (only valid for the captured workload)
     traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_final_ncu_dram_bytes.json")))
-        if tj["model"] == a.model and tj["batch"] == B and tj["segments"] == N:
-            traffic, traffic_src = tj["conv_dram_bytes_per_step"], "profiles/r01_final_ncu_dram_bytes.json"
-    except (OSError, KeyError, ValueError):
-        pass
+    for cand in ("r02_final_ncu_dram_bytes.json", "r01_final_ncu_dram_bytes.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", cand)))
+            if tj["model"] == a.model and tj["batch"] == B and tj["segments"] == N:
+                traffic, traffic_src = tj["conv_dram_bytes_per_step"], "profiles/" + cand
+                break
+        except (OSError, KeyError, ValueError):
+            pass
     roofline = {"bound": "tensor",
-                "kernel": "conv_umma_persistent_kernel + stem_rows_kernel (all %d conv launches/step)" % (conv_n // prof_iters),
+                "kernel": "conv_umma_persistent_kernel / conv_umma_pair_kernel / stem_rows_kernel (all %d conv launches/step)" % (conv_n // prof_iters),
                 "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                "peak_source": pk["src"], "traffic": traffic, "traffic_unit": "bytes/step (dram read+write, all conv launches)",
+                "peak_source": pk["src"] + ": the step is timed as %d back-to-back replays, so the sustained figure applies" % a.steps,
+                "frac_of_burst_peak": (achieved / burst) if burst else None,
+                "whole_step_tflops": world and (B * GFLOP_PER_VIDEO.get((a.model, N), 0.0) / ms_step),
+                "traffic": traffic, "traffic_unit": "bytes/step (dram read+write, all conv launches)",
                 "traffic_source": traffic_src,
-                "conv_ms_per_step": conv_ms / prof_iters, "other_ms_per_step": other_ms / prof_iters,
-                "share_of_step": conv_ms / max(conv_ms + other_ms, 1e-9)}
+                "conv_ms_per_step": conv_ms_step, "other_ms_per_step": ms_step - conv_ms_step,
+                "share_of_step": share,
+                "method": "share of the conv launches in a per-launch CUDA-event profile (eager: %.3f + %.3f ms) applied to the "
+                          "graph-timed ms_per_step" % (eager_conv_ms, eager_other_ms)}
 
     if rank != 0:
         grp.close()
         return
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if not a.no_cpu_baseline and world == 1:
-        vps, ms, cores = cpu_reference_forward(a.model, N, steps=3, warmup=1)
-        cpu_baseline = {"value": vps, "unit": "videos/s", "cores": cores, "kind": "port",
-                        "sample": "3 single-clip N=%d fp32 forwards of the oracle (caffe_3d CPU algorithm)" % N}
+        # CPU legs (the only place this arm touches oracle/): time the caffe-algorithm port and the torch-CPU graph on
+        # clip 0 with the PRODUCT's weights, and use their logits to check the device's
+        params = harness.params_dict(net)
+        vps, ms, cores, ref_fc8, mirror_fc8 = cpu_reference_forward(a.model, N, steps=3, warmup=1, params=params, x=clip0,
+                                                                  classes=classes)
+        cpu_baseline = {"value": vps, "unit": "videos/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+                        "logical_cpus": os.cpu_count(),
+                        "threads": "one OpenMP thread per physical core, OMP_PROC_BIND=close",
+                        "sample": "3 single-clip N=%d fp32 forwards of the oracle (caffe_3d CPU algorithm), clip 0 of the batch" % N}
+        rel = lambda g, w: float(np.abs(g.astype(np.float64) - w).max() / max(np.abs(w).max(), 1e-30))
+        parity = {"clip": 0, "blob": "fc8", "rel_max_vs_oracle_bf16_mirror": rel(dev_logits0, mirror_fc8),
+                  "rel_max_vs_oracle_fp32": rel(dev_logits0, ref_fc8),
+                  "oracle_bf16_mirror_vs_fp32": rel(mirror_fc8, ref_fc8),
+                  "vs": "oracle (oracle/refnet.py) on clip 0 with the weights read back from the product; "
+                        "tolerance of the tests: 2e-2 vs the bf16 mirror (tests/eco_testlib.py)"}
+        if a.model == "lite":
+            svps, sms, sthreads, s_fc8 = cpu_strong_forward(params, clip0, N)
+            cpu_baseline["strong"] = {"value": svps, "unit": "videos/s", "threads": sthreads, "kind": "torch-cpu fp32 (oneDNN/MKL)",
+                                      "sample": "3 single-clip N=%d forwards" % N,
+                                      "agrees_with_port_rel_max": rel(s_fc8, ref_fc8)}
     line = {"metric": "ECO-Lite-16 forward videos/sec" if a.model == "lite" else "ECO-Full-16 forward videos/sec",
             "value": value, "unit": "videos/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": workload, "global_batch": B * world, "parallelism": "batch-sharded x%d, no collective" % world,
                        "l2": "inputs (%.0f MB/GPU) and activations exceed the 126 MB L2" % (count * 4 / 1e6),
-                       "cuda_graph": not a.no_graph},
+                       "cuda_graph": not a.no_graph,
+                       "batch_choice": "B=32 videos/GPU: best of the batch sweep B in {1, 8, 16, 32, 64} at the current kernels "
+                                       "(profiles/r02_batch_sweep.md); res5 fills 147 of 148 SMs at exactly this batch"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "videos/s", "h2d_bytes_per_step": int(count * 4),
                     "d2h_bytes_per_step": int(B * classes * 4), "ms_per_step": max(e2e_ms, wall_ms) / a.steps,
@@ -363,7 +457,10 @@ def main():
                                      "h2d_bytes_per_step": int(count),
                                      "note": "raw uint8 frames in, BGR mean subtracted on the GPU (the host half of the "
                                              "reference's DataTransformer), otherwise as pipelined"}},
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e_u8": {"value": e2e_u8_value, "unit": "videos/s", "h2d_bytes_per_step": int(count), "d2h_bytes_per_step": int(B * classes * 4),
+                       "note": "the declared serving entry point (eco_net_forward_pipelined_u8): raw uint8 frames from pinned host "
+                               "memory, mean subtraction on the GPU, logits back to the host; wall clock over the same steps"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "gflop_per_video": GFLOP_PER_VIDEO.get((a.model, N))}
     print(json.dumps(line))
     grp.close()

@@ -219,6 +219,22 @@ class Net(object):
         check(lib().eco_net_last_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def describe_plan(self):
+        """one dict per planned op: what the planner chose (kernel, tile, grid) for the current shapes"""
+        need = C.c_size_t()
+        check(lib().eco_net_describe_plan(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(lib().eco_net_describe_plan(self._h, buf, need.value, C.byref(need)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            parts = line.split(" ")
+            d = {"name": parts[0]}
+            for kv in parts[1:]:
+                k, _, v = kv.partition("=")
+                d[k] = int(v) if v.lstrip("-").isdigit() else v
+            rows.append(d)
+        return rows
+
     def profile_forward(self, cap=1024):
         arr = (_caffe.OpTime * cap)()
         n = C.c_int()

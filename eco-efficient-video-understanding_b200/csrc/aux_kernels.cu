@@ -609,6 +609,15 @@ cudaError_t launch_u8_to_f32_mean(const unsigned char* src, float* dst, long lon
   u8_to_f32_mean_kernel<<<grid_cap(n), kThreads, 0, st>>>(src, dst, outer, C, inner, mean0, mean1, mean2, mean3);
   return cudaGetLastError();
 }
+// per-device function attributes (called once per device by Net::ensure_device)
+cudaError_t aux_kernels_configure() {
+  cudaError_t e = cudaFuncSetAttribute(pool2d_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pool2d_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(pool2d_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {
   const long long n = (long long)p.NB * p.OD * p.OH * p.OW * (p.C / 8);
   if (n == 0) return cudaSuccess;
@@ -622,13 +631,6 @@ cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {
     const size_t rows_in = (size_t)(rows_out - 1) * p.sH + p.KH;
     const size_t smem = rows_in * row_bytes;
     if (smem <= 200 * 1024 && row_bytes % 16 == 0 && p.NB <= 65535) {
-      static bool configured = false;
-      if (!configured) {
-        cudaFuncSetAttribute(pool2d_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(pool2d_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(pool2d_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
-      }
       const bool k3 = p.KH == 3 && p.KW == 3 && p.sH == p.sW && (p.sW == 1 || p.sW == 2);
       if (epilogue && (p.is_max || !k3)) return cudaErrorNotSupported;
       dim3 grid((p.OH + rows_out - 1) / rows_out, p.NB, 1);

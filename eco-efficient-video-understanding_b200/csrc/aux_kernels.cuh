@@ -43,6 +43,11 @@ struct PoolParams {
   // used when a 1x1 convolution behind an AVE pooling was moved in front of it (both are linear)
   const float* bias; const float* scale; const float* shift; int relu;
 };
+cudaError_t aux_kernels_configure();  // max dynamic shared memory attributes, once per device
+// the row-staged kernel is the only one with the affine epilogue: 3 input rows of a dense map must fit its 200 KB
+inline bool pool_cl_affine_supported(int IW, int C, long long NB) {
+  return (size_t)3 * IW * C * 2 <= (size_t)200 * 1024 && NB <= 65535 && C % 8 == 0;
+}
 // caffe pooling on channels-last bf16 (pooling_layer.cpp:199-262 semantics), C % 8 == 0
 cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st);
 

@@ -86,6 +86,7 @@ BlobData read_blob(Reader r) {
       b.data.resize(old + n);
       std::memcpy(b.data.data() + old, d.p, n * 4);
     } else if (field == 5 && wire == 5) {
+      if (r.end - r.p < 4) throw std::runtime_error("truncated caffemodel (float field)");
       float f;
       std::memcpy(&f, r.p, 4);
       r.p += 4;
@@ -176,8 +177,8 @@ void Net::copy_from(const std::string& path) {
     // "Ignoring source layer" when the name is unknown (net.cpp:860-863)
     OrigLayer* target = nullptr;
     for (auto& L : layers_)
-      if (L.name == lname) target = &L;
-    if (!target || blobs.empty()) continue;
+      if (L.name == lname) { target = &L; break; }  // first match, as the reference's linear search (net.cpp:856-859)
+    if (!target) continue;
     if (target->params.size() != blobs.size()) {
       std::ostringstream o;
       o << "Incompatible number of blobs for layer " << lname << ": " << target->params.size() << " vs " << blobs.size();

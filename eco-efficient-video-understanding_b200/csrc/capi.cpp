@@ -315,5 +315,16 @@ int eco_net_profile_forward(eco_net* net, eco_op_time* out, int cap, int* n) {
   *n = N(net).profile(out, cap);
   ECO_API_END
 }
+int eco_net_describe_plan(eco_net* net, char* buf, size_t cap, size_t* needed) {
+  ECO_API_BEGIN
+  const std::string d = N(net).describe_plan();
+  if (needed) *needed = d.size() + 1;
+  if (buf && cap) {
+    const size_t n = d.size() < cap - 1 ? d.size() : cap - 1;
+    std::memcpy(buf, d.data(), n);
+    buf[n] = 0;
+  }
+  ECO_API_END
+}
 
 }  // extern "C"

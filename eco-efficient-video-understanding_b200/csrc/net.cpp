@@ -149,6 +149,7 @@ Net::Net(const std::string& text, int phase) : phase_(phase) {
 
 Net::~Net() {
   free_plan();
+  if (stage_) cudaFree(stage_);
   if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
 
@@ -596,17 +597,23 @@ void Net::ensure_device() {
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     own_stream_ = true;
   }
-  static bool configured = false;
-  if (!configured) {
+  // function attributes (max dynamic shared memory) and the SM count are per device: caffe allows
+  // Caffe::SetDevice to switch devices inside one process (common.hpp:160-174)
+  static bool configured[64] = {};
+  static int sms[64] = {};
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  ECO_CHECK(dev >= 0 && dev < 64, "device ordinal " << dev << " out of range");
+  if (!configured[dev]) {
     cudaDeviceProp prop;
-    int dev = 0;
-    CUDA_OK(cudaGetDevice(&dev));
     CUDA_OK(cudaGetDeviceProperties(&prop, dev));
     ECO_CHECK(prop.major == 10, "libeco_b200 is built for sm_100a only; device is sm_" << prop.major << prop.minor);
     CUDA_OK(conv_umma_configure());
-    g_num_sms = prop.multiProcessorCount;
-    configured = true;
+    CUDA_OK(aux_kernels_configure());
+    sms[dev] = prop.multiProcessorCount;
+    configured[dev] = true;
   }
+  g_num_sms = sms[dev];
 }
 
 void* Net::dalloc(size_t bytes, bool zero) {
@@ -937,6 +944,8 @@ bool Net::try_commute_pool_conv(int li, std::vector<bool>& done, std::vector<int
     auto pd = nd_param(*cp, "pad", "pad", 2, 0);
     if (k[0] != 1 || k[1] != 1 || st[0] != 1 || st[1] != 1 || pd[0] != 0 || pd[1] != 0) return false;
   }
+  // the pooling then runs on the row-staged kernel (the only one with the bias/BN/ReLU epilogue): its limits
+  if (!pool_cl_affine_supported(tensors_[xb].shape[3], C.params[0].shape[0], tensors_[xb].shape[0])) return false;
   // the conv group must reduce to "one stored output" (conv -> BN [-> in-place ReLU])
   const int T0 = C.tops[0];
   if (tensors_[T0].consumers.size() != 1) return false;
@@ -1092,6 +1101,14 @@ void Net::plan_conv_group(int li, std::vector<bool>& done, int in_override) {
       }
     }
     if (nbn != 1) bn = -1;
+    // conv -> in-place layer on `pre` (e.g. ReLU with top == bottom) -> BN: the BN must see the rewritten blob
+    // (the reference computes BN(relu(conv))), so it cannot be folded into the conv epilogue
+    if (bn >= 0)
+      for (int ci : tensors_[pre].consumers) {
+        if (ci >= bn || done[ci]) continue;
+        const OrigLayer& W = layers_[ci];
+        if (std::find(W.tops.begin(), W.tops.end(), pre) != W.tops.end()) { bn = -1; break; }
+      }
   }
   if (bn >= 0) {
     c.bn_layer = bn;
@@ -1998,15 +2015,18 @@ void Net::upload_params() {
 
 // =====================================================================================
 // host <-> device blob traffic (what SyncedMemory::to_cpu/to_gpu do lazily, syncedmem.cpp:21-70)
-static float* g_stage = nullptr;
-static size_t g_stage_bytes = 0;
-static float* staging(size_t bytes) {
-  if (bytes > g_stage_bytes) {
-    if (g_stage) cudaFree(g_stage);
-    CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g_stage), bytes));
-    g_stage_bytes = bytes;
+// per-net staging buffer for the fp32 <-> channels-last conversions (all users run on this net's stream, in order)
+float* Net::staging(size_t bytes) {
+  if (bytes > stage_bytes_) {
+    if (stage_) {
+      CUDA_OK(cudaStreamSynchronize(stream_));
+      cudaFree(stage_);
+      stage_ = nullptr;
+    }
+    CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&stage_), bytes));
+    stage_bytes_ = bytes;
   }
-  return g_stage;
+  return stage_;
 }
 
 void Net::download(Tensor& t) {
@@ -2338,6 +2358,31 @@ float Net::forward(int start, int end) {
   run_ops(full, lo, hi, nullptr, &launches);
   last_launches_ = launches;
   return 0.f;
+}
+
+std::string Net::describe_plan() {
+  if (!planned_) plan();
+  std::ostringstream o;
+  static const char* tn[] = {"conv", "pool_cl", "global_avg", "pool_f32", "fc", "ssr", "eltwise", "copy2d", "cl_to_f32",
+                             "f32_to_cl", "softmax"};
+  for (const Op& op : ops_) {
+    o << op.name << " type=" << ((int)op.type < 11 ? tn[(int)op.type] : "train");
+    if (op.type == Op::CONV) {
+      const ConvOp& c = convs_[op.conv];
+      const ConvKernelParams& k = c.pair ? c.kpp : c.kp;
+      const char* kern = c.rows ? "stem_rows" : c.pair ? "pair" : c.halo ? "halo" : k.persistent ? "persistent" : "one_tile";
+      const int mt = c.pair ? 2 : (k.persistent ? k.m_halves : 1);
+      const long long tile_m = (long long)kBlockM * mt;
+      const long long tiles = c.rows ? (long long)c.rp.F * c.rp.strips
+                                     : ((long long)k.M + tile_m - 1) / tile_m * ((c.Cout + k.block_n - 1) / k.block_n);
+      o << " kernel=" << kern << " M=" << k.M << " Cout=" << c.Cout << " Cin=" << c.Cin << " taps=" << c.K[0] * c.K[1] * c.K[2]
+        << " block_n=" << k.block_n << " mt=" << mt << " tiles=" << tiles << " stages=" << k.stages
+        << " a_mode=" << k.a_mode << " nseg=" << k.nseg << " multicast=" << k.multicast << " raw=" << (c.raw_tensor >= 0)
+        << " out=" << (c.out_tensor >= 0) << " res=" << (c.res_tensor >= 0) << " pool=" << (c.pool_tensor >= 0);
+    }
+    o << "\n";
+  }
+  return o.str();
 }
 
 int Net::profile(eco_op_time* out, int cap) {

@@ -212,6 +212,7 @@ class Net {
   int num_params(int vis_layer) const;
   void mark_params_dirty(int vis_layer);
   int profile(eco_op_time* out, int cap);
+  std::string describe_plan();
   int last_launches() const { return last_launches_; }
   void copy_from(const std::string& path);
   void save(const std::string& path) const;
@@ -282,6 +283,9 @@ class Net {
   bool plan_halo(ConvOp& c);
   void plan_stem_rows(ConvOp& c);
   bool is_stem_conv(const OrigLayer& L) const;
+  float* stage_ = nullptr;
+  size_t stage_bytes_ = 0;
+  float* staging(size_t bytes);
   void download(Tensor& t);
   void upload(Tensor& t);
   ClView view(const Tensor& t) const;

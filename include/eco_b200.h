@@ -136,6 +136,9 @@ typedef struct eco_op_time {
   double bytes;       /* algorithmic HBM bytes: input once + output once + weights once */
 } eco_op_time;
 int eco_net_profile_forward(eco_net* net, eco_op_time* out, int cap, int* n);
+/* one text line per planned op: name, kernel, tile shape (block_n, MT, pair), grid, stages -- what the planner chose for
+ * the current shapes (plans on first use).  `needed` receives the full length incl. the terminating 0. */
+int eco_net_describe_plan(eco_net* net, char* buf, size_t cap, size_t* needed);
 
 #ifdef __cplusplus
 }

@@ -17,13 +17,16 @@ lo, hi = shard(7, g.world, g.rank)
 g.barrier()
 mx = g.max_over_ranks(10.0 + g.rank)       # device time per rank -> the slowest rank defines the step
 tot = g.sum_over_ranks(hi - lo)
-print(json.dumps({"rank": g.rank, "world": g.world, "shard": [lo, hi], "max": mx, "total": tot}))
+# one file per rank: two ranks printing to the shared stdout can interleave inside a line
+with open(os.path.join(os.environ["ECO_TEST_OUT"], "rank%%d.json" %% g.rank), "w") as f:
+    json.dump({"rank": g.rank, "world": g.world, "shard": [lo, hi], "max": mx, "total": tot}, f)
 g.close()
 ''' % ROOT
 
 
-def _torchrun(args, timeout=240):
+def _torchrun(args, timeout=240, extra_env=None):
     env = dict(os.environ)
+    env.update(extra_env or {})
     env["OMP_NUM_THREADS"] = "2"
     import socket
     with socket.socket() as sk:   # a free port: parallel test runs must not collide on the rendezvous
@@ -37,9 +40,9 @@ def _torchrun(args, timeout=240):
 def test_gloo_world2_shard_barrier_max(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    r = _torchrun([str(script)])
+    r = _torchrun([str(script)], extra_env={"ECO_TEST_OUT": str(tmp_path)})
     assert r.returncode == 0, r.stderr[-2000:]
-    rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    rows = [json.loads((tmp_path / ("rank%d.json" % k)).read_text()) for k in (0, 1)]
     assert sorted(x["rank"] for x in rows) == [0, 1]
     assert all(x["world"] == 2 and x["max"] == 11.0 and x["total"] == 7.0 for x in rows)
     assert sorted(tuple(x["shard"]) for x in rows) == [(0, 4), (4, 7)]
