@@ -389,6 +389,205 @@ int ref_pool_forward(const float* x, float* y, int num, int C, int nsp,
   return 0;
 }
 
+/* ------------------------------------------------------------------------ */
+/* Convolution backward.  src/caffe/layers/conv_layer.cpp:44-75 (loop over     */
+/* images, bias / weight / bottom gradients) over                               */
+/* base_conv_layer.cpp:290-328: weight_cpu_gemm  dW[Cout,K] += dY[Cout,M] x col^T[M,K]   */
+/*                              backward_cpu_gemm dcol[K,M] = W^T[K,Cout] x dY[Cout,M];   */
+/*                              col2im (util/im2col.cpp: scatter-add of dcol)   */
+/*                              backward_cpu_bias db[o] += sum_m dY[o,m].        */
+/* Parameter gradients ACCUMULATE into dw / db (caffe's beta = 1); dx is overwritten. */
+static void col2im_nd(const float* col, int cin, int nsp, const int* in_shape, const int* out_shape,
+                      const int* kernel, const int* stride, const int* pad, float* im) {
+  int k[REF_MAX_SP] = {1, 1, 1}, s[REF_MAX_SP] = {1, 1, 1}, p[REF_MAX_SP] = {0, 0, 0};
+  int is[REF_MAX_SP] = {1, 1, 1}, os[REF_MAX_SP] = {1, 1, 1};
+  for (int i = 0; i < nsp; ++i) {
+    int j = REF_MAX_SP - nsp + i;
+    k[j] = kernel[i]; s[j] = stride[i]; p[j] = pad[i];
+    is[j] = in_shape[i]; os[j] = out_shape[i];
+  }
+  const long in_sp = (long)is[0] * is[1] * is[2];
+  const long out_sp = (long)os[0] * os[1] * os[2];
+  const int ktaps = k[0] * k[1] * k[2];
+#pragma omp parallel for schedule(static)
+  for (int c = 0; c < cin; ++c) {  /* one channel per thread: scatter-adds of different taps never race */
+    float* dst = im + (long)c * in_sp;
+    memset(dst, 0, sizeof(float) * (size_t)in_sp);
+    for (int t = 0; t < ktaps; ++t) {
+      int tt = t;
+      const int kx = tt % k[2]; tt /= k[2];
+      const int ky = tt % k[1]; tt /= k[1];
+      const int kz = tt;
+      const float* src = col + ((long)c * ktaps + t) * out_sp;
+      for (int oz = 0; oz < os[0]; ++oz) {
+        const int iz = oz * s[0] - p[0] + kz;
+        if (iz < 0 || iz >= is[0]) continue;
+        for (int oy = 0; oy < os[1]; ++oy) {
+          const int iy = oy * s[1] - p[1] + ky;
+          if (iy < 0 || iy >= is[1]) continue;
+          const float* sr = src + ((long)oz * os[1] + oy) * os[2];
+          float* drow = dst + ((long)iz * is[1] + iy) * is[2];
+          for (int ox = 0; ox < os[2]; ++ox) {
+            const int ix = ox * s[2] - p[2] + kx;
+            if (ix >= 0 && ix < is[2]) drow[ix] += sr[ox];
+          }
+        }
+      }
+    }
+  }
+}
+
+static void transpose2d(const float* a, float* b, long rows, long cols) {  /* b[cols][rows] = a[rows][cols]^T */
+#pragma omp parallel for schedule(static)
+  for (long r0 = 0; r0 < rows; r0 += 32)
+    for (long c0 = 0; c0 < cols; c0 += 32) {
+      const long r1 = r0 + 32 < rows ? r0 + 32 : rows, c1 = c0 + 32 < cols ? c0 + 32 : cols;
+      for (long r = r0; r < r1; ++r)
+        for (long c = c0; c < c1; ++c) b[c * rows + r] = a[r * cols + c];
+    }
+}
+
+int ref_conv_backward(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
+                      int num, int cin, int cout, int nsp, const int* in_shape,
+                      const int* kernel, const int* stride, const int* pad) {
+  if (nsp < 1 || nsp > REF_MAX_SP) return -1;
+  int out_shape[REF_MAX_SP];
+  long in_sp = 1, out_sp = 1, ktaps = 1;
+  for (int i = 0; i < nsp; ++i) {
+    out_shape[i] = ref_conv_out_dim(in_shape[i], kernel[i], stride[i], pad[i]);
+    if (out_shape[i] <= 0) return -2;
+    in_sp *= in_shape[i]; out_sp *= out_shape[i]; ktaps *= kernel[i];
+  }
+  const long K = (long)cin * ktaps;
+  float* col = (float*)malloc(sizeof(float) * (size_t)(K * out_sp));
+  float* colT = dw ? (float*)malloc(sizeof(float) * (size_t)(K * out_sp)) : NULL;
+  float* wT = dx ? (float*)malloc(sizeof(float) * (size_t)(K * cout)) : NULL;
+  float* dwn = dw ? (float*)malloc(sizeof(float) * (size_t)(K * cout)) : NULL;
+  if (!col || (dw && (!colT || !dwn)) || (dx && !wT)) { free(col); free(colT); free(wT); free(dwn); return -3; }
+  if (dx) transpose2d(w, wT, cout, K);
+  for (int n = 0; n < num; ++n) {
+    const float* xn = x + (long)n * cin * in_sp;
+    const float* dyn = dy + (long)n * cout * out_sp;
+    if (db) {
+#pragma omp parallel for schedule(static)
+      for (int o = 0; o < cout; ++o) {
+        double sacc = 0.0;
+        const float* d = dyn + (long)o * out_sp;
+        for (long i = 0; i < out_sp; ++i) sacc += d[i];
+        db[o] += (float)sacc;
+      }
+    }
+    if (dw) {
+      im2col_nd(xn, cin, nsp, in_shape, out_shape, kernel, stride, pad, col);
+      transpose2d(col, colT, K, out_sp);                 /* colT[M][K] */
+      ref_sgemm(dyn, colT, dwn, cout, (int)K, (int)out_sp);  /* [Cout,M] x [M,K] */
+#pragma omp parallel for schedule(static)
+      for (long i = 0; i < K * cout; ++i) dw[i] += dwn[i];
+    }
+    if (dx) {
+      ref_sgemm(wT, dyn, col, (int)K, (int)out_sp, cout);   /* dcol[K,M] = W^T x dY */
+      col2im_nd(col, cin, nsp, in_shape, out_shape, kernel, stride, pad, dx + (long)n * cin * in_sp);
+    }
+  }
+  free(col); free(colT); free(wT); free(dwn);
+  return 0;
+}
+
+/* Pooling backward.  src/caffe/layers/pooling_layer.cpp:280-377.               */
+/*   MAX: the forward pass records the index of the FIRST maximum in scan order  */
+/*        (strictly-greater update, :206-222); backward adds top_diff there.     */
+/*   AVE: top_diff / pool_size (pad-inclusive divisor) added to every in-image    */
+/*        element of the window.                                                  */
+int ref_pool_backward(const float* x, const float* dy, float* dx, int num, int C, int nsp,
+                      const int* in_shape, const int* kernel, const int* stride,
+                      const int* pad, int method) {
+  int k[3] = {1, 1, 1}, s[3] = {1, 1, 1}, p[3] = {0, 0, 0}, is[3] = {1, 1, 1}, os[3] = {1, 1, 1};
+  if (nsp < 1 || nsp > 3) return -1;
+  for (int i = 0; i < nsp; ++i) {
+    int j = 3 - nsp + i;
+    k[j] = kernel[i]; s[j] = stride[i]; p[j] = pad[i]; is[j] = in_shape[i];
+    os[j] = ref_pool_out_dim(in_shape[i], kernel[i], stride[i], pad[i]);
+  }
+  const long in_sp = (long)is[0] * is[1] * is[2], out_sp = (long)os[0] * os[1] * os[2];
+#pragma omp parallel for schedule(static)
+  for (long nc = 0; nc < (long)num * C; ++nc) {
+    const float* xp = x + nc * in_sp;
+    const float* dyp = dy + nc * out_sp;
+    float* dxp = dx + nc * in_sp;
+    memset(dxp, 0, sizeof(float) * (size_t)in_sp);
+    for (int oz = 0; oz < os[0]; ++oz)
+      for (int oy = 0; oy < os[1]; ++oy)
+        for (int ox = 0; ox < os[2]; ++ox) {
+          int z0 = oz * s[0] - p[0], y0 = oy * s[1] - p[1], x0 = ox * s[2] - p[2];
+          const float g = dyp[((long)oz * os[1] + oy) * os[2] + ox];
+          if (method == 0) {
+            int z1 = z0 + k[0] < is[0] ? z0 + k[0] : is[0];
+            int y1 = y0 + k[1] < is[1] ? y0 + k[1] : is[1];
+            int x1 = x0 + k[2] < is[2] ? x0 + k[2] : is[2];
+            if (z0 < 0) z0 = 0; if (y0 < 0) y0 = 0; if (x0 < 0) x0 = 0;
+            float r = -FLT_MAX;
+            long best = -1;
+            for (int z = z0; z < z1; ++z)
+              for (int yy = y0; yy < y1; ++yy)
+                for (int xx = x0; xx < x1; ++xx) {
+                  const long idx = ((long)z * is[1] + yy) * is[2] + xx;
+                  if (xp[idx] > r) { r = xp[idx]; best = idx; }
+                }
+            if (best >= 0) dxp[best] += g;
+          } else {
+            int z1 = z0 + k[0] < is[0] + p[0] ? z0 + k[0] : is[0] + p[0];
+            int y1 = y0 + k[1] < is[1] + p[1] ? y0 + k[1] : is[1] + p[1];
+            int x1 = x0 + k[2] < is[2] + p[2] ? x0 + k[2] : is[2] + p[2];
+            const int pool_size = (z1 - z0) * (y1 - y0) * (x1 - x0);
+            if (z0 < 0) z0 = 0; if (y0 < 0) y0 = 0; if (x0 < 0) x0 = 0;
+            if (z1 > is[0]) z1 = is[0]; if (y1 > is[1]) y1 = is[1]; if (x1 > is[2]) x1 = is[2];
+            for (int z = z0; z < z1; ++z)
+              for (int yy = y0; yy < y1; ++yy)
+                for (int xx = x0; xx < x1; ++xx) dxp[((long)z * is[1] + yy) * is[2] + xx] += g / (float)pool_size;
+          }
+        }
+  }
+  return 0;
+}
+
+/* BN backward, TRAIN phase, not frozen.  src/caffe/layers/bn_layer.cpp:241-335:  */
+/*   dslope += sum x_norm*dy ; dbias += sum dy ;                                  */
+/*   dx = inv_std * ( slope*dy - mean(slope*dy) - x_norm * mean(x_norm * slope*dy) )  */
+/* x_norm = (x - batch_mean) * inv_std as saved by the forward pass (:183-188).    */
+void ref_bn_backward_train(const float* x, const float* dy, float* dx, const float* slope,
+                           const float* batch_mean, const float* batch_var, float eps,
+                           int num, int C, long spatial, float* dslope, float* dbias) {
+#pragma omp parallel for schedule(static)
+  for (int c = 0; c < C; ++c) {
+    const float m = batch_mean[c];
+    const float inv_std = powf(batch_var[c] + eps, -0.5f);
+    double s_dy = 0.0, s_dyx = 0.0;
+    for (int n = 0; n < num; ++n) {
+      const float* xp = x + ((long)n * C + c) * spatial;
+      const float* dp = dy + ((long)n * C + c) * spatial;
+      for (long i = 0; i < spatial; ++i) {
+        const float xn = (xp[i] - m) * inv_std;
+        s_dy += dp[i];
+        s_dyx += (double)dp[i] * xn;
+      }
+    }
+    if (dslope) dslope[c] += (float)s_dyx;
+    if (dbias) dbias[c] += (float)s_dy;
+    if (!dx) continue;
+    const double cnt = (double)num * (double)spatial;
+    const float mean_g = (float)(slope[c] * s_dy / cnt), mean_gx = (float)(slope[c] * s_dyx / cnt);
+    for (int n = 0; n < num; ++n) {
+      const float* xp = x + ((long)n * C + c) * spatial;
+      const float* dp = dy + ((long)n * C + c) * spatial;
+      float* op = dx + ((long)n * C + c) * spatial;
+      for (long i = 0; i < spatial; ++i) {
+        const float xn = (xp[i] - m) * inv_std;
+        op[i] = (slope[c] * dp[i] - mean_g - xn * mean_gx) * inv_std;
+      }
+    }
+  }
+}
+
 /* Eltwise SUM with coefficients: src/caffe/layers/eltwise_layer.cpp:66-72       */
 void ref_eltwise_sum(const float* a, const float* b, float ca, float cb, float* y, long n) {
 #pragma omp parallel for schedule(static)

@@ -123,6 +123,46 @@ def bn_forward_train(x, slope, bias, run_mean, run_var, momentum=0.9, eps=1e-5):
     return y, bm, bv
 
 
+def conv_backward(x, w, dy, kernel, stride, pad, need_dx=True, has_bias=True):
+    """Returns (dx or None, dw, db or None) -- conv_layer.cpp:44-75 over base_conv_layer.cpp:290-328."""
+    x, w, dy = _f32(x), _f32(w), _f32(dy)
+    num, cin = x.shape[:2]
+    cout = w.shape[0]
+    dx = np.zeros_like(x) if need_dx else None
+    dw = np.zeros_like(w)
+    db = np.zeros(cout, np.float32) if has_bias else None
+    rc = lib().ref_conv_backward(_fp(x), _fp(w), _fp(dy), _fp(dx) if need_dx else None, _fp(dw),
+                                 _fp(db) if has_bias else None, num, cin, cout, x.ndim - 2, _ip(x.shape[2:]),
+                                 _ip(kernel), _ip(stride), _ip(pad))
+    if rc != 0:
+        raise RuntimeError("ref_conv_backward rc=%d" % rc)
+    return dx, dw, db
+
+
+def pool_backward(x, dy, kernel, stride, pad, method):
+    x, dy = _f32(x), _f32(dy)
+    dx = np.empty_like(x)
+    rc = lib().ref_pool_backward(_fp(x), _fp(dy), _fp(dx), x.shape[0], x.shape[1], x.ndim - 2, _ip(x.shape[2:]),
+                                 _ip(kernel), _ip(stride), _ip(pad), 0 if method == "MAX" else 1)
+    if rc != 0:
+        raise RuntimeError("ref_pool_backward rc=%d" % rc)
+    return dx
+
+
+def bn_backward_train(x, dy, slope, batch_mean, batch_var, eps=1e-5, need_dx=True):
+    """Returns (dx or None, dslope, dbias) -- bn_layer.cpp:241-335."""
+    x, dy = _f32(x), _f32(dy)
+    num, ch = x.shape[:2]
+    spatial = int(np.prod(x.shape[2:])) if x.ndim > 2 else 1
+    dx = np.empty_like(x) if need_dx else None
+    ds = np.zeros(ch, np.float32)
+    dbias = np.zeros(ch, np.float32)
+    lib().ref_bn_backward_train(_fp(x), _fp(dy), _fp(dx) if need_dx else None, _fp(_f32(slope).ravel()),
+                                _fp(_f32(batch_mean).ravel()), _fp(_f32(batch_var).ravel()), C.c_float(eps),
+                                num, ch, C.c_long(spatial), _fp(ds), _fp(dbias))
+    return dx, ds, dbias
+
+
 def relu(x, slope=0.0):
     x = _f32(x)
     y = np.empty_like(x)
@@ -339,7 +379,7 @@ class RefNet:
         return self
 
     # ---- forward ---------------------------------------------------------------
-    def forward(self, inputs, bf16=False, keep=None, teacher=None, teacher_raw=None):
+    def forward(self, inputs, bf16=False, keep=None, teacher=None, teacher_raw=None, dropout_masks=None, seed=7):
         """inputs: array for the single net input or {name: array}.  Returns {blob: array}
         for every blob (in-place layers overwrite, as in caffe).
 
@@ -352,6 +392,8 @@ class RefNet:
         fused residual add reads back from memory."""
         if not isinstance(inputs, dict):
             inputs = {self.inputs[0]: inputs}
+        self._dropout_masks = dropout_masks or {}
+        self._rng = np.random.default_rng(seed)
         return self._walk(inputs, bf16=bf16, teacher=teacher, teacher_raw=teacher_raw)
 
     def _walk(self, inputs, shapes_only=False, out_param_shapes=None, bf16=False, bn_hook=None, teacher=None,
@@ -359,6 +401,8 @@ class RefNet:
         blobs = {}
         shp = {}
         own = {}
+        self.tape = []       # (layer, [bottom arrays], extra) per executed layer, for backward()
+        self.bn_batch = {}   # TRAIN-phase BN: layer name -> (batch mean, batch variance)
         plain = set()  # blobs the device keeps as plain fp32 vectors (downstream of a collapsing pool / fc)
         last_writer = {}
         for li, l in enumerate(self.layers):
@@ -383,6 +427,9 @@ class RefNet:
                         shp[top] = list(self.input_shapes.get(top, [1]))
                 continue
             bs = [shp[b] for b in l.bottoms]
+            extra = {}
+            if not shapes_only:
+                self.tape.append((l, [blobs[b] for b in l.bottoms], extra))
             if t == "Convolution":
                 p = l.msg.get1("convolution_param")
                 nsp = len(bs[0]) - 2
@@ -398,6 +445,7 @@ class RefNet:
                 if not shapes_only:
                     w = R(l.params[0])
                     b = l.params[1] if bias_term else None
+                    extra.update(k=k, s=s, pd=pd, bias=bias_term)
                     blobs[l.tops[0]] = conv_forward(blobs[l.bottoms[0]], w, b, k, s, pd)
                 shp[l.tops[0]] = osh
             elif t == "BN":
@@ -409,7 +457,20 @@ class RefNet:
                         bn_hook(l, x)
                     bp = l.msg.get1("bn_param") or _pt.Msg()
                     eps = float(bp.get1("eps", 1e-5))
-                    y = bn_forward_test(x, l.params[0], l.params[1], l.params[2], l.params[3], eps)
+                    frozen = bool(bp.get1("frozen", False))
+                    if self.phase == "TRAIN" and not frozen:
+                        # batch statistics + running-average update (bn_layer.cpp:107-157); the running blobs
+                        # of this RefNet are updated in place like the reference's blobs_[2], blobs_[3]
+                        rm = np.ascontiguousarray(l.params[2], np.float32).reshape(-1).copy()
+                        rv = np.ascontiguousarray(l.params[3], np.float32).reshape(-1).copy()
+                        y, bm, bv = bn_forward_train(x, l.params[0], l.params[1], rm, rv,
+                                                     float(bp.get1("momentum", 0.9)), eps)
+                        l.params[2] = rm.reshape(l.params[2].shape)
+                        l.params[3] = rv.reshape(l.params[3].shape)
+                        self.bn_batch[l.name] = (bm, bv)
+                        extra["train"] = True
+                    else:
+                        y = bn_forward_test(x, l.params[0], l.params[1], l.params[2], l.params[3], eps)
                     # bf16 mirror: BN output is stored bf16 unless an in-place ReLU follows
                     # (then the rounding happens after the ReLU -- one fused epilogue).
                     nxt = self.layers[li + 1] if li + 1 < len(self.layers) else None
@@ -433,6 +494,7 @@ class RefNet:
                 method = p.get1("pool", "MAX")
                 osh = bs[0][:2] + pool_out_shape(bs[0][2:], k, s, pd)
                 if not shapes_only:
+                    extra.update(k=k, s=s, pd=pd, method=method)
                     y = pool_forward(blobs[l.bottoms[0]], k, s, pd, method)
                     # bf16 mirror: pooled maps stay bf16 feature maps; pools that collapse the
                     # whole map (global pools / segment consensus) feed fp32 vectors to the fc.
@@ -446,6 +508,7 @@ class RefNet:
                 osh = list(bs[0])
                 osh[axis] = sum(b[axis] for b in bs)
                 if not shapes_only:
+                    extra["axis"] = axis
                     blobs[l.tops[0]] = np.concatenate([blobs[b] for b in l.bottoms], axis=axis)
                 shp[l.tops[0]] = osh
             elif t == "Eltwise":
@@ -469,6 +532,7 @@ class RefNet:
                             b = old_val
                         else:
                             a = old_val
+                    extra["coeff"] = co
                     blobs[l.tops[0]] = eltwise_sum(a, b, co[0], co[1])
                 shp[l.tops[0]] = list(bs[0])
             elif t == "Reshape":
@@ -490,12 +554,24 @@ class RefNet:
                 order = [int(o) for o in l.msg.get1("permute_param").getall("order")]
                 order += [i for i in range(len(bs[0])) if i not in order]
                 if not shapes_only:
+                    extra["order"] = order
                     blobs[l.tops[0]] = permute(blobs[l.bottoms[0]], order)
                 shp[l.tops[0]] = [bs[0][o] for o in order]
             elif t == "Dropout":
                 if not shapes_only:
-                    assert self.phase == "TEST", "oracle runs TEST-phase dropout (identity) only"
-                    blobs[l.tops[0]] = blobs[l.bottoms[0]]
+                    if self.phase == "TEST":
+                        blobs[l.tops[0]] = blobs[l.bottoms[0]]
+                    else:
+                        # dropout_layer.cpp:33-49: Bernoulli(1-p) mask, survivors scaled by 1/(1-p).  caffe's RNG
+                        # stream is not reproducible outside caffe; a mask can be supplied (e.g. the device's)
+                        ratio = float((l.msg.get1("dropout_param") or _pt.Msg()).get1("dropout_ratio", 0.5))
+                        xin = blobs[l.bottoms[0]]
+                        mask = self._dropout_masks.get(l.name)
+                        if mask is None:
+                            mask = (self._rng.random(xin.shape) < (1.0 - ratio))
+                        mask = np.asarray(mask, np.float32).reshape(xin.shape)
+                        extra["mask"], extra["scale"] = mask, np.float32(1.0 / (1.0 - ratio))
+                        blobs[l.tops[0]] = (xin * mask * extra["scale"]).astype(np.float32)
                 shp[l.tops[0]] = list(bs[0])
             elif t == "InnerProduct":
                 p = l.msg.get1("inner_product_param")
@@ -519,9 +595,12 @@ class RefNet:
                     x = blobs[l.bottoms[0]].astype(np.float64)
                     lab = blobs[l.bottoms[1]].astype(np.int64).ravel()
                     if t == "SoftmaxWithLoss":
+                        # softmax_loss_layer.cpp:48-77: loss = -sum log(max(prob[label], FLT_MIN)) / count (normalize)
                         z = x - x.max(1, keepdims=True)
-                        logp = z - np.log(np.exp(z).sum(1, keepdims=True))
-                        blobs[l.tops[0]] = np.float32(-logp[np.arange(len(lab)), lab].mean()).reshape(())
+                        prob = np.exp(z) / np.exp(z).sum(1, keepdims=True)
+                        extra["prob"], extra["label"] = prob, lab
+                        pl = np.maximum(prob[np.arange(len(lab)), lab], np.finfo(np.float32).tiny)
+                        blobs[l.tops[0]] = np.float32(-np.log(pl).sum() / len(lab)).reshape(())
                     else:
                         topk = int((l.msg.get1("accuracy_param") or _pt.Msg()).get1("top_k", 1))
                         # accuracy_layer.cpp: label counted if among the top_k scores
@@ -547,6 +626,103 @@ class RefNet:
                 own.setdefault(k, v)
             return own
         return blobs
+
+
+    # ---- backward -----------------------------------------------------------------
+    def backward(self, top_diffs=None, loss_weight=1.0):
+        """Backward pass over the tape of the last fp32 forward(), layer by layer in reverse (Net::BackwardFromTo,
+        net.cpp:637-706).  Blob diffs accumulate over all consumers of a blob (what the auto-inserted Split
+        layers do, split_layer.cpp); in-place layers replace the diff of their blob.  Parameter diffs are returned
+        fresh (zero-initialised), i.e. one iteration with iter_size 1.
+        top_diffs: optional {blob: dL/dblob} seeds (default: loss layers seed themselves with loss_weight).
+        Returns (blob_diffs, param_diffs): {blob: array}, {layer: [arrays in blob order]}."""
+        diffs = {}
+        pdiffs = {}
+        data_blobs = set(self.inputs)
+        for l in self.layers:
+            if l.type in DATA_TYPES:
+                data_blobs.update(l.tops)
+        needs = set()  # blobs whose gradient is needed: everything downstream of a parameterised layer
+        for l, _, _ in self.tape:
+            if l.params or any(b in needs for b in l.bottoms):
+                needs.update(l.tops)
+        if top_diffs:
+            for k, v in top_diffs.items():
+                diffs[k] = _f32(v).copy()
+
+        def add(name, g, inplace=False):
+            if name in data_blobs or name not in needs:
+                return
+            if inplace or name not in diffs:
+                diffs[name] = _f32(g)
+            else:
+                diffs[name] = diffs[name] + g
+
+        for l, bots, extra in reversed(self.tape):
+            t = l.type
+            if t in DATA_TYPES or t == "Accuracy":
+                continue
+            if t == "SoftmaxWithLoss":
+                prob, lab = extra["prob"], extra["label"]
+                g = prob.copy()
+                g[np.arange(len(lab)), lab] -= 1.0
+                w = float(diffs.get(l.tops[0], loss_weight)) if l.tops[0] in diffs else loss_weight
+                add(l.bottoms[0], (g * (w / len(lab))).astype(np.float32).reshape(bots[0].shape))
+                continue
+            top = l.tops[0]
+            if top not in diffs:
+                continue  # nothing flows back through this layer
+            dy = diffs[top]
+            inplace = l.bottoms and l.bottoms[0] == top
+            x = bots[0] if bots else None
+            if t == "Convolution":
+                need_dx = l.bottoms[0] in needs and l.bottoms[0] not in data_blobs
+                dx, dw, db = conv_backward(x, l.params[0], dy, extra["k"], extra["s"], extra["pd"], need_dx, extra["bias"])
+                pdiffs[l.name] = [dw] + ([db] if extra["bias"] else [])
+                if need_dx:
+                    add(l.bottoms[0], dx)
+            elif t == "BN":
+                bp = l.msg.get1("bn_param") or _pt.Msg()
+                eps = float(bp.get1("eps", 1e-5))
+                if extra.get("train"):
+                    bm, bv = self.bn_batch[l.name]
+                    dx, ds, dbias = bn_backward_train(x, dy, l.params[0], bm, bv, eps)
+                    pdiffs[l.name] = [ds.reshape(l.params[0].shape), dbias.reshape(l.params[1].shape),
+                                      np.zeros_like(l.params[2]), np.zeros_like(l.params[3])]
+                else:  # frozen / TEST statistics: dx = dy * slope / sqrt(var + eps)   (bn_layer.cpp:213-239)
+                    sc = (l.params[0].ravel() * np.power(l.params[3].ravel() + np.float32(eps), np.float32(-0.5)))
+                    dx = dy * sc.reshape([1, -1] + [1] * (dy.ndim - 2)).astype(np.float32)
+                add(l.bottoms[0], dx, inplace)
+            elif t == "ReLU":
+                slope = float((l.msg.get1("relu_param") or _pt.Msg()).get1("negative_slope", 0.0))
+                add(l.bottoms[0], (dy * ((x > 0) + slope * (x <= 0))).astype(np.float32), inplace)  # relu_layer.cpp:24-38
+            elif t == "Pooling":
+                add(l.bottoms[0], pool_backward(x, dy, extra["k"], extra["s"], extra["pd"], extra["method"]))
+            elif t == "Concat":
+                off = 0
+                for b, arr in zip(l.bottoms, bots):
+                    n = arr.shape[extra["axis"]]
+                    add(b, np.ascontiguousarray(np.take(dy, range(off, off + n), axis=extra["axis"])))
+                    off += n
+            elif t == "Eltwise":
+                for b, c in zip(l.bottoms, extra["coeff"]):
+                    add(b, dy * np.float32(c))
+            elif t == "Reshape":
+                add(l.bottoms[0], dy.reshape(x.shape))
+            elif t == "Permute":
+                add(l.bottoms[0], np.ascontiguousarray(np.transpose(dy, np.argsort(extra["order"]))))
+            elif t == "Dropout":
+                add(l.bottoms[0], dy * extra["mask"] * extra["scale"] if "mask" in extra else dy, inplace)
+            elif t == "InnerProduct":
+                m = x.shape[0]
+                x2, dy2 = x.reshape(m, -1), dy.reshape(m, -1)
+                pdiffs[l.name] = [(dy2.T @ x2).astype(np.float32)] + ([dy2.sum(0).astype(np.float32)] if len(l.params) > 1 else [])
+                add(l.bottoms[0], (dy2 @ l.params[0]).astype(np.float32).reshape(x.shape))   # inner_product_layer.cpp:96-120
+            elif t == "Softmax":
+                raise NotImplementedError("oracle backward: plain Softmax is not on the training path")
+            else:
+                raise NotImplementedError("oracle backward: layer type %s (%s)" % (t, l.name))
+        return diffs, pdiffs
 
 
 def eco_input(batch_videos, segments, seed=1234, size=224):
