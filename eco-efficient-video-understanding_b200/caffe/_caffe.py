@@ -18,6 +18,11 @@ class OpTime(C.Structure):
                 ("bytes", C.c_double)]
 
 
+class ParamSlot(C.Structure):
+    _fields_ = [("layer", C.c_int), ("blob", C.c_int), ("offset", C.c_size_t), ("count", C.c_size_t),
+                ("lr_mult", C.c_float), ("decay_mult", C.c_float)]
+
+
 def lib():
     """Load the CUDA library.  There is deliberately no fallback: without it nothing can run."""
     global _lib
@@ -61,6 +66,14 @@ def lib():
     L.eco_net_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.eco_net_backward.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.eco_net_sync.argtypes = [C.c_void_p]
+    L.eco_net_clear_param_diffs.argtypes = [C.c_void_p]
+    L.eco_net_param_diff_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t)]
+    L.eco_net_param_arena.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.eco_net_grad_arena.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.eco_net_num_param_slots.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.eco_net_param_slot.argtypes = [C.c_void_p, C.c_int, C.POINTER(ParamSlot)]
+    L.eco_net_params_updated_on_device.argtypes = [C.c_void_p]
+    L.eco_net_cuda_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.eco_blob_host_data.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
                                      C.POINTER(C.c_size_t)]
     L.eco_blob_host_diff.argtypes = L.eco_blob_host_data.argtypes
@@ -138,10 +151,18 @@ class Blob(object):
 
     @property
     def diff(self):
+        """fp32 view of the gradient (synced from the device after Net.backward()).  To SEED a backward pass write the
+        gradient with set_diff() or pass it to Net.backward(**{blob: array}) -- that is what marks it as newer on the host."""
+        p = C.POINTER(C.c_float)()
+        n = C.c_size_t()
+        check(lib().eco_blob_host_diff(self._net._h, self._i, 0, C.byref(p), C.byref(n)))
+        return _view(p, n.value, self.shape, self._net)
+
+    def set_diff(self, arr):
         p = C.POINTER(C.c_float)()
         n = C.c_size_t()
         check(lib().eco_blob_host_diff(self._net._h, self._i, 1, C.byref(p), C.byref(n)))
-        return _view(p, n.value, self.shape, self._net)
+        _view(p, n.value, self.shape, self._net)[...] = arr
 
 
 class ParamBlob(object):
@@ -170,7 +191,11 @@ class ParamBlob(object):
 
     @property
     def diff(self):
-        return np.zeros(self.shape, np.float32)
+        """parameter gradient (layer.blobs[i].diff), synced from the device gradient arena"""
+        p = C.POINTER(C.c_float)()
+        n = C.c_size_t()
+        check(lib().eco_net_param_diff_host(self._net._h, self._l, self._k, C.byref(p), C.byref(n)))
+        return _view(p, n.value, self.shape, self._net)
 
     num = property(lambda self: (tuple(self.shape) + (1, 1, 1, 1))[0])
     channels = property(lambda self: (tuple(self.shape) + (1, 1, 1, 1))[1])

@@ -127,10 +127,94 @@ class Net(object):
         return {out: allb[out].data for out in outputs}
 
     def backward(self, diffs=None, start=None, end=None, **kwargs):
+        """pycaffe.py:117-160: backward pass; kwargs = {top blob: diff} seeds, returns {blob: diff} for the net inputs
+        that carry a gradient plus the blobs named in `diffs`.  TRAIN-phase nets only."""
+        diffs = list(diffs or [])
         start_ind = self._layer_names.index(start) if start is not None else len(self.layers) - 1
-        end_ind = self._layer_names.index(end) if end is not None else 0
+        if end is not None:
+            end_ind = self._layer_names.index(end)
+            outputs = set([end] + diffs)
+        else:
+            end_ind = 0
+            outputs = set(self.inputs + diffs)
+        allb = self.blobs
+        if kwargs:
+            for top, arr in kwargs.items():
+                if top not in allb:
+                    raise Exception("Top diff arguments do not match net outputs / blobs.")
+                if arr.shape[0] != allb[top].shape[0]:
+                    raise Exception("Diff is not batch sized")
+                allb[top].set_diff(arr)
         self._backward(start_ind, end_ind)
-        return {}
+        out = {}
+        for name in outputs:
+            if name in allb:
+                try:
+                    out[name] = allb[name].diff
+                except RuntimeError:
+                    pass
+        return out
+
+    def clear_param_diffs(self):
+        check(lib().eco_net_clear_param_diffs(self._h))
+
+    def forward_backward_all(self, blobs=None, diffs=None, **kwargs):
+        """pycaffe.py:186-240, batch-wise forward + backward; kwargs hold inputs (and optionally top diffs) by name."""
+        all_outs = {out: [] for out in set(self.outputs + list(blobs or []))}
+        all_diffs = {d: [] for d in set(self.inputs + list(diffs or []))}
+        fkw = {k: v for k, v in kwargs.items() if k in self.inputs}
+        bkw = {k: v for k, v in kwargs.items() if k in self.outputs}
+        n = len(next(iter(fkw.values())))
+        fb = list(self._batch(fkw))
+        bb = list(self._batch(bkw)) if bkw else [{}] * len(fb)
+        for fbatch, bbatch in zip(fb, bb):
+            outs = self.forward(blobs=blobs, **fbatch)
+            dd = self.backward(diffs=diffs, **bbatch)
+            for out, arr in outs.items():
+                all_outs[out].extend(np.atleast_1d(arr).copy())
+            for d, arr in dd.items():
+                if d in all_diffs:
+                    all_diffs[d].extend(arr.copy())
+        for out in all_outs:
+            all_outs[out] = np.asarray(all_outs[out])[:n]
+        for d in all_diffs:
+            all_diffs[d] = np.asarray(all_diffs[d])[:n]
+        return all_outs, all_diffs
+
+    def set_input_arrays(self, data, labels):
+        """pycaffe.py:243-254 (MemoryData helper): fill the first two net inputs"""
+        if labels.ndim == 1:
+            labels = np.ascontiguousarray(labels[:, np.newaxis, np.newaxis, np.newaxis])
+        names = self.inputs
+        self.blobs[names[0]].data[...] = data
+        self.blobs[names[1]].data[...] = labels.reshape(self.blobs[names[1]].shape)
+
+    # device-resident training state (extensions used by the solver / the gradient all-reduce)
+    def arenas(self):
+        """(param_ptr, grad_ptr, count): fp32 device arenas holding every parameter blob / its gradient in layer order"""
+        p, g, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        check(lib().eco_net_param_arena(self._h, C.byref(p), C.byref(n)))
+        check(lib().eco_net_grad_arena(self._h, C.byref(g), C.byref(n)))
+        return p.value, g.value, n.value
+
+    def param_slots(self):
+        n = C.c_int()
+        check(lib().eco_net_num_param_slots(self._h, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            sl = _caffe.ParamSlot()
+            check(lib().eco_net_param_slot(self._h, i, C.byref(sl)))
+            out.append(dict(layer=self._layer_names[sl.layer], blob=sl.blob, offset=sl.offset, count=sl.count,
+                            lr_mult=sl.lr_mult, decay_mult=sl.decay_mult))
+        return out
+
+    def params_updated_on_device(self):
+        check(lib().eco_net_params_updated_on_device(self._h))
+
+    def cuda_stream(self):
+        s = C.c_void_p()
+        check(lib().eco_net_cuda_stream(self._h, C.byref(s)))
+        return s.value or 0
 
     def forward_all(self, blobs=None, **kwargs):
         all_outs = {out: [] for out in set(self.outputs + list(blobs or []))}

@@ -146,6 +146,7 @@ void put_bytes(std::string& o, int field, const std::string& s) {
 }  // namespace
 
 void Net::copy_from(const std::string& path) {
+  if (params_dev_newer_) sync_params_to_host();
   std::ifstream f(path, std::ios::binary);
   if (!f) throw std::runtime_error("Could not open " + path);
   std::string buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
@@ -201,6 +202,7 @@ void Net::copy_from(const std::string& path) {
 }
 
 void Net::save(const std::string& path) const {
+  if (params_dev_newer_) const_cast<Net*>(this)->sync_params_to_host();  // training updated the device arena
   std::string out;
   put_bytes(out, 1, name_);
   for (const auto& L : layers_) {

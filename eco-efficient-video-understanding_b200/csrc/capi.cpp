@@ -240,10 +240,56 @@ int eco_net_forward(eco_net* net, int start, int end, float* loss) {
 }
 int eco_net_backward(eco_net* net, int start, int end) {
   ECO_API_BEGIN
-  (void)start;
-  (void)end;
-  N(net);
-  throw std::runtime_error("Backward is not implemented in this round (training config is a later row of SURVEY.md section 8)");
+  if (!g_mode_gpu)
+    throw std::runtime_error("set_mode_cpu() was requested: libeco_b200 has no CPU execution path (call set_mode_gpu())");
+  N(net).backward(start, end);
+  ECO_API_END
+}
+int eco_net_clear_param_diffs(eco_net* net) {
+  ECO_API_BEGIN
+  N(net).clear_param_diffs();
+  ECO_API_END
+}
+int eco_net_param_diff_host(eco_net* net, int layer, int idx, float** data, size_t* count) {
+  ECO_API_BEGIN
+  *data = N(net).param_diff_host(layer, idx, count);
+  ECO_API_END
+}
+int eco_net_param_arena(eco_net* net, float** dev, size_t* count) {
+  ECO_API_BEGIN
+  *dev = N(net).param_arena(count);
+  ECO_API_END
+}
+int eco_net_grad_arena(eco_net* net, float** dev, size_t* count) {
+  ECO_API_BEGIN
+  *dev = N(net).grad_arena(count);
+  ECO_API_END
+}
+int eco_net_num_param_slots(eco_net* net, int* n) {
+  ECO_API_BEGIN
+  *n = (int)N(net).param_slots().size();
+  ECO_API_END
+}
+int eco_net_param_slot(eco_net* net, int i, eco_param_slot* out) {
+  ECO_API_BEGIN
+  const auto& sl = N(net).param_slots();
+  if (i < 0 || i >= (int)sl.size()) throw std::runtime_error("parameter slot index out of range");
+  out->layer = N(net).layers_[sl[i].layer].vis_index;
+  out->blob = sl[i].idx;
+  out->offset = sl[i].off;
+  out->count = sl[i].count;
+  out->lr_mult = sl[i].lr_mult;
+  out->decay_mult = sl[i].decay_mult;
+  ECO_API_END
+}
+int eco_net_params_updated_on_device(eco_net* net) {
+  ECO_API_BEGIN
+  N(net).params_updated_on_device();
+  ECO_API_END
+}
+int eco_net_cuda_stream(eco_net* net, void** stream) {
+  ECO_API_BEGIN
+  *stream = static_cast<void*>(N(net).stream());
   ECO_API_END
 }
 int eco_net_sync(eco_net* net) {

@@ -569,6 +569,7 @@ int Net::num_params(int vl) const {
   return o < 0 ? 0 : (int)layers_[o].params.size();
 }
 ParamBlob& Net::param(int vl, int idx) {
+  if (params_dev_newer_) sync_params_to_host();
   ECO_CHECK(vl >= 0 && vl < (int)vis_layers_.size(), "layer index out of range");
   const int o = vis_layers_[vl].orig;
   ECO_CHECK(o >= 0 && idx >= 0 && idx < (int)layers_[o].params.size(),
@@ -610,6 +611,7 @@ void Net::ensure_device() {
     ECO_CHECK(prop.major == 10, "libeco_b200 is built for sm_100a only; device is sm_" << prop.major << prop.minor);
     CUDA_OK(conv_umma_configure());
     CUDA_OK(aux_kernels_configure());
+    CUDA_OK(wgrad_umma_configure());
     sms[dev] = prop.multiProcessorCount;
     configured[dev] = true;
   }
@@ -626,6 +628,10 @@ void* Net::dalloc(size_t bytes, bool zero) {
 }
 
 void Net::free_plan() {
+  if (params_dev_newer_ && P_) {  // keep what training changed on the device (weights, BN running statistics)
+    try { sync_params_to_host(); } catch (...) {}
+    params_dev_newer_ = false;
+  }
   if (graph_exec_) {
     cudaGraphExecDestroy(graph_exec_);
     graph_exec_ = nullptr;
@@ -652,6 +658,16 @@ void Net::free_plan() {
   }
   ops_.clear();
   convs_.clear();
+  aux_.clear();
+  dgrads_.clear();
+  P_ = G_ = nullptr;
+  arena_count_ = 0;
+  slots_.clear();
+  slot_index_.clear();
+  wgrad_scratch_ = nullptr;
+  wgrad_scratch_bytes_ = 0;
+  params_dev_newer_ = false;
+  repack_ = true;
   error_flag_dev_ = nullptr;
   for (auto& t : tensors_) {
     t.dev = nullptr;
@@ -662,6 +678,9 @@ void Net::free_plan() {
     t.cs = 0;
     t.coff = 0;
     t.dev_newer = false;
+    t.ddev = nullptr;
+    t.needs_grad = false;
+    t.diff_dev_newer = false;
   }
   for (auto& L : layers_) L.params_dirty = true;
   planned_ = false;
@@ -1193,6 +1212,15 @@ void Net::plan() {
   ensure_device();
   infer_shapes();
   const int NL = (int)layers_.size();
+  // TRAIN-phase nets run the training plan: every blob is materialised (the backward pass reads the activations),
+  // the fast-plan rewrites stay off, BN uses batch statistics, Dropout draws a mask, and plan_train() adds the
+  // parameter / gradient arenas and the backward state of every op.
+  train_ = phase_ == ECO_PHASE_TRAIN;
+  struct KeepAllGuard {
+    bool& ref; bool saved;
+    KeepAllGuard(bool& r, bool force) : ref(r), saved(r) { if (force) ref = true; }
+    ~KeepAllGuard() { ref = saved; }
+  } keep_all_guard(keep_all_, train_);
 
   // ---- 1. kinds ----
   for (auto& t : tensors_) {
@@ -1216,7 +1244,7 @@ void Net::plan() {
     } else if (t == "BN" || t == "ReLU" || t == "Dropout" || t == "Eltwise") {
       top.kind = b0->kind;
       top.ch_axis = b0->ch_axis;
-      if (t == "Dropout" && L.tops[0] != L.bottoms[0]) view_of[L.tops[0]] = L.bottoms[0];
+      if (t == "Dropout" && L.tops[0] != L.bottoms[0] && !train_) view_of[L.tops[0]] = L.bottoms[0];
       if (t == "Eltwise")
         for (int b : L.bottoms) ECO_CHECK(tensors_[b].kind == b0->kind, "Eltwise " << L.name << " mixes layouts");
     } else if (t == "Pooling") {
@@ -1322,7 +1350,7 @@ void Net::plan() {
       if (t == "BN") {
         const pt::Msg* bp = L.msg->msg("bn_param");
         const bool frozen = bp ? bp->boolean("frozen", false) : false;
-        ECO_CHECK(phase_ == ECO_PHASE_TEST || frozen, "TRAIN-phase BN (batch statistics) is not implemented in this round");
+        if (!(phase_ == ECO_PHASE_TEST || frozen)) op.type = Op::BN_TRAIN;  // batch statistics (bn_layer.cpp:107-157)
         const auto& yc = tensors_[op.out].consumers;
         for (int ci : yc)
           if (ci > li && is_inplace_relu(layers_[ci], op.out) && !done[ci]) {
@@ -1373,8 +1401,27 @@ void Net::plan() {
         ops_.push_back(op);
       }
       done[li] = true;
+    } else if (t == "Dropout" && train_) {
+      ECO_CHECK(tensors_[L.bottoms[0]].kind == Kind::F32, "Dropout " << L.name << " on a feature map is outside ECO's path "
+                                                                              "(ECO drops the pooled vector)");
+      op.type = Op::DROPOUT;
+      op.in0 = L.bottoms[0];
+      op.out = L.tops[0];
+      tensors_[op.out].materialized = true;
+      done[li] = true;
+      ops_.push_back(op);
+    } else if (t == "SoftmaxWithLoss" || t == "Accuracy") {
+      ECO_CHECK(L.bottoms.size() >= 2 && !L.tops.empty(), t << " " << L.name << " needs scores, labels and a top");
+      ECO_CHECK(tensors_[L.bottoms[0]].kind == Kind::F32 && tensors_[L.bottoms[0]].shape.size() == 2,
+                t << " " << L.name << ": scores must be a plain [N, classes] blob");
+      op.type = t == "Accuracy" ? Op::ACCURACY : Op::LOSS;
+      op.in0 = L.bottoms[0];
+      op.in1 = L.bottoms[1];
+      op.out = L.tops[0];
+      tensors_[op.out].materialized = true;
+      done[li] = true;
+      ops_.push_back(op);
     } else if (t == "Permute" || t == "Dropout" || t == "Split") {
-      ECO_CHECK(t != "Dropout" || phase_ == ECO_PHASE_TEST, "TRAIN-phase Dropout is not implemented in this round");
       done[li] = true;
     } else if (t == "InnerProduct") {
       ECO_CHECK(tensors_[L.bottoms[0]].kind == Kind::F32,
@@ -1872,6 +1919,26 @@ void Net::plan() {
         break;
     }
   }
+  aux_.assign(ops_.size(), TrainAux{});
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    Op& op = ops_[i];
+    if (op.type == Op::LOSS || op.type == Op::ACCURACY) {
+      const Tensor& x = tensors_[op.in0];
+      TrainAux& a = aux_[i];
+      const OrigLayer& L = layers_[op.layer];
+      if (op.type == Op::LOSS) {
+        const pt::Msg* lp = L.msg->msg("loss_param");
+        ECO_CHECK(!lp || (!lp->has("ignore_label") && lp->boolean("normalize", true)),
+                  "SoftmaxWithLoss " << L.name << ": ignore_label / normalize:false are not used on ECO's path");
+        a.loss_weight = (float)L.msg->num("loss_weight", 1.0);  // loss layers default to weight 1 (loss_layer.cpp)
+        a.prob = static_cast<float*>(dalloc((size_t)std::max<long long>(x.count(), 1) * 4, true));
+      } else {
+        const pt::Msg* ap = L.msg->msg("accuracy_param");
+        a.top_k = ap ? (int)ap->integer("top_k", 1) : 1;
+      }
+    }
+  }
+  if (train_) plan_train();
   CUDA_OK(cudaStreamSynchronize(stream_));
   planned_ = true;
 }
@@ -1887,6 +1954,7 @@ static inline uint16_t f2bf(float f) {
 }
 
 void Net::upload_params() {
+  if (train_) { upload_params_train(); return; }
   bool any = false;
   for (auto& L : layers_) any |= L.params_dirty;
   if (!any) return;
@@ -2079,7 +2147,21 @@ float* Net::host_diff(int vb, bool for_write, size_t* count) {
   Tensor& t = tensors_[vis_blobs_[vb].tensor];
   const size_t n = (size_t)t.count();
   if (t.host_diff.n != n) t.host_diff.resize(n, false);
-  (void)for_write;
+  if (planned_ && train_ && t.ddev && t.diff_dev_newer && n) {
+    // cpu_diff(): bring the device gradient over (fp32, caffe layout)
+    if (t.kind == Kind::CL) {
+      float* st = staging(n * 4);
+      ClView v = view(t);
+      v.ptr = static_cast<__nv_bfloat16*>(t.ddev);
+      CUDA_OK(launch_cl_to_f32(v, st, stream_));
+      CUDA_OK(cudaMemcpyAsync(t.host_diff.p, st, n * 4, cudaMemcpyDeviceToHost, stream_));
+    } else {
+      CUDA_OK(cudaMemcpyAsync(t.host_diff.p, t.ddev, n * 4, cudaMemcpyDeviceToHost, stream_));
+    }
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    t.diff_dev_newer = false;
+  }
+  if (for_write) t.diff_host_newer = true;  // mutable_cpu_diff(): the next Backward starts from this gradient
   if (count) *count = n;
   return t.host_diff.p;
 }
@@ -2206,6 +2288,12 @@ void Net::run_op(Op& op, bool with_xform) {
     case Op::F32_TO_CL:
       CUDA_OK(launch_f32_to_cl(static_cast<const float*>(tensors_[op.in0].dev), view(tensors_[op.out]), stream_));
       break;
+    case Op::BN_TRAIN:
+    case Op::DROPOUT:
+    case Op::LOSS:
+    case Op::ACCURACY:
+      run_train_op(op, aux_[&op - ops_.data()]);
+      break;
     case Op::SOFTMAX:
       CUDA_OK(launch_softmax_f32(static_cast<const float*>(tensors_[op.in0].dev), static_cast<float*>(tensors_[op.out].dev),
                                  tensors_[op.in0].shape[0], (int)(tensors_[op.in0].count() / std::max(1, tensors_[op.in0].shape[0])),
@@ -2226,7 +2314,7 @@ void Net::mark_written(int tid) {
 // outside the graph so their source pointer can change from call to call.
 void Net::run_ops(bool full, int lo, int hi, const float* input_override, int* launches) {
   int n = 0;
-  if (full && use_graph_) {
+  if (full && use_graph_ && !train_) {
     for (auto& op : ops_)
       if (op.type == Op::CONV && convs_[op.conv].stem_in) run_input_xform(convs_[op.conv], input_override);
     if (!graph_valid_) {
@@ -2354,19 +2442,37 @@ float Net::forward(int start, int end) {
     if (t.host_newer && t.root >= 0) upload(t);
   for (int vb : inputs_) tensors_[vis_blobs_[vb].tensor].dev_newer = false;
 
+  if (train_) ++train_iter_;  // a new dropout mask per forward pass
   int launches = 0;
   run_ops(full, lo, hi, nullptr, &launches);
   last_launches_ = launches;
-  return 0.f;
+  // loss = sum over loss layers of loss_weight * top (Net::ForwardFromTo, net.cpp:566-583); reading it synchronises
+  float loss = 0.f;
+  bool any_loss = false;
+  for (size_t i = 0; i < ops_.size(); ++i)
+    if (ops_[i].type == Op::LOSS && !(ops_[i].last_layer < lo || ops_[i].first_layer > hi)) any_loss = true;
+  if (any_loss) {
+    if (!loss_host_) CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&loss_host_), 64 * sizeof(float)));
+    int k = 0;
+    for (size_t i = 0; i < ops_.size() && k < 64; ++i)
+      if (ops_[i].type == Op::LOSS)
+        CUDA_OK(cudaMemcpyAsync(loss_host_ + k++, tensors_[ops_[i].out].dev, 4, cudaMemcpyDeviceToHost, stream_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    k = 0;
+    for (size_t i = 0; i < ops_.size() && k < 64; ++i)
+      if (ops_[i].type == Op::LOSS) loss += aux_[i].loss_weight * loss_host_[k++];
+  }
+  last_loss_ = loss;
+  return loss;
 }
 
 std::string Net::describe_plan() {
   if (!planned_) plan();
   std::ostringstream o;
   static const char* tn[] = {"conv", "pool_cl", "global_avg", "pool_f32", "fc", "ssr", "eltwise", "copy2d", "cl_to_f32",
-                             "f32_to_cl", "softmax"};
+                             "f32_to_cl", "softmax", "bn_train", "dropout", "loss", "accuracy"};
   for (const Op& op : ops_) {
-    o << op.name << " type=" << ((int)op.type < 11 ? tn[(int)op.type] : "train");
+    o << op.name << " type=" << tn[(int)op.type];
     if (op.type == Op::CONV) {
       const ConvOp& c = convs_[op.conv];
       const ConvKernelParams& k = c.pair ? c.kpp : c.kp;
@@ -2413,5 +2519,7 @@ int Net::profile(eco_op_time* out, int cap) {
   for (auto& e : ev) cudaEventDestroy(e);
   return n;
 }
+
+#include "net_train.inc"
 
 }  // namespace eco

@@ -14,6 +14,8 @@
 #include "aux_kernels.cuh"
 #include "conv_umma.cuh"
 #include "prototxt.hpp"
+#include "train_kernels.cuh"
+#include "wgrad_umma.cuh"
 
 struct eco_op_time;
 
@@ -58,6 +60,11 @@ struct Tensor {
   HostBuf host, host_diff;
   bool host_newer = false;  // host written since the last upload
   bool dev_newer = false;   // device written since the last download
+  // gradient (TRAIN-phase nets): same layout as the data (bf16 channels-last view or plain fp32)
+  void* ddev = nullptr;
+  bool needs_grad = false;       // lies downstream of a parameter: Backward computes its diff
+  bool diff_host_newer = false;  // host_diff written by the caller (seed for backward)
+  bool diff_dev_newer = false;
   int producer = -1;        // orig layer index that (last) writes it, -1: net input
   std::vector<int> consumers;  // orig layer indices reading it, in order
 
@@ -155,8 +162,41 @@ struct ConvOp {
   double flops = 0, bytes = 0;
 };
 
+// one parameter blob inside the device arenas of a TRAIN-phase net (fp32 master weights / gradients, caffe layout)
+struct ParamSlot {
+  int layer = -1, idx = -1;
+  size_t off = 0, count = 0;           // in floats
+  float lr_mult = 1.f, decay_mult = 1.f;  // ParamSpec (caffe.proto), BN running statistics forced to 0 (bn_layer.cpp:46-53)
+};
+
+// backward state of one forward op
+struct TrainAux {
+  // BN TRAIN: saved batch statistics (bn_layer.cpp:183-188 keeps x_norm_ / x_inv_std_; x_norm is recomputed here)
+  float *mean = nullptr, *inv_std = nullptr, *batch_var = nullptr, *sums = nullptr;
+  float *slope = nullptr, *bias = nullptr, *run_mean = nullptr, *run_var = nullptr;  // into the parameter arena
+  float *dslope = nullptr, *dbias = nullptr;                                          // into the gradient arena
+  float momentum = 0.9f, eps = 1e-5f;
+  bool relu = false;
+  int x_tensor = -1, y_tensor = -1;
+  // convolution backward
+  bool has_dgrad = false, dilated = false;
+  int dg = -1;                      // index into dgrads_ (a ConvOp describing dX = conv(dY', flipped W^T))
+  __nv_bfloat16* dil = nullptr;     // zero-dilated dY for strided convolutions [NB, E..., Cout]
+  int E[3] = {1, 1, 1};
+  WgradParams wg{};
+  CUtensorMap tmY{};
+  float *dw = nullptr, *db = nullptr, *w_master = nullptr;
+  // dropout
+  float ratio = 0.f;
+  // loss / fc
+  float loss_weight = 1.f;
+  float* prob = nullptr;
+  int top_k = 1;
+};
+
 struct Op {
-  enum Type { CONV, POOL_CL, GLOBAL_AVG, POOL_F32, FC, SSR, ELTWISE, COPY2D, CL_TO_F32, F32_TO_CL, SOFTMAX };
+  enum Type { CONV, POOL_CL, GLOBAL_AVG, POOL_F32, FC, SSR, ELTWISE, COPY2D, CL_TO_F32, F32_TO_CL, SOFTMAX,
+              BN_TRAIN, DROPOUT, LOSS, ACCURACY };
   Type type;
   std::string name;
   int first_layer = 0, last_layer = 0;  // orig layer range covered
@@ -216,6 +256,18 @@ class Net {
   int last_launches() const { return last_launches_; }
   void copy_from(const std::string& path);
   void save(const std::string& path) const;
+  // ---- training path (train.cpp): Net::BackwardFromTo net.cpp:637-706, params()/diffs ----
+  void backward(int start, int end);
+  void clear_param_diffs();
+  float* param_diff_host(int vis_layer, int idx, size_t* count);
+  bool is_train() const { return train_; }
+  // device arenas (valid after the first forward / plan): all parameter blobs in layer order, fp32, caffe layout
+  float* param_arena(size_t* count);
+  float* grad_arena(size_t* count);
+  const std::vector<ParamSlot>& param_slots();
+  void params_updated_on_device();   // a solver changed the arena: repack the GEMM operands, host copies are stale
+  cudaStream_t stream();
+  float last_loss() const { return last_loss_; }
 
  private:
   std::shared_ptr<pt::Msg> proto_;
@@ -286,6 +338,31 @@ class Net {
   float* stage_ = nullptr;
   size_t stage_bytes_ = 0;
   float* staging(size_t bytes);
+  // training state
+  bool train_ = false;
+  float* P_ = nullptr;               // parameter arena
+  float* G_ = nullptr;               // gradient arena
+  size_t arena_count_ = 0;
+  std::vector<ParamSlot> slots_;
+  std::map<std::pair<int, int>, int> slot_index_;  // (orig layer, blob) -> slot
+  std::vector<TrainAux> aux_;        // parallel to ops_
+  std::vector<ConvOp> dgrads_;
+  float* wgrad_scratch_ = nullptr;
+  size_t wgrad_scratch_bytes_ = 0;
+  bool params_dev_newer_ = false;    // arena newer than the host ParamBlobs (solver update, BN running statistics)
+  bool repack_ = true;               // bf16 GEMM operands must be rebuilt from the arena
+  unsigned long long train_iter_ = 0;
+  float last_loss_ = 0.f;
+  float* loss_host_ = nullptr;       // pinned
+  void plan_train();
+  void upload_params_train();
+  void sync_params_to_host();
+  void setup_dgrad(Op& op, TrainAux& a);
+  void setup_wgrad(Op& op, TrainAux& a);
+  void run_train_op(Op& op, TrainAux& a);
+  void backward_op(size_t i, std::vector<char>& written);
+  ClView dview(const Tensor& t) const;
+  float* slot_ptr(float* arena, int layer, int idx);
   void download(Tensor& t);
   void upload(Tensor& t);
   ClView view(const Tensor& t) const;

@@ -1,0 +1,674 @@
+// train_kernels.cu -- HBM-bound kernels of the training path (sm_100a).  One pass per tensor, 16-byte accesses along
+// the channel axis of the channels-last maps, per-channel reductions as block partials + fp32 atomics.
+// Reference semantics, by kernel:
+//   BN TRAIN forward / backward   caffe_3d/src/caffe/layers/bn_layer.cpp:107-207, :241-335
+//   pooling backward              pooling_layer.cpp:280-377 (max_idx_ = first maximum, :206-222)
+//   dropout                       dropout_layer.cpp:33-75
+//   inner product backward        inner_product_layer.cpp:96-120
+//   softmax loss / accuracy       softmax_loss_layer.cpp:48-120, accuracy_layer.cpp:50-92
+//   solver update                 solver.cpp:637-797 (ClipGradients, Normalize, Regularize, ComputeUpdateValue), :820-860
+#include "train_kernels.cuh"
+
+#include <cfloat>
+
+namespace eco {
+namespace {
+
+constexpr int kT = 256;
+
+__device__ __forceinline__ void up8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+    f[2 * j] = __low2float(t);
+    f[2 * j + 1] = __high2float(t);
+  }
+}
+__device__ __forceinline__ uint4 pk8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+
+inline int grid_for(long long items, int cap_mult = 8) {
+  long long b = (items + kT - 1) / kT;
+  const long long cap = 148LL * cap_mult;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-channel reductions.  Thread t of a block owns channel group g = t % G (8 channels, one 16-byte load per row)
+// and walks rows r = first + t / G, + rows_per_block ...; partials are combined across the block's row lanes in
+// shared memory and added to the output with one atomic per channel and block.
+//   MODE 0: S1 = sum x                MODE 1: S1 = sum (x - mean)^2
+//   MODE 2: g = dy * (y > 0 if relu); S1 = sum g, S2 = sum g * (x - mean) * inv_std
+template <int MODE>
+__global__ void colreduce_cl_kernel(ClView x, ClView y, ClView dy, const float* __restrict__ mean,
+                                    const float* __restrict__ inv_std, int relu, float* __restrict__ out) {
+  extern __shared__ float red[];  // [lanes][G*8] (x2 for MODE 2)
+  const int G = x.C / 8;
+  const long long rows = x.outer * x.inner;
+  const int lanes = blockDim.x / G;  // row lanes per block (>= 1: launcher guarantees G <= blockDim.x)
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  float s1[8], s2[8], mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; mu[j] = 0.f; is[j] = 1.f; }
+  if (MODE >= 1 && lane < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = mean[g * 8 + j];
+      if (MODE == 2) is[j] = inv_std[g * 8 + j];
+    }
+  }
+  if (lane < lanes) {
+    for (long long r = (long long)blockIdx.x * lanes + lane; r < rows; r += (long long)gridDim.x * lanes) {
+      float xv[8];
+      up8(ld8(x.ptr + r * x.cs + x.coff + g * 8), xv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] += xv[j];
+      } else if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = xv[j] - mu[j]; s1[j] = fmaf(d, d, s1[j]); }
+      } else {
+        float gv[8], yv[8];
+        up8(ld8(dy.ptr + r * dy.cs + dy.coff + g * 8), gv);
+        if (relu) {
+          up8(ld8(y.ptr + r * y.cs + y.coff + g * 8), yv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += gv[j];
+          s2[j] = fmaf(gv[j], (xv[j] - mu[j]) * is[j], s2[j]);
+        }
+      }
+    }
+  }
+  const int C = x.C;
+  float* r1 = red;
+  float* r2 = red + (size_t)lanes * C;
+  if (lane < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      r1[(size_t)lane * C + g * 8 + j] = s1[j];
+      if (MODE == 2) r2[(size_t)lane * C + g * 8 + j] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      a += r1[(size_t)l * C + c];
+      if (MODE == 2) b += r2[(size_t)l * C + c];
+    }
+    atomicAdd(out + c, a);
+    if (MODE == 2) atomicAdd(out + C + c, b);
+  }
+}
+
+template <int MODE>
+cudaError_t launch_colreduce(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, int relu, float* out,
+                             cudaStream_t st) {
+  const long long rows = x.outer * x.inner;
+  if (rows == 0 || x.C == 0) return cudaSuccess;
+  if (x.C % 8 != 0) return cudaErrorInvalidValue;
+  const int G = x.C / 8;
+  int threads = 256;
+  while (threads < G) threads *= 2;
+  if (threads > 1024) return cudaErrorInvalidValue;  // C <= 8192
+  const int lanes = threads / G;
+  const size_t smem = (size_t)lanes * x.C * sizeof(float) * (MODE == 2 ? 2 : 1);
+  long long blocks = (rows + (long long)lanes * 8 - 1) / ((long long)lanes * 8);  // >= 8 rows per lane
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  colreduce_cl_kernel<MODE><<<(unsigned)blocks, threads, smem, st>>>(x, y, dy, mean, inv_std, relu, out);
+  return cudaGetLastError();
+}
+
+__global__ void bn_finish_mean_kernel(const float* __restrict__ sum, float* __restrict__ mean, int C, double count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) mean[c] = (float)((double)sum[c] / count);
+}
+__global__ void bn_finish_var_kernel(const float* __restrict__ sqdev, const float* __restrict__ mean, float* __restrict__ inv_std,
+                                     float* __restrict__ batch_var, float* __restrict__ run_mean, float* __restrict__ run_var,
+                                     int C, double count, float momentum, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float var = (float)((double)sqdev[c] / count);  // biased (bn_layer.cpp:141-151)
+  batch_var[c] = var;
+  run_mean[c] = (1.f - momentum) * mean[c] + momentum * run_mean[c];  // caffe_cpu_axpby(1 - m, batch, m, running)
+  run_var[c] = (1.f - momentum) * var + momentum * run_var[c];
+  inv_std[c] = powf(var + eps, -0.5f);
+}
+
+// elementwise over [rows][C/8] groups
+__global__ void bn_apply_cl_kernel(ClView x, ClView y, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                                   const float* __restrict__ slope, const float* __restrict__ bias, int relu) {
+  const int G = x.C / 8;
+  const long long total = x.outer * x.inner * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const long long r = t / G;
+    float v[8];
+    up8(ld8(x.ptr + r * x.cs + x.coff + g * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      float o = (v[j] - mean[c]) * inv_std[c];  // x_norm first, as bn_layer.cpp:132-181 orders it
+      o = o * slope[c] + bias[c];
+      v[j] = relu ? fmaxf(o, 0.f) : o;
+    }
+    *reinterpret_cast<uint4*>(y.ptr + r * y.cs + y.coff + g * 8) = pk8(v);
+  }
+}
+
+__global__ void bn_bwd_apply_cl_kernel(ClView x, ClView y, ClView dy, ClView dx, const float* __restrict__ mean,
+                                       const float* __restrict__ inv_std, const float* __restrict__ slope,
+                                       const float* __restrict__ sums, float inv_count, int relu, int accumulate) {
+  const int G = x.C / 8, C = x.C;
+  const long long total = x.outer * x.inner * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const long long r = t / G;
+    float xv[8], gv[8], o[8];
+    up8(ld8(x.ptr + r * x.cs + x.coff + g * 8), xv);
+    up8(ld8(dy.ptr + r * dy.cs + dy.coff + g * 8), gv);
+    if (relu) {
+      float yv[8];
+      up8(ld8(y.ptr + r * y.cs + y.coff + g * 8), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
+    }
+    if (accumulate) up8(ld8(dx.ptr + r * dx.cs + dx.coff + g * 8), o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      const float is = inv_std[c], sl = slope[c];
+      const float xn = (xv[j] - mean[c]) * is;
+      const float d = (sl * gv[j] - sl * sums[c] * inv_count - xn * (sl * sums[C + c] * inv_count)) * is;
+      o[j] = accumulate ? o[j] + d : d;
+    }
+    *reinterpret_cast<uint4*>(dx.ptr + r * dx.cs + dx.coff + g * 8) = pk8(o);
+  }
+}
+__global__ void bn_param_grads_kernel(const float* __restrict__ sums, float* __restrict__ dslope, float* __restrict__ dbias, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dslope) dslope[c] += sums[C + c];
+  if (dbias) dbias[c] += sums[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling backward, gather form: one thread per (input position, 8 channels)
+__global__ void pool_bwd_cl_kernel(const PoolParams p, const __nv_bfloat16* __restrict__ dy, long long dy_cs, int dy_coff,
+                                   __nv_bfloat16* __restrict__ dx, long long dx_cs, int dx_coff, int accumulate) {
+  const int G = p.C / 8;
+  const long long total = (long long)p.NB * p.ID * p.IH * p.IW * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long r = t / G;
+    const long long ipix = r;
+    const int ix = (int)(r % p.IW); r /= p.IW;
+    const int iy = (int)(r % p.IH); r /= p.IH;
+    const int iz = (int)(r % p.ID);
+    const long long n = r / p.ID;
+    // output windows that contain (iz, iy, ix): o*s - pad <= i < o*s - pad + K
+    const int oz_lo = max(0, (iz + p.pD - p.KD + p.sD) / p.sD), oz_hi = min(p.OD - 1, (iz + p.pD) / p.sD);
+    const int oy_lo = max(0, (iy + p.pH - p.KH + p.sH) / p.sH), oy_hi = min(p.OH - 1, (iy + p.pH) / p.sH);
+    const int ox_lo = max(0, (ix + p.pW - p.KW + p.sW) / p.sW), ox_hi = min(p.OW - 1, (ix + p.pW) / p.sW);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    float me[8];
+    if (p.is_max) up8(ld8(p.x + ipix * p.x_cs + p.x_coff + g * 8), me);
+    for (int oz = oz_lo; oz <= oz_hi; ++oz)
+      for (int oy = oy_lo; oy <= oy_hi; ++oy)
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          int z0 = oz * p.sD - p.pD, y0 = oy * p.sH - p.pH, x0 = ox * p.sW - p.pW;
+          const long long opix = ((n * p.OD + oz) * p.OH + oy) * p.OW + ox;
+          float gv[8];
+          up8(ld8(dy + opix * dy_cs + dy_coff + g * 8), gv);
+          if (!p.is_max) {
+            const int z1 = min(z0 + p.KD, p.ID + p.pD), y1 = min(y0 + p.KH, p.IH + p.pH), x1 = min(x0 + p.KW, p.IW + p.pW);
+            const float inv = 1.f / (float)((z1 - z0) * (y1 - y0) * (x1 - x0));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += gv[j] * inv;  // top_diff / pool_size (pooling_layer.cpp:352)
+            continue;
+          }
+          // MAX: this element receives the window's gradient iff it is the first maximum in scan order, i.e. it is
+          // >= every later element and > every earlier one (strictly-greater update, pooling_layer.cpp:206-222)
+          const int z1 = min(z0 + p.KD, p.ID), y1 = min(y0 + p.KH, p.IH), x1 = min(x0 + p.KW, p.IW);
+          z0 = max(z0, 0); y0 = max(y0, 0); x0 = max(x0, 0);
+          bool win[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) win[j] = true;
+          for (int z = z0; z < z1; ++z)
+            for (int yy = y0; yy < y1; ++yy)
+              for (int xx = x0; xx < x1; ++xx) {
+                if (z == iz && yy == iy && xx == ix) continue;
+                const bool earlier = (z < iz) || (z == iz && (yy < iy || (yy == iy && xx < ix)));
+                const long long q = ((n * p.ID + z) * p.IH + yy) * p.IW + xx;
+                float ov[8];
+                up8(ld8(p.x + q * p.x_cs + p.x_coff + g * 8), ov);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) win[j] = win[j] && (earlier ? me[j] > ov[j] : me[j] >= ov[j]);
+              }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (win[j]) acc[j] += gv[j];
+        }
+    __nv_bfloat16* o = dx + ipix * dx_cs + dx_coff + g * 8;
+    if (accumulate) {
+      float old[8];
+      up8(ld8(o), old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += old[j];
+    }
+    *reinterpret_cast<uint4*>(o) = pk8(acc);
+  }
+}
+
+__global__ void global_avg_bwd_cl_kernel(const float* __restrict__ dy, ClView dx, int accumulate) {
+  const int G = dx.C / 8;
+  const long long total = dx.outer * dx.inner * G;
+  const float inv = 1.f / (float)dx.inner;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const long long r = t / G;
+    const long long o = r / dx.inner;
+    float v[8];
+    __nv_bfloat16* d = dx.ptr + r * dx.cs + dx.coff + g * 8;
+    if (accumulate) up8(ld8(d), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gj = dy[o * dx.C + g * 8 + j] * inv;
+      v[j] = accumulate ? v[j] + gj : gj;
+    }
+    *reinterpret_cast<uint4*>(d) = pk8(v);
+  }
+}
+
+__global__ void cl_axpy_kernel(ClView x, ClView y, int accumulate) {
+  const int G = x.C / 8;
+  const long long total = x.outer * x.inner * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const long long r = t / G;
+    const uint4 xv = ld8(x.ptr + r * x.cs + x.coff + g * 8);
+    __nv_bfloat16* d = y.ptr + r * y.cs + y.coff + g * 8;
+    if (!accumulate) {
+      *reinterpret_cast<uint4*>(d) = xv;
+    } else {
+      float a[8], b[8];
+      up8(xv, a);
+      up8(ld8(d), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] += a[j];
+      *reinterpret_cast<uint4*>(d) = pk8(b);
+    }
+  }
+}
+__global__ void f32_axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a, int accumulate) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    y[t] = accumulate ? fmaf(a, x[t], y[t]) : a * x[t];
+}
+
+__global__ void dilate_cl_kernel(ClView s, int OD, int OH, int OW, __nv_bfloat16* __restrict__ dst, int ED, int EH, int EW,
+                                 int sD, int sH, int sW) {
+  const int G = s.C / 8;
+  const long long total = s.outer * s.inner * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long r = t / G;
+    const long long pix = r;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH); r /= OH;
+    const int oz = (int)(r % OD);
+    const long long n = r / OD;
+    const long long dpix = ((n * ED + (long long)oz * sD) * EH + (long long)oy * sH) * EW + (long long)ox * sW;
+    *reinterpret_cast<uint4*>(dst + dpix * s.C + g * 8) = ld8(s.ptr + pix * s.cs + s.coff + g * 8);
+  }
+}
+
+// counter-based RNG: one 64-bit mix (splitmix64 finaliser) per element; the same (seed, index) gives the same draw in
+// the forward and the backward pass, so no mask is stored
+__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+__global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, uint32_t thres, float scale,
+                                   uint64_t seed) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    y[t] = hash_u32(seed, (uint64_t)t) >= thres ? x[t] * scale : 0.f;  // keep with probability 1 - ratio
+}
+
+// ------------------------------------------------------------------------------------------------
+// inner product backward: dW[n][k] += sum_m dy[m][n] x[m][k]; db[n] += sum_m dy[m][n]; dx[m][k] (+)= sum_n dy[m][n] W[n][k]
+__global__ void ip_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                float* __restrict__ db, int M, int N, int K) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)N * K) return;
+  const int k = (int)(t % K), n = (int)(t / K);
+  float acc = 0.f;
+  for (int m = 0; m < M; ++m) acc = fmaf(dy[(long long)m * N + n], x[(long long)m * K + k], acc);
+  dw[t] += acc;
+  if (k == 0 && db) {
+    float b = 0.f;
+    for (int m = 0; m < M; ++m) b += dy[(long long)m * N + n];
+    db[n] += b;
+  }
+}
+__global__ void ip_bwd_x_kernel(const float* __restrict__ w, const float* __restrict__ dy, float* __restrict__ dx, int M, int N,
+                                int K, int accumulate) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)M * K) return;
+  const int k = (int)(t % K), m = (int)(t / K);
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) acc = fmaf(dy[(long long)m * N + n], w[(long long)n * K + k], acc);
+  dx[t] = accumulate ? dx[t] + acc : acc;
+}
+
+// one block per row
+__global__ void softmax_loss_fwd_kernel(const float* __restrict__ x, const float* __restrict__ label, float* __restrict__ prob,
+                                        float* __restrict__ loss, int M, int N) {
+  __shared__ float sred[32];
+  const int m = blockIdx.x;
+  const float* xp = x + (long long)m * N;
+  float mx = -FLT_MAX;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) mx = fmaxf(mx, xp[n]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = sred[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, sred[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) s += expf(xp[n] - mx);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sred[w];
+  for (int n = threadIdx.x; n < N; n += blockDim.x) prob[(long long)m * N + n] = expf(xp[n] - mx) / s;
+  if (threadIdx.x == 0) {
+    const int lab = (int)label[m];
+    const float p = (lab >= 0 && lab < N) ? expf(xp[lab] - mx) / s : 1.f;
+    atomicAdd(loss, -logf(fmaxf(p, FLT_MIN)) / (float)M);
+  }
+}
+__global__ void softmax_loss_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ label, float* __restrict__ dx,
+                                        int M, int N, float scale) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)M * N) return;
+  const int n = (int)(t % N), m = (int)(t / N);
+  dx[t] = (prob[t] - ((int)label[m] == n ? 1.f : 0.f)) * scale;
+}
+__global__ void accuracy_kernel(const float* __restrict__ x, const float* __restrict__ label, float* __restrict__ acc, int M, int N,
+                                int top_k) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int lab = (int)label[m];
+  if (lab < 0 || lab >= N) return;
+  const float v = x[(long long)m * N + lab];
+  int ahead = 0;  // entries ranked before the label by std::greater<pair<value, index>>
+  for (int n = 0; n < N; ++n) {
+    const float o = x[(long long)m * N + n];
+    if (o > v || (o == v && n > lab)) ++ahead;
+  }
+  if (ahead < top_k) atomicAdd(acc, 1.f / (float)M);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin, int taps,
+                                   int cblocks, long long Ktotal) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(t % taps);
+    const long long oc = t / taps;
+    const int ch = (int)(oc % Cin);
+    const long long o = oc / Cin;
+    dst[o * Ktotal + ((long long)tap * cblocks + ch / 64) * 64 + ch % 64] = __float2bfloat16_rn(w[t]);
+  }
+}
+__global__ void pack_stem_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, long long Ktotal) {
+  const long long total = (long long)Cout * 3 * 49;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int kx = (int)(t % 7), ky = (int)((t / 7) % 7), ch = (int)((t / 49) % 3);
+    const long long o = t / 147;
+    const int ty = ky >> 1, dy = ky & 1, tx = kx >> 1, dx = kx & 1;
+    dst[o * Ktotal + ty * 64 + tx * 16 + (dy * 2 + dx) * 3 + ch] = __float2bfloat16_rn(w[t]);
+  }
+}
+__global__ void pack_conv_w_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin, int KD,
+                                         int KH, int KW, int oblocks, long long Ktotal) {
+  const int taps = KD * KH * KW;
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(t % taps);
+    const long long oc = t / taps;
+    const int ch = (int)(oc % Cin);
+    const int o = (int)(oc / Cin);
+    const int ftap = taps - 1 - tap;  // flip every spatial axis
+    dst[(long long)ch * Ktotal + ((long long)ftap * oblocks + o / 64) * 64 + o % 64] = __float2bfloat16_rn(w[t]);
+  }
+}
+__global__ void wgrad_finish_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int Cout, int Cin, int taps,
+                                    int cin_ld, int cout_ld) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(t % taps);
+    const long long oc = t / taps;
+    const int ch = (int)(oc % Cin);
+    const int o = (int)(oc / Cin);
+    dw[t] += scratch[((long long)tap * cin_ld + ch) * cout_ld + o];
+  }
+}
+__global__ void wgrad_finish_stem_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int Cout, int cout_ld) {
+  const long long total = (long long)Cout * 147;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int kx = (int)(t % 7), ky = (int)((t / 7) % 7), ch = (int)((t / 49) % 3);
+    const int o = (int)(t / 147);
+    const int ty = ky >> 1, dy = ky & 1, tx = kx >> 1, dx = kx & 1;
+    // the stem GEMM sees a 4(h) x 1(w) filter over 64-value windows: tap = ty, "channel" = tx * 16 + cell value
+    dw[t] += scratch[((long long)ty * 64 + tx * 16 + (dy * 2 + dx) * 3 + ch) * cout_ld + o];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float sred[32];
+  float s = 0.f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    s = fmaf(x[t], x[t], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+__global__ void scale_kernel(float* __restrict__ x, long long n, const float* __restrict__ scale) {
+  const float a = *scale;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) x[t] *= a;
+}
+__global__ void clip_factor_kernel(const float* __restrict__ sumsq, float clip, float norm, float* __restrict__ scale) {
+  // ClipGradients runs on the accumulated (not yet iter_size-normalised) diffs, solver.cpp:637-660
+  (void)norm;
+  const float l2 = sqrtf(*sumsq);
+  *scale = (clip >= 0.f && l2 > clip) ? clip / l2 : 1.f;
+}
+__global__ void sgd_update_kernel(float* __restrict__ w, float* __restrict__ diff, float* __restrict__ hist, long long n, float rate,
+                                  float momentum, float decay, float norm, const float* __restrict__ clip_scale, int nesterov) {
+  const float cs = clip_scale ? *clip_scale : 1.f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    // solver.cpp: ClipGradients (scale_diff) -> Normalize (1 / iter_size) -> Regularize (L2) -> ComputeUpdateValue -> Update
+    const float g = diff[t] * cs * norm + decay * w[t];
+    const float h0 = hist[t];
+    const float h1 = momentum * h0 + rate * g;
+    hist[t] = h1;
+    const float upd = nesterov ? (1.f + momentum) * h1 - momentum * h0 : h1;
+    diff[t] = upd;  // caffe leaves the update value in the diff (Net::Update subtracts it)
+    w[t] -= upd;
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+cudaError_t launch_colsum_cl(ClView x, float* out, cudaStream_t st) {
+  return launch_colreduce<0>(x, x, x, nullptr, nullptr, 0, out, st);
+}
+cudaError_t launch_colsqdev_cl(ClView x, const float* mean, float* out, cudaStream_t st) {
+  return launch_colreduce<1>(x, x, x, mean, nullptr, 0, out, st);
+}
+cudaError_t launch_bn_bwd_sums_cl(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, int relu, float* out,
+                                  cudaStream_t st) {
+  return launch_colreduce<2>(x, y, dy, mean, inv_std, relu, out, st);
+}
+cudaError_t launch_bn_finish_mean(const float* sum, float* mean, int C, double count, cudaStream_t st) {
+  bn_finish_mean_kernel<<<(C + 127) / 128, 128, 0, st>>>(sum, mean, C, count);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_finish_var(const float* sqdev, const float* mean, float* inv_std, float* batch_var, float* run_mean,
+                                 float* run_var, int C, double count, float momentum, float eps, cudaStream_t st) {
+  bn_finish_var_kernel<<<(C + 127) / 128, 128, 0, st>>>(sqdev, mean, inv_std, batch_var, run_mean, run_var, C, count, momentum, eps);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_apply_cl(ClView x, ClView y, const float* mean, const float* inv_std, const float* slope,
+                               const float* bias, int relu, cudaStream_t st) {
+  const long long n = x.outer * x.inner * (x.C / 8);
+  if (n == 0) return cudaSuccess;
+  bn_apply_cl_kernel<<<grid_for(n, 16), kT, 0, st>>>(x, y, mean, inv_std, slope, bias, relu);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_bwd_apply_cl(ClView x, ClView y, ClView dy, ClView dx, const float* mean, const float* inv_std,
+                                   const float* slope, const float* sums, double count, int relu, int accumulate,
+                                   float* dslope, float* dbias, cudaStream_t st) {
+  const long long n = x.outer * x.inner * (x.C / 8);
+  if (n == 0) return cudaSuccess;
+  if (dx.ptr) bn_bwd_apply_cl_kernel<<<grid_for(n, 16), kT, 0, st>>>(x, y, dy, dx, mean, inv_std, slope, sums, (float)(1.0 / count), relu, accumulate);
+  if (dslope || dbias) bn_param_grads_kernel<<<(x.C + 127) / 128, 128, 0, st>>>(sums, dslope, dbias, x.C);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_bwd_cl(const PoolParams& p, const __nv_bfloat16* dy, long long dy_cs, int dy_coff, __nv_bfloat16* dx,
+                               long long dx_cs, int dx_coff, int accumulate, cudaStream_t st) {
+  const long long n = (long long)p.NB * p.ID * p.IH * p.IW * (p.C / 8);
+  if (n == 0) return cudaSuccess;
+  pool_bwd_cl_kernel<<<grid_for(n, 32), kT, 0, st>>>(p, dy, dy_cs, dy_coff, dx, dx_cs, dx_coff, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_global_avg_bwd_cl(const float* dy, ClView dx, int accumulate, cudaStream_t st) {
+  const long long n = dx.outer * dx.inner * (dx.C / 8);
+  if (n == 0) return cudaSuccess;
+  global_avg_bwd_cl_kernel<<<grid_for(n, 16), kT, 0, st>>>(dy, dx, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_cl_axpy(ClView x, ClView y, int accumulate, cudaStream_t st) {
+  const long long n = x.outer * x.inner * (x.C / 8);
+  if (n == 0) return cudaSuccess;
+  cl_axpy_kernel<<<grid_for(n, 16), kT, 0, st>>>(x, y, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_f32_axpy(const float* x, float* y, long long n, float a, int accumulate, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  f32_axpy_kernel<<<grid_for(n, 16), kT, 0, st>>>(x, y, n, a, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_dilate_cl(ClView src, int OD, int OH, int OW, __nv_bfloat16* dst, int ED, int EH, int EW, int sD, int sH,
+                             int sW, cudaStream_t st) {
+  const long long n = src.outer * src.inner * (src.C / 8);
+  if (n == 0) return cudaSuccess;
+  dilate_cl_kernel<<<grid_for(n, 16), kT, 0, st>>>(src, OD, OH, OW, dst, ED, EH, EW, sD, sH, sW);
+  return cudaGetLastError();
+}
+cudaError_t launch_dropout_f32(const float* x, float* y, long long n, float ratio, uint64_t seed, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  // uint_thres_ = UINT_MAX * threshold (dropout_layer.cpp:20-21); keep when the draw is >= it
+  const uint32_t thres = (uint32_t)((double)0xFFFFFFFFu * (double)ratio);
+  dropout_f32_kernel<<<grid_for(n, 8), kT, 0, st>>>(x, y, n, thres, 1.f / (1.f - ratio), seed);
+  return cudaGetLastError();
+}
+cudaError_t launch_inner_product_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int M,
+                                     int N, int K, int accumulate_dx, cudaStream_t st) {
+  if (dw) ip_bwd_w_kernel<<<(unsigned)(((long long)N * K + kT - 1) / kT), kT, 0, st>>>(x, dy, dw, db, M, N, K);
+  if (dx) ip_bwd_x_kernel<<<(unsigned)(((long long)M * K + kT - 1) / kT), kT, 0, st>>>(w, dy, dx, M, N, K, accumulate_dx);
+  return cudaGetLastError();
+}
+cudaError_t launch_softmax_loss_fwd(const float* x, const float* label, float* prob, float* loss, int M, int N, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  if (M == 0) return cudaSuccess;
+  softmax_loss_fwd_kernel<<<M, 128, 0, st>>>(x, label, prob, loss, M, N);
+  return cudaGetLastError();
+}
+cudaError_t launch_softmax_loss_bwd(const float* prob, const float* label, float* dx, int M, int N, float loss_weight,
+                                    cudaStream_t st) {
+  if (M == 0) return cudaSuccess;
+  softmax_loss_bwd_kernel<<<(unsigned)(((long long)M * N + kT - 1) / kT), kT, 0, st>>>(prob, label, dx, M, N, loss_weight / (float)M);
+  return cudaGetLastError();
+}
+cudaError_t launch_accuracy(const float* x, const float* label, float* acc, int M, int N, int top_k, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  if (M == 0) return cudaSuccess;
+  accuracy_kernel<<<(M + 127) / 128, 128, 0, st>>>(x, label, acc, M, N, top_k);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_conv_w(const float* w, __nv_bfloat16* dst, int Cout, int Cin, int taps, int cblocks, long long Ktotal,
+                               cudaStream_t st) {
+  pack_conv_w_kernel<<<grid_for((long long)Cout * Cin * taps, 16), kT, 0, st>>>(w, dst, Cout, Cin, taps, cblocks, Ktotal);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_stem_w(const float* w, __nv_bfloat16* dst, int Cout, long long Ktotal, cudaStream_t st) {
+  pack_stem_w_kernel<<<grid_for((long long)Cout * 147, 16), kT, 0, st>>>(w, dst, Cout, Ktotal);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_conv_w_dgrad(const float* w, __nv_bfloat16* dst, int Cout, int Cin, int KD, int KH, int KW, int oblocks,
+                                     long long Ktotal, cudaStream_t st) {
+  pack_conv_w_dgrad_kernel<<<grid_for((long long)Cout * Cin * KD * KH * KW, 16), kT, 0, st>>>(w, dst, Cout, Cin, KD, KH, KW, oblocks, Ktotal);
+  return cudaGetLastError();
+}
+cudaError_t launch_wgrad_finish(const float* scratch, float* dw, int Cout, int Cin, int taps, int cin_ld, int cout_ld,
+                                cudaStream_t st) {
+  wgrad_finish_kernel<<<grid_for((long long)Cout * Cin * taps, 16), kT, 0, st>>>(scratch, dw, Cout, Cin, taps, cin_ld, cout_ld);
+  return cudaGetLastError();
+}
+cudaError_t launch_wgrad_finish_stem(const float* scratch, float* dw, int Cout, int cout_ld, cudaStream_t st) {
+  wgrad_finish_stem_kernel<<<grid_for((long long)Cout * 147, 16), kT, 0, st>>>(scratch, dw, Cout, cout_ld);
+  return cudaGetLastError();
+}
+cudaError_t launch_sumsq(const float* x, long long n, float* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  sumsq_kernel<<<grid_for(n, 4), kT, 0, st>>>(x, n, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_scale(float* x, long long n, const float* scale_dev, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  scale_kernel<<<grid_for(n, 8), kT, 0, st>>>(x, n, scale_dev);
+  return cudaGetLastError();
+}
+cudaError_t launch_sgd_update(float* w, float* diff, float* hist, long long n, float rate, float momentum, float decay, float norm,
+                              const float* clip_scale_dev, int nesterov, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  sgd_update_kernel<<<grid_for(n, 8), kT, 0, st>>>(w, diff, hist, n, rate, momentum, decay, norm, clip_scale_dev, nesterov);
+  return cudaGetLastError();
+}
+cudaError_t launch_clip_factor(const float* sumsq, float clip, float norm, float* scale, cudaStream_t st) {
+  clip_factor_kernel<<<1, 1, 0, st>>>(sumsq, clip, norm, scale);
+  return cudaGetLastError();
+}
+
+}  // namespace eco

@@ -92,7 +92,30 @@ int eco_net_reshape(eco_net* net);
 
 /* ---- execution (Net::ForwardFromTo net.cpp:566-583, BackwardFromTo :637-706) ---- */
 int eco_net_forward(eco_net* net, int start, int end, float* loss);  /* layer indices as in caffe; end = -1: last */
-int eco_net_backward(eco_net* net, int start, int end);              /* training path: not in this round */
+/* Backward over visible layers start..end (start >= end, -1/-1 = whole net), TRAIN-phase nets only: fills the blob diffs
+ * and ACCUMULATES the parameter diffs (caffe's beta = 1, conv_layer.cpp:44-75); clear them with eco_net_clear_param_diffs
+ * (Solver::Step does that once per iteration, solver.cpp:178-195). */
+int eco_net_backward(eco_net* net, int start, int end);
+int eco_net_clear_param_diffs(eco_net* net);
+/* fp32 host copy of a parameter gradient (layer->blobs()[i]->cpu_diff()), synced from the device */
+int eco_net_param_diff_host(eco_net* net, int layer, int blob_idx, float** data, size_t* count);
+
+/* ---- device-resident training state (what Solver / the gradient all-reduce work on; net.cpp:670-702, solver.cpp:310-347) ----
+ * All parameter blobs of a TRAIN-phase net live in ONE fp32 device arena in layer order (caffe layout per blob), the
+ * gradients in a second arena of the same layout: a solver updates, and NCCL all-reduces, contiguous ranges of them. */
+typedef struct eco_param_slot {
+  int layer, blob;          /* visible layer index, blob index inside the layer */
+  size_t offset, count;     /* floats from the arena base */
+  float lr_mult, decay_mult; /* ParamSpec; BN running statistics are forced to 0 (bn_layer.cpp:46-53) */
+} eco_param_slot;
+int eco_net_param_arena(eco_net* net, float** dev, size_t* count);
+int eco_net_grad_arena(eco_net* net, float** dev, size_t* count);
+int eco_net_num_param_slots(eco_net* net, int* n);
+int eco_net_param_slot(eco_net* net, int i, eco_param_slot* out);
+/* tell the net that the parameter arena was changed on the device (solver step): GEMM operands are re-packed at the next
+ * forward and the host views are refreshed on access */
+int eco_net_params_updated_on_device(eco_net* net);
+int eco_net_cuda_stream(eco_net* net, void** cuda_stream);   /* the stream the net's kernels run on */
 int eco_net_sync(eco_net* net);                                      /* wait for the net's stream */
 
 /* ---- blob data (Blob::cpu_data / mutable_cpu_data / cpu_diff, SyncedMemory syncedmem.cpp:21-70) ---- */

@@ -207,6 +207,36 @@ def eco_lite_deploy(segments=16, classes=101, fc_name="fc8u", batch=5, dropout=0
     return o.f.getvalue()
 
 
+def eco_lite_train(segments=16, classes=400, fc_name="fc8", batch=17, dropout=0.3, net_name="o3d"):
+    """ECO-Lite train/test net (cf. models_ECO_Lite/kinetics/ECO_Lite.prototxt): the VideoData layer is replaced by the two
+    net inputs it would produce -- `data` [B, 3N, 224, 224] and `label` [B, 1, 1, 1] (the GPU data pipeline is SURVEY 8(f1)) --
+    then `reshape_data`, the same trunk / head / classifier as the deploy net, SoftmaxWithLoss in both phases and the two
+    Accuracy layers in TEST phase."""
+    o = _W()
+    o.w('name: "%s"' % net_name)
+    o.w('input: "data"')
+    for d in (batch, 3 * segments, 224, 224):
+        o.w("input_dim: %d" % d)
+    o.w('input: "label"')
+    for d in (batch, 1, 1, 1):
+        o.w("input_dim: %d" % d)
+    o.w('layer { name: "reshape_data" type: "Reshape" bottom: "data" top: "reshape_data" '
+        'reshape_param { shape { dim: -1 dim: 3 dim: 224 dim: 224 } } }')
+    t = _trunk_to_3c(o, "reshape_data")
+    t = _cbr2d(o, "inception_3c", "double_3x3_reduce", t, 64, 1)
+    t = _cbr2d(o, "inception_3c", "double_3x3_1", t, 96, 3, None, 1)
+    _head3d(o, t, segments)
+    _tail3d(o, segments, dropout)
+    _fc(o, fc_name, "global_pool_reshape", classes)
+    o.w('layer { name: "loss" type: "SoftmaxWithLoss" bottom: "fc8" bottom: "label" include { phase: TRAIN } top: "loss" }')
+    o.w('layer { name: "loss" type: "SoftmaxWithLoss" bottom: "fc8" bottom: "label" top: "loss" include { phase: TEST } }')
+    o.w('layer { name: "top1" type: "Accuracy" bottom: "fc8" bottom: "label" top: "top1" accuracy_param { top_k: 1 } '
+        'include { phase: TEST } }')
+    o.w('layer { name: "top5" type: "Accuracy" bottom: "fc8" bottom: "label" top: "top5" accuracy_param { top_k: 5 } '
+        'include { phase: TEST } }')
+    return o.f.getvalue()
+
+
 def eco_full_deploy(segments=16, classes=400, fc_name="fc8N", batch=5, dropout3d=0.5, dropout2d=0.6,
                     net_name="o3d"):
     """ECO-Full deploy net (cf. models_ECO_Full/kinetics/deploy.prototxt): the Lite graph plus
