@@ -2441,6 +2441,12 @@ float Net::forward(int start, int end) {
   for (auto& t : tensors_)
     if (t.host_newer && t.root >= 0) upload(t);
   for (int vb : inputs_) tensors_[vis_blobs_[vb].tensor].dev_newer = false;
+  // blobs that are views of an input (reshape_data of the train/test nets) read their host mirror back from the device
+  for (int vb : inputs_) {
+    const int it = vis_blobs_[vb].tensor;
+    for (size_t q = 0; q < tensors_.size(); ++q)
+      if ((int)q != it && tensors_[q].root == tensors_[it].root && tensors_[q].materialized) tensors_[q].dev_newer = true;
+  }
 
   if (train_) ++train_iter_;  // a new dropout mask per forward pass
   int launches = 0;

@@ -629,13 +629,23 @@ class RefNet:
 
 
     # ---- backward -----------------------------------------------------------------
-    def backward(self, top_diffs=None, loss_weight=1.0):
+    def backward(self, top_diffs=None, loss_weight=1.0, teacher_diffs=None):
         """Backward pass over the tape of the last fp32 forward(), layer by layer in reverse (Net::BackwardFromTo,
         net.cpp:637-706).  Blob diffs accumulate over all consumers of a blob (what the auto-inserted Split
         layers do, split_layer.cpp); in-place layers replace the diff of their blob.  Parameter diffs are returned
         fresh (zero-initialised), i.e. one iteration with iter_size 1.
         top_diffs: optional {blob: dL/dblob} seeds (default: loss layers seed themselves with loss_weight).
+        teacher_diffs: optional {blob: dL/dblob as the DEVICE computed it}.  When the pass reaches the last writer of
+        such a blob, the oracle's own (accumulated) diff is recorded and the teacher's is substituted for everything
+        upstream, so each layer's backward is judged on the top gradient the device actually had (the backward
+        analogue of forward(teacher=...)); combine with a teacher-forced forward so the tape holds the device's
+        activations.  The recorded own values are what `blob_diffs` returns then.
         Returns (blob_diffs, param_diffs): {blob: array}, {layer: [arrays in blob order]}."""
+        own = {}
+        last_writer = {}
+        for l, _, _ in self.tape:
+            for t_ in l.tops:
+                last_writer[t_] = l
         diffs = {}
         pdiffs = {}
         data_blobs = set(self.inputs)
@@ -662,6 +672,11 @@ class RefNet:
             t = l.type
             if t in DATA_TYPES or t == "Accuracy":
                 continue
+            if teacher_diffs is not None:
+                for t_ in l.tops:
+                    if last_writer.get(t_) is l and t_ in diffs and t_ in teacher_diffs and t_ not in own:
+                        own[t_] = diffs[t_]
+                        diffs[t_] = _f32(teacher_diffs[t_]).reshape(diffs[t_].shape)
             if t == "SoftmaxWithLoss":
                 prob, lab = extra["prob"], extra["label"]
                 g = prob.copy()
@@ -722,6 +737,10 @@ class RefNet:
                 raise NotImplementedError("oracle backward: plain Softmax is not on the training path")
             else:
                 raise NotImplementedError("oracle backward: layer type %s (%s)" % (t, l.name))
+        if teacher_diffs is not None:
+            for k, v in diffs.items():
+                own.setdefault(k, v)
+            return own, pdiffs
         return diffs, pdiffs
 
 
