@@ -179,6 +179,147 @@ def cpu_strong_forward(params, x, segments, steps=3, warmup=1, threads=None):
     return steps / dt, dt / steps * 1e3, threads, fc8
 
 
+TRAIN_SOLVER = """base_lr: 0.001 lr_policy: "step" gamma: 0.1 stepsize: 24000 max_iter: 60000 iter_size: 1
+momentum: 0.9 weight_decay: 0.0005 clip_gradients: 40 solver_type: NESTEROV"""   # models_ECO_Lite/kinetics/solver.prototxt (iter_size 1)
+
+
+def train_main(a, rank, local_rank, world):
+    """BASELINE config #4: ECO-Lite training, Kinetics-400 head, batch-sharded over the GPUs of one box, the ONLY collective
+    being the gradient all-reduce (NCCL, bucketed, overlapped with backward).  One step = Solver::Step(1): clear diffs,
+    forward, backward, exchange, clip + L2 + Nesterov update.  videos/s = world * batch * steps / time."""
+    segments = a.segments if a.segments != 16 or "--segments" in sys.argv else 32
+    batch = a.batch if "--batch" in sys.argv else 16
+    classes = 400
+    workload = "ECO-Lite N=%d training step (fwd+bwd+grad all-reduce+Nesterov), %d classes, batch %d videos/GPU, synthetic frames" % (
+        segments, classes, batch)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        import gen_eco_prototxt as gen
+        from oracle import refnet
+        threads = physical_cores()
+        refnet.lib().ref_set_num_threads(threads)
+        net = refnet.RefNet(gen.eco_lite_train(segments=segments, classes=classes, batch=1), phase="TRAIN").init_params(4321)
+        x = refnet.eco_input(1, segments).reshape(1, 3 * segments, 224, 224)
+        lab = np.array([7], np.float32).reshape(1, 1, 1, 1)
+        steps = max(1, min(a.steps, 2))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            net.forward({"data": x, "label": lab})
+            net.backward()
+        dt = time.perf_counter() - t0
+        vps = steps / dt
+        print(json.dumps({"impl": "reference", "metric": "ECO-Lite-%d training videos/sec" % segments, "value": vps, "unit": "videos/s",
+                          "n_gpus": a.gpus, "steps": steps, "warmup": 0, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": workload, "note": "oracle forward+backward (caffe_3d CPU algorithm), ONE clip per step, no update"},
+                          "cpu_baseline": {"value": vps, "unit": "videos/s", "cores": threads, "kind": "port", "cpu_model": cpu_model(),
+                                           "sample": "%d single-clip forward+backward passes" % steps},
+                          "e2e": {"value": vps, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    import torch
+    import caffe
+    import gen_eco_prototxt as gen
+    import harness
+    from caffe.parallel import GradExchange
+    from dist_util import Group
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    caffe.set_device(local_rank)
+    caffe.set_mode_gpu()
+    grp = Group("nccl", torch.device("cuda", local_rank))
+    solver = caffe.NesterovSolver(solver_text=TRAIN_SOLVER, net_text=gen.eco_lite_train(segments=segments, classes=classes, batch=batch))
+    net = solver.net
+    harness.init_params(net, 4321)
+    ex = GradExchange(solver, nbuckets=a.buckets)
+    ex.broadcast_params(0)
+    stream = ex.compute
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234 + rank)
+    frames = torch.randint(0, 256, (batch, 3 * segments, 224, 224), generator=g, device="cuda", dtype=torch.uint8).float()
+    frames -= torch.tensor([104.0, 117.0, 123.0], device="cuda").repeat(segments).view(1, 3 * segments, 1, 1)
+    count = frames.numel()
+    labels = np.random.default_rng(99 + rank).integers(0, classes, size=(batch, 1, 1, 1)).astype(np.float32)
+    net.blobs["label"].data[...] = labels
+    torch.cuda.synchronize()
+    net.set_input_device("data", frames.data_ptr(), count)
+    losses = []
+    for _ in range(max(a.warmup, 3)):
+        losses.append(solver.step(1))
+    net.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    grp.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(a.steps):
+        losses.append(solver.step(1))
+    e1.record(stream)
+    grp.barrier()
+    sampler.window(tw0, time.perf_counter())
+    ms_total = grp.max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / a.steps
+    value = world * batch * a.steps / (ms_total / 1e3)
+    # e2e: the batch comes from the input blob's pinned host mirror every step (what a data layer would fill), loss read back
+    host_in = net.blobs["data"].data
+    host_in[...] = frames.cpu().numpy()
+    for _ in range(2):
+        net.blobs["data"].data
+        solver.step(1)
+    grp.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        net.blobs["data"].data
+        net.blobs["label"].data
+        losses.append(solver.step(1))
+    torch.cuda.synchronize()
+    grp.barrier()
+    e2e_ms = grp.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    sampler.window(t0, time.perf_counter())
+    clocks = sampler.finish()
+    e2e_value = world * batch * a.steps / (e2e_ms / 1e3)
+    # collective alone: the same buckets all-reduced back to back on an idle GPU (what is overlapped with backward above)
+    coll_ms = None
+    if world > 1:
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            torch.distributed.all_reduce(ex.grad)
+        c1.record()
+        torch.cuda.synchronize()
+        coll_ms = grp.max_over_ranks(c0.elapsed_time(c1) / 5)
+    gf_video = 3.0 * GFLOP_PER_VIDEO[("lite", 16)] * segments / 16.0   # forward + dgrad + wgrad implicit GEMMs (SURVEY 8(d): 557.8 at N=32)
+    pk = peaks()
+    achieved = batch * gf_video / ms_step   # GFLOP / ms = TFLOP/s
+    _, _, arena = net.arenas()
+    if rank != 0:
+        grp.close()
+        return
+    line = {"metric": "ECO-Lite-%d training videos/sec (fwd+bwd+grad all-reduce+Nesterov update)" % segments, "value": value,
+            "unit": "videos/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 activations / fp32 master weights and gradients",
+            "data": "synthetic",
+            "config": {"workload": workload, "global_batch": batch * world, "parallelism": "dp%d: batch-sharded replicas, NCCL SUM all-reduce of the "
+                       "gradient arena in %d buckets launched from the backward pass (overlapped), 1/world folded into the update" % (world, a.buckets),
+                       "l2": "activations exceed the 126 MB L2", "solver": "models_ECO_Lite/kinetics/solver.prototxt values, iter_size 1"},
+            "clocks": clocks, "gpu_launches": int(net.last_launch_count()) * a.steps,
+            "e2e": {"value": e2e_value, "unit": "videos/s", "h2d_bytes_per_step": int(count * 4 + batch * 4), "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / a.steps},
+            "collective": {"payload_bytes_per_iter": int(arena * 4), "buckets": a.buckets, "allreduce_alone_ms": coll_ms,
+                           "note": "allreduce_alone_ms = the whole arena all-reduced on an idle GPU; inside the step it runs on a side "
+                                   "stream under the backward kernels"},
+            "roofline": {"bound": "tensor", "kernel": "forward conv GEMMs + dgrad (same kernel) + wgrad_umma_kernel", "achieved": achieved,
+                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "peak_source": pk["src"],
+                         "traffic": None, "gflop_per_video": gf_video,
+                         "note": "whole-step rate: algorithmic conv FLOPs (3 x forward) / ms_per_step, everything else included in the time"},
+            "loss_first_last": [float(losses[0]), float(losses[-1])], "cpu_baseline": None}
+    print(json.dumps(line))
+    grp.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,6 +329,9 @@ def main():
     ap.add_argument("--model", default="lite", choices=["lite", "full"])
     ap.add_argument("--segments", type=int, default=16)
     ap.add_argument("--batch", type=int, default=32, help="videos per GPU per step")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE metric (forward videos/s); train: config #4 (fwd + bwd + NCCL grad all-reduce + Nesterov)")
+    ap.add_argument("--buckets", type=int, default=3, help="train: gradient all-reduce buckets")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     a = ap.parse_args()
@@ -195,6 +339,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.mode == "train":
+        return train_main(a, rank, local_rank, world)
     workload = "ECO-%s N=%d forward, %d classes, batch %d videos/GPU, synthetic 224x224x3 frames" % (
         "Lite" if a.model == "lite" else "Full", a.segments, CLASSES if a.model == "lite" else 400, a.batch)
 

@@ -7,3 +7,4 @@ from ._caffe import Layer, Blob
 
 __all__ = ["Net", "TRAIN", "TEST", "set_mode_cpu", "set_mode_gpu", "set_device", "set_logging_disabled", "Layer",
            "Blob", "device_count"]
+from .solver import Solver, SGDSolver, NesterovSolver, get_solver  # noqa: F401

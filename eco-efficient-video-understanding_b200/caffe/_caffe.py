@@ -23,6 +23,10 @@ class ParamSlot(C.Structure):
                 ("lr_mult", C.c_float), ("decay_mult", C.c_float)]
 
 
+GRAD_BUCKET_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t)
+GRAD_SYNC_FN = C.CFUNCTYPE(None, C.c_void_p)
+
+
 def lib():
     """Load the CUDA library.  There is deliberately no fallback: without it nothing can run."""
     global _lib
@@ -74,6 +78,20 @@ def lib():
     L.eco_net_param_slot.argtypes = [C.c_void_p, C.c_int, C.POINTER(ParamSlot)]
     L.eco_net_params_updated_on_device.argtypes = [C.c_void_p]
     L.eco_net_cuda_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.eco_net_set_grad_bucket_hook.argtypes = [C.c_void_p, C.c_int, GRAD_BUCKET_FN, C.c_void_p]
+    L.eco_net_num_grad_buckets.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.eco_net_grad_bucket.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.eco_solver_create.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.eco_solver_create_from_string.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.eco_solver_destroy.argtypes = [C.c_void_p]
+    L.eco_solver_net.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.eco_solver_iter.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.eco_solver_learning_rate.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.eco_solver_step.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+    L.eco_solver_apply_update.argtypes = [C.c_void_p]
+    L.eco_solver_set_grad_sync.argtypes = [C.c_void_p, GRAD_SYNC_FN, C.c_void_p, C.c_int]
+    L.eco_solver_snapshot.argtypes = [C.c_void_p, C.c_char_p]
+    L.eco_solver_restore.argtypes = [C.c_void_p, C.c_char_p]
     L.eco_blob_host_data.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)),
                                      C.POINTER(C.c_size_t)]
     L.eco_blob_host_diff.argtypes = L.eco_blob_host_data.argtypes

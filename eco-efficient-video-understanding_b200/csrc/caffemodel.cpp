@@ -228,4 +228,54 @@ void Net::save(const std::string& path) const {
   f.write(out.data(), (std::streamsize)out.size());
 }
 
+// ---- SolverState (caffe.proto:217-222): iter = 1, learned_net = 2, history = 3 (repeated BlobProto), current_step = 4 ----
+void write_solverstate(const std::string& path, int iter, const std::string& learned_net, int current_step,
+                       const std::vector<std::pair<std::vector<int>, std::vector<float>>>& history) {
+  std::string out;
+  put_key(out, 1, 0);
+  put_varint(out, (uint64_t)iter);
+  put_bytes(out, 2, learned_net);
+  for (const auto& h : history) {
+    std::string bm;
+    std::string packed(reinterpret_cast<const char*>(h.second.data()), h.second.size() * 4);
+    put_bytes(bm, 5, packed);
+    std::string dims, shp;
+    for (int d : h.first) put_varint(dims, (uint64_t)d);
+    put_bytes(shp, 1, dims);
+    put_bytes(bm, 7, shp);
+    put_bytes(out, 3, bm);
+  }
+  put_key(out, 4, 0);
+  put_varint(out, (uint64_t)current_step);
+  std::ofstream f(path, std::ios::binary);
+  if (!f) throw std::runtime_error("Could not open " + path + " for writing");
+  f.write(out.data(), (std::streamsize)out.size());
+}
+
+void read_solverstate(const std::string& path, int* iter, std::string* learned_net, int* current_step,
+                      std::vector<std::vector<float>>* history) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw std::runtime_error("Could not open " + path);
+  std::string buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  Reader r{reinterpret_cast<const uint8_t*>(buf.data()), reinterpret_cast<const uint8_t*>(buf.data()) + buf.size()};
+  *iter = 0;
+  *current_step = 0;
+  learned_net->clear();
+  history->clear();
+  while (r.ok()) {
+    const uint64_t key = r.varint();
+    const int field = (int)(key >> 3), wire = (int)(key & 7);
+    if (field == 1 && wire == 0) *iter = (int)r.varint();
+    else if (field == 4 && wire == 0) *current_step = (int)r.varint();
+    else if (field == 2 && wire == 2) {
+      Reader s2 = r.sub();
+      learned_net->assign(reinterpret_cast<const char*>(s2.p), (size_t)(s2.end - s2.p));
+    } else if (field == 3 && wire == 2) {
+      history->push_back(read_blob(r.sub()).data);
+    } else {
+      r.skip(wire);
+    }
+  }
+}
+
 }  // namespace eco

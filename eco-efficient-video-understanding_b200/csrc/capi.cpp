@@ -7,9 +7,15 @@
 
 #include "../../include/eco_b200.h"
 #include "net.hpp"
+#include "solver.hpp"
 
 struct eco_net {
   eco::Net* impl;
+  bool borrowed = false;   // owned by a solver
+};
+struct eco_solver {
+  eco::Solver* impl;
+  eco_net net_handle;
 };
 
 namespace eco {
@@ -95,7 +101,7 @@ int eco_net_create(const char* path, int phase, eco_net** out) {
 }
 int eco_net_destroy(eco_net* net) {
   ECO_API_BEGIN
-  if (net) {
+  if (net && !net->borrowed) {
     delete net->impl;
     delete net;
   }
@@ -370,6 +376,112 @@ int eco_net_describe_plan(eco_net* net, char* buf, size_t cap, size_t* needed) {
     std::memcpy(buf, d.data(), n);
     buf[n] = 0;
   }
+  ECO_API_END
+}
+
+int eco_net_set_grad_bucket_hook(eco_net* net, int nbuckets, eco_grad_bucket_fn fn, void* user) {
+  ECO_API_BEGIN
+  N(net).set_grad_bucket_hook(nbuckets, fn, user);
+  ECO_API_END
+}
+int eco_net_num_grad_buckets(eco_net* net, int* n) {
+  ECO_API_BEGIN
+  *n = (int)N(net).grad_buckets().size();
+  ECO_API_END
+}
+int eco_net_grad_bucket(eco_net* net, int i, size_t* offset, size_t* count) {
+  ECO_API_BEGIN
+  const auto& b = N(net).grad_buckets();
+  if (i < 0 || i >= (int)b.size()) throw std::runtime_error("bucket index out of range");
+  *offset = b[i].off;
+  *count = b[i].count;
+  ECO_API_END
+}
+
+/* ---- solver ---- */
+static eco::Solver& S(eco_solver* s) {
+  if (!s || !s->impl) throw std::runtime_error("null eco_solver handle");
+  return *s->impl;
+}
+static int solver_create(const std::string& text, const std::string& net_text, const std::string& dir, eco_solver** out) {
+  ECO_API_BEGIN
+  if (!out) throw std::runtime_error("null argument");
+  eco_solver* h = new eco_solver;
+  h->impl = nullptr;
+  try {
+    h->impl = new eco::Solver(text, net_text, dir);
+  } catch (...) {
+    delete h;
+    throw;
+  }
+  h->net_handle.impl = &h->impl->net();
+  h->net_handle.borrowed = true;
+  *out = h;
+  ECO_API_END
+}
+int eco_solver_create(const char* solver_prototxt_path, eco_solver** out) {
+  if (!solver_prototxt_path) { eco::set_last_error("null path"); return 1; }
+  std::ifstream f(solver_prototxt_path);
+  if (!f) { eco::set_last_error(std::string("Could not open ") + solver_prototxt_path); return 1; }
+  std::stringstream ss;
+  ss << f.rdbuf();
+  std::string dir(solver_prototxt_path);
+  const size_t slash = dir.find_last_of('/');
+  dir = slash == std::string::npos ? std::string() : dir.substr(0, slash);
+  return solver_create(ss.str(), "", dir, out);
+}
+int eco_solver_create_from_string(const char* solver_text, const char* net_text, eco_solver** out) {
+  return solver_create(solver_text ? solver_text : "", net_text ? net_text : "", "", out);
+}
+int eco_solver_destroy(eco_solver* s) {
+  ECO_API_BEGIN
+  if (s) {
+    delete s->impl;
+    delete s;
+  }
+  ECO_API_END
+}
+int eco_solver_net(eco_solver* s, eco_net** net) {
+  ECO_API_BEGIN
+  S(s);
+  *net = &s->net_handle;
+  ECO_API_END
+}
+int eco_solver_iter(eco_solver* s, int* iter) {
+  ECO_API_BEGIN
+  *iter = S(s).iter();
+  ECO_API_END
+}
+int eco_solver_learning_rate(eco_solver* s, float* rate) {
+  ECO_API_BEGIN
+  *rate = S(s).learning_rate();
+  ECO_API_END
+}
+int eco_solver_step(eco_solver* s, int iters, float* loss) {
+  ECO_API_BEGIN
+  if (!g_mode_gpu) throw std::runtime_error("set_mode_cpu() was requested: libeco_b200 has no CPU execution path");
+  const float l = S(s).step(iters);
+  if (loss) *loss = l;
+  ECO_API_END
+}
+int eco_solver_apply_update(eco_solver* s) {
+  ECO_API_BEGIN
+  S(s).apply_update();
+  ECO_API_END
+}
+int eco_solver_set_grad_sync(eco_solver* s, eco_grad_sync_fn fn, void* user, int world) {
+  ECO_API_BEGIN
+  S(s).set_grad_sync(fn, user, world);
+  ECO_API_END
+}
+int eco_solver_snapshot(eco_solver* s, const char* prefix) {
+  ECO_API_BEGIN
+  S(s).snapshot(prefix ? prefix : "");
+  ECO_API_END
+}
+int eco_solver_restore(eco_solver* s, const char* state_file) {
+  ECO_API_BEGIN
+  S(s).restore(state_file ? state_file : "");
   ECO_API_END
 }
 

@@ -266,6 +266,14 @@ class Net {
   float* grad_arena(size_t* count);
   const std::vector<ParamSlot>& param_slots();
   void params_updated_on_device();   // a solver changed the arena: repack the GEMM operands, host copies are stale
+  // Gradient exchange hook: the arena is cut into `n` contiguous buckets of roughly equal size (slot boundaries, layer
+  // order); during Backward, as soon as every layer of a bucket has produced its gradients, fn(user, bucket, offset, count)
+  // is called on the host (the kernels are enqueued on stream(), not finished): the callee records an event and starts
+  // the all-reduce of grad[offset, offset + count) on a side stream while the earlier layers are still being computed.
+  typedef void (*BucketFn)(void* user, int bucket, size_t offset, size_t count);
+  void set_grad_bucket_hook(int n, BucketFn fn, void* user);
+  struct Bucket { int min_layer; size_t off, count; };
+  const std::vector<Bucket>& grad_buckets();
   cudaStream_t stream();
   float last_loss() const { return last_loss_; }
 
@@ -352,6 +360,10 @@ class Net {
   bool params_dev_newer_ = false;    // arena newer than the host ParamBlobs (solver update, BN running statistics)
   bool repack_ = true;               // bf16 GEMM operands must be rebuilt from the arena
   unsigned long long train_iter_ = 0;
+  int bucket_n_ = 0;
+  BucketFn bucket_fn_ = nullptr;
+  void* bucket_user_ = nullptr;
+  std::vector<Bucket> buckets_;
   float last_loss_ = 0.f;
   float* loss_host_ = nullptr;       // pinned
   void plan_train();

@@ -506,8 +506,8 @@ __global__ void scale_kernel(float* __restrict__ x, long long n, const float* __
 }
 __global__ void clip_factor_kernel(const float* __restrict__ sumsq, float clip, float norm, float* __restrict__ scale) {
   // ClipGradients runs on the accumulated (not yet iter_size-normalised) diffs, solver.cpp:637-660
-  (void)norm;
-  const float l2 = sqrtf(*sumsq);
+  // `norm` = 1 / world: the reference scales the exchanged diffs by 1 / MPI_all_rank before ApplyUpdate (solver.cpp:332-337)
+  const float l2 = sqrtf(*sumsq) * norm;
   *scale = (clip >= 0.f && l2 > clip) ? clip / l2 : 1.f;
 }
 __global__ void sgd_update_kernel(float* __restrict__ w, float* __restrict__ diff, float* __restrict__ hist, long long n, float rate,

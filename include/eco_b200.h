@@ -116,6 +116,34 @@ int eco_net_param_slot(eco_net* net, int i, eco_param_slot* out);
  * forward and the host views are refreshed on access */
 int eco_net_params_updated_on_device(eco_net* net);
 int eco_net_cuda_stream(eco_net* net, void** cuda_stream);   /* the stream the net's kernels run on */
+/* Gradient exchange hook (replaces the per-blob host-staged MPI_Allreduce of net.cpp:670-702): the gradient arena is cut
+ * into `nbuckets` contiguous ranges in layer order; during eco_net_backward `fn(user, bucket, offset, count)` is called on
+ * the host as soon as all kernels that produce grad[offset, offset+count) are ENQUEUED on the net's stream -- the caller
+ * records an event there and starts ncclAllReduce of that range on a side stream, overlapping the rest of backward. */
+typedef void (*eco_grad_bucket_fn)(void* user, int bucket, size_t offset, size_t count);
+int eco_net_set_grad_bucket_hook(eco_net* net, int nbuckets, eco_grad_bucket_fn fn, void* user);
+int eco_net_num_grad_buckets(eco_net* net, int* n);
+int eco_net_grad_bucket(eco_net* net, int i, size_t* offset, size_t* count);   /* bucket 0 = the last layers */
+
+/* ---- Solver (caffe::Solver / SGDSolver / NesterovSolver, solver.hpp; _caffe.cpp:296-317): SGD and Nesterov momentum
+ * with lr_mult / decay_mult per blob, L2 decay, global-norm clipping, every lr_policy of solver.cpp:580-620, iter_size
+ * accumulation, Snapshot / Restore (.caffemodel + .solverstate, caffe.proto:217-222).  The train net's inputs (data, label)
+ * are filled by the caller through the net handle before each step (the VideoData layer is SURVEY 8(f1)). ---- */
+typedef struct eco_solver eco_solver;
+int eco_solver_create(const char* solver_prototxt_path, eco_solver** out);    /* `net:` is resolved next to the solver file */
+int eco_solver_create_from_string(const char* solver_text, const char* net_text /* NULL: read `net:` */, eco_solver** out);
+int eco_solver_destroy(eco_solver* s);
+int eco_solver_net(eco_solver* s, eco_net** net);          /* borrowed handle, valid until eco_solver_destroy */
+int eco_solver_iter(eco_solver* s, int* iter);
+int eco_solver_learning_rate(eco_solver* s, float* rate);
+int eco_solver_step(eco_solver* s, int iters, float* last_loss);   /* Solver::Step */
+int eco_solver_apply_update(eco_solver* s);                /* SGDSolver::ApplyUpdate on the current diffs, ++iter */
+/* called between backward and the update of every iteration; `world` = number of data-parallel replicas whose gradients
+ * the callee sums: the update then uses diff / world (solver.cpp:332-337) */
+typedef void (*eco_grad_sync_fn)(void* user);
+int eco_solver_set_grad_sync(eco_solver* s, eco_grad_sync_fn fn, void* user, int world);
+int eco_solver_snapshot(eco_solver* s, const char* prefix /* NULL/"": snapshot_prefix */);
+int eco_solver_restore(eco_solver* s, const char* solverstate_path);
 int eco_net_sync(eco_net* net);                                      /* wait for the net's stream */
 
 /* ---- blob data (Blob::cpu_data / mutable_cpu_data / cpu_diff, SyncedMemory syncedmem.cpp:21-70) ---- */
