@@ -43,6 +43,8 @@ def lib():
         getattr(L, fn).restype = C.c_char_p
     L.eco_net_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     L.eco_net_create_from_string.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.eco_net_create_from_string_until.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.eco_net_push_frames.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.eco_net_destroy.argtypes = [C.c_void_p]
     L.eco_net_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.eco_net_set_stream.argtypes = [C.c_void_p, C.c_void_p]

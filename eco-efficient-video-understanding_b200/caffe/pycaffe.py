@@ -39,6 +39,8 @@ class Net(object):
             if not os.path.isfile(model_file):
                 raise RuntimeError("Could not open file " + str(model_file))
             check(lib().eco_net_create(os.fsencode(model_file), int(phase), C.byref(self._h)))
+        elif kwargs.get("until_blob"):
+            check(lib().eco_net_create_from_string_until(text.encode(), int(phase), kwargs["until_blob"].encode(), C.byref(self._h)))
         else:
             check(lib().eco_net_create_from_string(text.encode(), int(phase), C.byref(self._h)))
         for k, v in kwargs.get("options", {}).items():
@@ -50,8 +52,12 @@ class Net(object):
         self._refresh_registry()
 
     @classmethod
-    def from_string(cls, text, phase, **options):
-        return cls("<string>", phase, prototxt_text=text, options=options)
+    def from_string(cls, text, phase, until_blob=None, **options):
+        return cls("<string>", phase, prototxt_text=text, options=options, until_blob=until_blob)
+
+    def push_frames(self, dst_blob, src_net, src_blob):
+        """append the frames of src_net.blobs[src_blob] to the sliding window held in self.blobs[dst_blob] (device to device)"""
+        check(lib().eco_net_push_frames(self._h, self._blob_names.index(dst_blob), src_net._h, src_net._blob_names.index(src_blob)))
 
     def _refresh_registry(self):
         L = lib()

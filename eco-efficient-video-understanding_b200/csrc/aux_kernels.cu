@@ -22,7 +22,13 @@ __global__ void f32_to_cl_kernel(const float* __restrict__ src, ClView d) {
     const long long oi = t / d.C;
     const long long i = oi % d.inner, o = oi / d.inner;
     const float v = src[(o * d.C + c) * d.inner + i];
-    d.ptr[oi * d.cs + d.coff + c] = __float2bfloat16_rn(v);
+    __nv_bfloat16* q = d.ptr + oi * d.ps() + d.coff + c;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    q[0] = hi;
+    if (d.seg) {
+      q[d.seg] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      q[2 * d.seg] = hi;
+    }
   }
 }
 __global__ void cl_to_f32_kernel(ClView s, float* __restrict__ dst) {
@@ -34,7 +40,8 @@ __global__ void cl_to_f32_kernel(ClView s, float* __restrict__ dst) {
     const long long oc = t / s.inner;
     const int c = (int)(oc % s.C);
     const long long o = oc / s.C;
-    dst[t] = __bfloat162float(s.ptr[(o * s.inner + i) * s.cs + s.coff + c]);
+    const __nv_bfloat16* q = s.ptr + (o * s.inner + i) * s.ps() + s.coff + c;
+    dst[t] = __bfloat162float(q[0]) + (s.seg ? __bfloat162float(q[s.seg]) : 0.f);
   }
 }
 
@@ -476,10 +483,52 @@ __global__ void global_avg_cl_kernel(ClView s, float* __restrict__ dst) {
        t += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(t % s.C);
     const long long o = t / s.C;
-    const __nv_bfloat16* px = s.ptr + o * s.inner * s.cs + s.coff + c;
+    const long long ps = s.ps();
+    const __nv_bfloat16* px = s.ptr + o * s.inner * ps + s.coff + c;
     float acc = 0.f;
-    for (long long i = 0; i < s.inner; ++i) acc += __bfloat162float(px[i * s.cs]);
+    for (long long i = 0; i < s.inner; ++i)
+      acc += __bfloat162float(px[i * ps]) + (s.seg ? __bfloat162float(px[i * ps + s.seg]) : 0.f);
     dst[t] = acc / (float)s.inner;
+  }
+}
+
+// split-precision pooling: one thread per (output position, channel); caffe's window rules (pooling_layer.cpp:199-262)
+__global__ void pool_cl_split_kernel(const PoolParams p, long long xseg, long long yseg) {
+  const long long total = (long long)p.NB * p.OD * p.OH * p.OW * p.C;
+  const long long xps = 3 * p.x_cs, yps = 3 * p.y_cs;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % p.C);
+    long long r = t / p.C;
+    const long long opix = r;
+    const int ox = (int)(r % p.OW); r /= p.OW;
+    const int oy = (int)(r % p.OH); r /= p.OH;
+    const int oz = (int)(r % p.OD);
+    const long long n = r / p.OD;
+    int z0 = oz * p.sD - p.pD, y0 = oy * p.sH - p.pH, x0 = ox * p.sW - p.pW;
+    int z1, y1, x1;
+    float div = 1.f;
+    if (p.is_max) {
+      z1 = min(z0 + p.KD, p.ID); y1 = min(y0 + p.KH, p.IH); x1 = min(x0 + p.KW, p.IW);
+    } else {
+      z1 = min(z0 + p.KD, p.ID + p.pD); y1 = min(y0 + p.KH, p.IH + p.pH); x1 = min(x0 + p.KW, p.IW + p.pW);
+      div = (float)((z1 - z0) * (y1 - y0) * (x1 - x0));
+      z1 = min(z1, p.ID); y1 = min(y1, p.IH); x1 = min(x1, p.IW);
+    }
+    z0 = max(z0, 0); y0 = max(y0, 0); x0 = max(x0, 0);
+    float acc = p.is_max ? -FLT_MAX : 0.f;
+    for (int z = z0; z < z1; ++z)
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+          const __nv_bfloat16* q = p.x + (((n * p.ID + z) * p.IH + y) * p.IW + x) * xps + p.x_coff + c;
+          const float v = __bfloat162float(q[0]) + __bfloat162float(q[xseg]);
+          acc = p.is_max ? fmaxf(acc, v) : acc + v;
+        }
+    if (!p.is_max) acc = acc / div;
+    __nv_bfloat16* o = p.y + opix * yps + p.y_coff + c;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(acc);
+    o[0] = hi;
+    o[yseg] = __float2bfloat16_rn(acc - __bfloat162float(hi));
+    o[2 * yseg] = hi;
   }
 }
 
@@ -655,6 +704,13 @@ cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st) {
   }
   const long long blocks = (n + kThreads - 1) / kThreads;
   pool_cl_kernel<<<(unsigned)(blocks > 148LL * 64 ? 148LL * 64 : blocks), kThreads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_cl_split(const PoolParams& p, long long x_seg, long long y_seg, cudaStream_t st) {
+  const long long n = (long long)p.NB * p.OD * p.OH * p.OW * p.C;
+  if (n == 0) return cudaSuccess;
+  if (p.bias || p.scale || p.relu) return cudaErrorNotSupported;
+  pool_cl_split_kernel<<<grid_cap(n), kThreads, 0, st>>>(p, x_seg, y_seg);
   return cudaGetLastError();
 }
 cudaError_t launch_global_avg_cl(ClView src, float* dst, cudaStream_t st) {

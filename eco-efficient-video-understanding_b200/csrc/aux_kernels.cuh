@@ -14,6 +14,10 @@ struct ClView {
   int C;             // logical channels
   long long cs;      // channel stride of the underlying buffer (>= C)
   int coff;          // first channel inside the buffer
+  // split-precision storage (planner option `precision`): three planes [hi | lo | hi] per pixel, `seg` elements apart
+  // (= cs), pixel stride 3 * cs; value = hi + lo.  0: plain bf16, pixel stride cs.
+  long long seg = 0;
+  __host__ __device__ long long ps() const { return seg ? 3 * cs : cs; }
 };
 
 // fp32 logical (caffe row-major [outer, C, inner]) -> channels-last bf16, and back.
@@ -51,6 +55,8 @@ inline bool pool_cl_affine_supported(int IW, int C, long long NB) {
 // caffe pooling on channels-last bf16 (pooling_layer.cpp:199-262 semantics), C % 8 == 0
 cudaError_t launch_pool_cl(const PoolParams& p, cudaStream_t st);
 
+// generic N-D pooling on split-precision maps (x/y views carry seg != 0): pooled in fp32 from hi + lo, stored split
+cudaError_t launch_pool_cl_split(const PoolParams& p, long long x_seg, long long y_seg, cudaStream_t st);
 // mean over `inner` of a channels-last tensor -> fp32 [outer, C]  (global_pool / global_pool2D)
 cudaError_t launch_global_avg_cl(ClView src, float* dst, cudaStream_t st);
 

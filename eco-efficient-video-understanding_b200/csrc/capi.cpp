@@ -87,6 +87,25 @@ int eco_net_create_from_string(const char* text, int phase, eco_net** out) {
   *out = h;
   ECO_API_END
 }
+int eco_net_create_from_string_until(const char* text, int phase, const char* until_blob, eco_net** out) {
+  ECO_API_BEGIN
+  if (!text || !out) throw std::runtime_error("null argument");
+  eco_net* h = new eco_net;
+  h->impl = nullptr;
+  try {
+    h->impl = new eco::Net(text, phase, until_blob ? until_blob : "");
+  } catch (...) {
+    delete h;
+    throw;
+  }
+  *out = h;
+  ECO_API_END
+}
+int eco_net_push_frames(eco_net* dst, int dst_blob, eco_net* src, int src_blob) {
+  ECO_API_BEGIN
+  N(dst).push_frames(dst_blob, N(src), src_blob);
+  ECO_API_END
+}
 int eco_net_create(const char* path, int phase, eco_net** out) {
   ECO_API_BEGIN
   if (!path) throw std::runtime_error("null path");
@@ -254,6 +273,16 @@ int eco_net_backward(eco_net* net, int start, int end) {
 int eco_net_clear_param_diffs(eco_net* net) {
   ECO_API_BEGIN
   N(net).clear_param_diffs();
+  ECO_API_END
+}
+int eco_net_update(eco_net* net) {
+  ECO_API_BEGIN
+  size_t n = 0;
+  float* P = N(net).param_arena(&n);
+  float* G = N(net).grad_arena(&n);
+  cudaError_t e = eco::launch_f32_axpy(G, P, (long long)n, -1.f, 1, N(net).stream());
+  if (e != cudaSuccess) throw std::runtime_error(std::string("Net::Update: ") + cudaGetErrorString(e));
+  N(net).params_updated_on_device();
   ECO_API_END
 }
 int eco_net_param_diff_host(eco_net* net, int layer, int idx, float** data, size_t* count) {

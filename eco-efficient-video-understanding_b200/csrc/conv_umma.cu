@@ -199,6 +199,16 @@ __device__ __forceinline__ void load16_bf16_add(const __nv_bfloat16* src, float 
   }
 }
 
+// split-precision store: hi = bf16(f), lo = bf16(f - hi); planes [hi | lo | hi], `seg` elements apart
+__device__ __forceinline__ void store16_split(__nv_bfloat16* dst, long long seg, const float (&f)[16], int nvalid) {
+  float lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) lo[j] = f[j] - __bfloat162float(__float2bfloat16_rn(f[j]));
+  store16_bf16(dst, f, nvalid);
+  store16_bf16(dst + seg, lo, nvalid);
+  store16_bf16(dst + 2 * seg, f, nvalid);
+}
+
 // Exactly one lane of a converged warp.  The tcgen05 / TMA instructions take uniform-register operands: issued
 // under `if (lane == 0)` ptxas cannot prove a single active thread and wraps EVERY such instruction in an
 // ELECT / BRA.U.ANY serialisation loop (seen in the SASS, ~60 issue cycles per tcgen05.mma whatever N, measured
@@ -327,8 +337,16 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams& p, uint32_
       float f[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
-      if (p.res) load16_bf16_add(p.res + (long long)m * p.res_cs + p.res_coff + cg, f, nvalid);
-      if (p.raw) store16_bf16(p.raw + (long long)m * p.raw_cs + p.raw_coff + cg, f, nvalid);
+      if (p.res) {
+        const __nv_bfloat16* r = p.res + (long long)m * p.res_cs + p.res_coff + cg;
+        load16_bf16_add(r, f, nvalid);
+        if (p.res_seg) load16_bf16_add(r + p.res_seg, f, nvalid);  // + lo plane
+      }
+      if (p.raw) {
+        __nv_bfloat16* r = p.raw + (long long)m * p.raw_cs + p.raw_coff + cg;
+        if (p.raw_seg) store16_split(r, p.raw_seg, f, nvalid);
+        else store16_bf16(r, f, nvalid);
+      }
       if (p.out) {
         if (has_scale) {
 #pragma unroll
@@ -338,7 +356,9 @@ __device__ __forceinline__ void epilogue_rows(const ConvKernelParams& p, uint32_
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        store16_bf16(p.out + (long long)m * p.out_cs + p.out_coff + cg, f, nvalid);
+        __nv_bfloat16* o = p.out + (long long)m * p.out_cs + p.out_coff + cg;
+        if (p.out_seg) store16_split(o, p.out_seg, f, nvalid);
+        else store16_bf16(o, f, nvalid);
       }
     }
   }

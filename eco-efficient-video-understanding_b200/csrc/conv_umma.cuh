@@ -60,6 +60,11 @@ struct ConvKernelParams {
   __nv_bfloat16* raw;   long long raw_cs;  int raw_coff;   // raw (null -> not stored)
   const __nv_bfloat16* res; long long res_cs; int res_coff;  // residual added into raw (null -> none)
   int* error_flag;                   // set non-zero if an mbarrier wait times out
+  // ---- split-precision mode (one-tile kernel only; planner option `precision`): every feature map is stored as three
+  // bf16 planes [hi | lo | hi] per pixel (hi = bf16(v), lo = bf16(v - hi)), `*_seg` elements apart, so that a convolution
+  // over the 3C "channels" with weights [w_hi | w_hi | w_lo] computes hi*w_hi + lo*w_hi + hi*w_lo in the fp32
+  // accumulator: ~16 significant bits per operand instead of 8.  0 = plain bf16 storage. ----
+  long long out_seg, raw_seg, res_seg;
   // ---- output segments (persistent kernel, out-only epilogue): sibling 1x1 convolutions that read the same
   // tensor run as ONE GEMM whose N range is the concatenation of their output channels; segment g covers
   // channels [seg_end[g-1], seg_end[g]) and goes to its own tensor (seg_coff already has the segment start

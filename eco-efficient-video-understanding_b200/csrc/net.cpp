@@ -140,7 +140,7 @@ static int pool_out_dim(int in, int k, int s, int p) {
 }
 
 // =====================================================================================
-Net::Net(const std::string& text, int phase) : phase_(phase) {
+Net::Net(const std::string& text, int phase, const std::string& until_blob) : phase_(phase), until_blob_(until_blob) {
   proto_ = pt::parse(text);
   build_graph();
   infer_shapes();
@@ -150,6 +150,7 @@ Net::Net(const std::string& text, int phase) : phase_(phase) {
 Net::~Net() {
   free_plan();
   if (stage_) cudaFree(stage_);
+  if (push_event_) cudaEventDestroy(push_event_);
   if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
 
@@ -190,6 +191,14 @@ void Net::build_graph() {
   for (auto* v : net.all("layer"))
     if (v->msg && layer_in_phase(*v->msg, phase_)) lmsgs.push_back(v->msg.get());
 
+  if (!until_blob_.empty()) {
+    int last = -1;
+    for (size_t i = 0; i < lmsgs.size(); ++i)
+      for (auto& t : lmsgs[i]->strs("top"))
+        if (t == until_blob_) last = (int)i;
+    ECO_CHECK(last >= 0, "no layer produces blob '" << until_blob_ << "'");
+    lmsgs.resize((size_t)last + 1);
+  }
   for (auto& ni : net_inputs) {
     int t = add_tensor(ni.first);
     tensors_[t].shape = ni.second;
@@ -537,6 +546,7 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "multicast") multicast_ = v;
   else if (key == "fuse_1x1") fuse_1x1_ = v;
   else if (key == "debug_flags") debug_flags_ = v;
+  else if (key == "precision") precision_ = v;  // 0 bf16 storage (default), 1 split precision (fp32-faithful forward, ~3x the MMA work)
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
   else ECO_CHECK(false, "unknown option '" << key << "'");
   free_plan();
@@ -665,6 +675,7 @@ void Net::free_plan() {
   slots_.clear();
   slot_index_.clear();
   wgrad_scratch_ = nullptr;
+  reduce_scratch_ = nullptr;
   wgrad_scratch_bytes_ = 0;
   params_dev_newer_ = false;
   repack_ = true;
@@ -694,6 +705,7 @@ ClView Net::view(const Tensor& t) const {
   v.C = t.C();
   v.cs = t.cs;
   v.coff = t.coff;
+  v.seg = (precision_ && t.kind == Kind::CL) ? t.cs : 0;
   return v;
 }
 
@@ -1221,6 +1233,17 @@ void Net::plan() {
     KeepAllGuard(bool& r, bool force) : ref(r), saved(r) { if (force) ref = true; }
     ~KeepAllGuard() { ref = saved; }
   } keep_all_guard(keep_all_, train_);
+  // split precision runs on the one-tile kernel only (its epilogue has the three-plane store); the specialised kernels
+  // and fast-plan rewrites are switched off for this plan
+  struct IntGuard {
+    int& ref; int saved;
+    IntGuard(int& r, bool force, int v) : ref(r), saved(r) { if (force) ref = v; }
+    ~IntGuard() { ref = saved; }
+  };
+  ECO_CHECK(!(precision_ && train_), "option precision=1 is an inference mode (TRAIN-phase nets keep fp32 master weights instead)");
+  const bool prec = precision_ != 0;
+  IntGuard g1(persistent_, prec, 0), g2(pair_, prec, 0), g3(stem_rows_, prec, 0), g4(fuse_1x1_, prec, 0), g5(pool_commute_, prec, 0),
+      g6(halo_, prec, 0), g7(multicast_, prec, 0);
 
   // ---- 1. kinds ----
   for (auto& t : tensors_) {
@@ -1505,7 +1528,7 @@ void Net::plan() {
     if (t.kind == Kind::CL) {
       if (t.cs == 0) t.cs = round_up(t.C(), 8);
       ECO_CHECK(t.C() % 8 == 0 || t.cs >= t.C(), "bad channel stride");
-      t.dev_bytes = (size_t)(t.outer() * t.inner()) * (size_t)t.cs * 2;
+      t.dev_bytes = (size_t)(t.outer() * t.inner()) * (size_t)t.cs * 2 * (precision_ ? 3 : 1);
       t.dev = dalloc(t.dev_bytes, t.cs != t.C());
     } else {
       t.dev_bytes = (size_t)std::max<long long>(t.count(), 1) * 4;
@@ -1620,7 +1643,7 @@ void Net::plan() {
         kp.OD = c.O[0]; kp.OH = c.O[1]; kp.OW = c.O[2];
         kp.M = c.NB * c.O[0] * c.O[1] * c.O[2];
         c.stem = (x.kind == Kind::F32 && nsp == 2 && c.Cin == 3 && k[0] == 7 && k[1] == 7 && s[0] == 2 && s[1] == 2 &&
-                  pd[0] == 3 && pd[1] == 3);
+                  pd[0] == 3 && pd[1] == 3) && !precision_;
         if (c.stem) {
           // 7x7/s2/p3 over 3 channels == 4x4/s1 over 2x2 space-to-depth cells of the zero-padded image;
           // the 4 horizontally adjacent cells (4 x 16 ch) of a window are contiguous in memory, so the
@@ -1642,17 +1665,26 @@ void Net::plan() {
           if (x.kind == Kind::F32) {
             // generic fp32 input: convert to channels-last bf16 with channels padded to 8
             const int c8 = round_up(c.Cin, 8);
-            c.stem_bytes = (size_t)c.NB * c.I[0] * c.I[1] * c.I[2] * c8 * 2;
+            const int planes = precision_ ? 3 : 1;
+            c.stem_bytes = (size_t)c.NB * c.I[0] * c.I[1] * c.I[2] * c8 * 2 * planes;
             c.stem_in = static_cast<__nv_bfloat16*>(dalloc(c.stem_bytes, true));
             kp.x = c.stem_in;
-            kp.x_sW = c8;
-            c.Cin_k = c8;
+            kp.x_sW = c8 * planes;
+            c.Cin_k = c8 * planes;
+            c.cin_stride = c8;
           } else {
             ECO_CHECK(x.dev, "Convolution " << L.name << ": input " << x.name << " is not materialised");
             ECO_CHECK(x.C() % 8 == 0 && x.coff % 8 == 0 && x.cs % 8 == 0, "channel alignment");
             kp.x = static_cast<__nv_bfloat16*>(x.dev) + x.coff;
             kp.x_sW = x.cs;
             c.Cin_k = c.Cin;
+            c.cin_stride = (int)x.cs;
+            if (precision_) {
+              // the three planes [hi | lo | hi] of a whole buffer are the 3C "channels" of the GEMM's K axis
+              ECO_CHECK(x.coff == 0 && x.cs == x.C(), "precision=1: convolution " << L.name << " reads a channel slice of a larger buffer");
+              kp.x_sW = 3 * x.cs;
+              c.Cin_k = 3 * c.Cin;
+            }
           }
           kp.x_sH = kp.x_sW * c.I[2];
           kp.x_sD = kp.x_sH * c.I[1];
@@ -1724,9 +1756,10 @@ void Net::plan() {
           ECO_CHECK(t.dev && t.kind == Kind::CL, "conv " << L.name << ": tensor " << t.name << " has no channels-last storage");
           ECO_CHECK(t.cs % 8 == 0 && t.coff % 8 == 0, "channel alignment of " << t.name);
           ptr = static_cast<__nv_bfloat16*>(t.dev);
-          cs = t.cs;
+          cs = precision_ ? 3 * t.cs : t.cs;   // pixel stride
           coff = t.coff;
         };
+        auto seg_of = [&](int tid) -> long long { return (precision_ && tid >= 0) ? tensors_[tid].cs : 0; };
         if (!c.members.empty()) {
           ECO_CHECK(c.members.size() <= 4, "fused 1x1 group too large");
           kp.nseg = (int)c.members.size();
@@ -1749,6 +1782,9 @@ void Net::plan() {
         __nv_bfloat16* rp = nullptr;
         bind(c.res_tensor, rp, kp.res_cs, kp.res_coff);
         kp.res = rp;
+        kp.out_seg = seg_of(c.out_tensor);
+        kp.raw_seg = seg_of(c.raw_tensor);
+        kp.res_seg = seg_of(c.res_tensor);
         make_tensor_maps(c);  // may downgrade a_mode to the gather for this layer
         {
           const size_t per_stage = (size_t)kBlockM * 128 + (size_t)kp.block_n * 128;
@@ -2042,8 +2078,22 @@ void Net::upload_params() {
             for (int ch = 0; ch < c.Cin; ++ch)
               for (int t = 0; t < taps; ++t) {
                 const float v = w[((size_t)o * c.Cin + ch) * taps + t];
-                const size_t kidx = ((size_t)t * kp.cblocks + ch / kBlockK) * kBlockK + ch % kBlockK;
-                wp[(size_t)o * c.Ktotal + kidx] = f2bf(v);
+                if (!precision_) {
+                  const size_t kidx = ((size_t)t * kp.cblocks + ch / kBlockK) * kBlockK + ch % kBlockK;
+                  wp[(size_t)o * c.Ktotal + kidx] = f2bf(v);
+                  continue;
+                }
+                // planes of A are [hi | lo | hi]: weights [w_hi | w_hi | w_lo] give hi*w_hi + lo*w_hi + hi*w_lo
+                const uint16_t hi = f2bf(v);
+                uint32_t hb = (uint32_t)hi << 16;
+                float hf;
+                std::memcpy(&hf, &hb, 4);
+                const uint16_t lo = f2bf(v - hf);
+                for (int pl = 0; pl < 3; ++pl) {
+                  const int cc = pl * c.cin_stride + ch;
+                  const size_t kidx = ((size_t)t * kp.cblocks + cc / kBlockK) * kBlockK + cc % kBlockK;
+                  wp[(size_t)o * c.Ktotal + kidx] = pl == 2 ? lo : hi;
+                }
               }
         }
         CUDA_OK(cudaMemcpyAsync(c.w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice, stream_));
@@ -2185,6 +2235,35 @@ const float* Net::device_f32(int vb, size_t* count) {
   return static_cast<const float*>(t.dev);
 }
 
+void Net::push_frames(int dst_vb, Net& src, int src_vb) {
+  if (!planned_) plan();
+  if (!src.planned_) src.plan();
+  ECO_CHECK(dst_vb >= 0 && dst_vb < (int)vis_blobs_.size() && src_vb >= 0 && src_vb < (int)src.vis_blobs_.size(), "blob index out of range");
+  Tensor& d = tensors_[vis_blobs_[dst_vb].tensor];
+  Tensor& s = src.tensors_[src.vis_blobs_[src_vb].tensor];
+  ECO_CHECK(d.kind == Kind::CL && s.kind == Kind::CL && d.dev && s.dev && d.materialized && s.materialized,
+            "push_frames: both blobs must be materialised feature maps ('" << d.name << "', '" << s.name << "')");
+  ECO_CHECK(d.ch_axis == 1 && s.ch_axis == 1 && d.coff == 0 && s.coff == 0 && d.cs == d.C() && s.cs == s.C() && d.C() == s.C() &&
+                d.inner() == s.inner(), "push_frames: blobs must be dense [frames, C, ...] maps of equal frame size");
+  const int planes = precision_ ? 3 : 1;
+  ECO_CHECK((precision_ != 0) == (src.precision_ != 0), "push_frames: nets differ in precision mode");
+  const size_t row = (size_t)d.inner() * (size_t)d.cs * 2 * planes;
+  const long long F = d.outer(), k = s.outer();
+  ECO_CHECK(k >= 1 && k <= F, "push_frames: source has " << k << " frames, destination " << F);
+  if (!push_event_) CUDA_OK(cudaEventCreateWithFlags(&push_event_, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(push_event_, src.stream_));
+  CUDA_OK(cudaStreamWaitEvent(stream_, push_event_, 0));
+  char* base = static_cast<char*>(d.dev);
+  if (k < F) {  // overlapping move through the staging buffer (at most N - 1 frames of 150 KB)
+    const size_t tail = (size_t)(F - k) * row;
+    char* st = reinterpret_cast<char*>(staging(tail));
+    CUDA_OK(cudaMemcpyAsync(st, base + (size_t)k * row, tail, cudaMemcpyDeviceToDevice, stream_));
+    CUDA_OK(cudaMemcpyAsync(base, st, tail, cudaMemcpyDeviceToDevice, stream_));
+  }
+  CUDA_OK(cudaMemcpyAsync(base + (size_t)(F - k) * row, s.dev, (size_t)k * row, cudaMemcpyDeviceToDevice, stream_));
+  mark_written(vis_blobs_[dst_vb].tensor);
+}
+
 void Net::sync() {
   if (stream_) CUDA_OK(cudaStreamSynchronize(stream_));
   if (error_flag_dev_) {
@@ -2233,8 +2312,9 @@ void Net::run_input_xform(ConvOp& c, const float* src) {
     v.outer = c.NB;
     v.inner = (long long)c.I[0] * c.I[1] * c.I[2];
     v.C = c.Cin;
-    v.cs = c.Cin_k;
+    v.cs = precision_ ? c.cin_stride : c.Cin_k;
     v.coff = 0;
+    v.seg = precision_ ? c.cin_stride : 0;
     CUDA_OK(launch_f32_to_cl(in, v, stream_));
   }
 }
@@ -2256,7 +2336,8 @@ void Net::run_op(Op& op, bool with_xform) {
       break;
     }
     case Op::POOL_CL:
-      CUDA_OK(launch_pool_cl(op.pool, stream_));
+      if (precision_) CUDA_OK(launch_pool_cl_split(op.pool, tensors_[op.in0].cs, tensors_[op.out].cs, stream_));
+      else CUDA_OK(launch_pool_cl(op.pool, stream_));
       break;
     case Op::GLOBAL_AVG:
       CUDA_OK(launch_global_avg_cl(view(tensors_[op.in0]), static_cast<float*>(tensors_[op.out].dev), stream_));
@@ -2269,13 +2350,16 @@ void Net::run_op(Op& op, bool with_xform) {
                                    static_cast<float*>(tensors_[op.out].dev), op.M, op.N, op.Kd, stream_));
       break;
     case Op::SSR:
+      ECO_CHECK(!precision_, "precision=1: stand-alone BN / ReLU layers (" << op.name << ") are not supported; ECO's are fused");
       CUDA_OK(launch_scale_shift_relu_cl(view(tensors_[op.in0]), view(tensors_[op.out]), op.scale_dev, op.shift_dev,
                                          op.relu ? 1 : 0, stream_));
       break;
     case Op::ELTWISE:
+      ECO_CHECK(!precision_, "precision=1: stand-alone Eltwise (" << op.name << ") is not supported; ECO's are fused");
       CUDA_OK(launch_eltwise_sum_cl(view(tensors_[op.in0]), view(tensors_[op.in1]), view(tensors_[op.out]), stream_));
       break;
     case Op::COPY2D: {
+      ECO_CHECK(!precision_ || tensors_[op.out].kind == Kind::F32, "precision=1: Concat " << op.name << " needs a copy of a feature map");
       const char* src = static_cast<const char*>(tensors_[op.in0].dev) + op.src_off;
       char* dst = static_cast<char*>(tensors_[op.out].dev) + op.dst_off;
       CUDA_OK(cudaMemcpy2DAsync(dst, op.dst_pitch, src, op.src_pitch, op.width_bytes, op.rows, cudaMemcpyDeviceToDevice,

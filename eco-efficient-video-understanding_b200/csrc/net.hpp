@@ -130,6 +130,7 @@ struct ConvOp {
   int res_tensor = -1;  // residual input
   // geometry
   int nsp = 2, Cin = 0, Cin_k = 0, Cout = 0, Cout_pad = 0;
+  int cin_stride = 0;  // split precision: channels per plane of the input operand (plane p, channel c -> p * cin_stride + c)
   int K[3] = {1, 1, 1}, S[3] = {1, 1, 1}, P[3] = {0, 0, 0};
   int I[3] = {1, 1, 1}, O[3] = {1, 1, 1};
   int NB = 0;
@@ -220,7 +221,8 @@ struct Op {
 
 class Net {
  public:
-  Net(const std::string& text, int phase);
+  // `until_blob`: keep only the layers up to the last one that writes this blob (a trunk-only net for the online feature cache)
+  Net(const std::string& text, int phase, const std::string& until_blob = "");
   ~Net();
 
   // registry
@@ -254,6 +256,10 @@ class Net {
   int profile(eco_op_time* out, int cap);
   std::string describe_plan();
   int last_launches() const { return last_launches_; }
+  // online sliding window (scripts/online_recognition/online_recognition.py:64-93 recomputes all N frames per step): shift the
+  // frames (outer index) of a channels-last blob of THIS net towards 0 by the frame count of `src_blob` of net `src` and
+  // append those frames at the end, device to device, ordered after src's stream
+  void push_frames(int dst_vis_blob, Net& src, int src_vis_blob);
   void copy_from(const std::string& path);
   void save(const std::string& path) const;
   // ---- training path (train.cpp): Net::BackwardFromTo net.cpp:637-706, params()/diffs ----
@@ -279,6 +285,8 @@ class Net {
 
  private:
   std::shared_ptr<pt::Msg> proto_;
+  std::string until_blob_;
+  cudaEvent_t push_event_ = nullptr;
   std::vector<std::shared_ptr<pt::Msg>> keep_;
   std::map<std::string, int> tensor_index_;
   // options
@@ -296,6 +304,7 @@ class Net {
   int pool_commute_ = 1;  // 1: AVE 3x3/s1 pooling -> 1x1 conv (+BN+ReLU) runs as conv -> pooling(+bias+BN+ReLU) when nothing else reads the pooled blob
   int stem_rows_ = 1;  // 0: stem as 4x1 im2col GEMM; 1: rows kernel, pool1 folded in when its input has no other reader; 2: rows kernel, never fold the pool
   int debug_flags_ = 0;
+  int precision_ = 0;  // 1: split-precision storage (three bf16 planes hi|lo|hi per map, weights w_hi|w_hi|w_lo): ~fp32-faithful forward
   bool epi_staged_ = false;
   bool user_stream_ = false;
   // plan
@@ -356,6 +365,7 @@ class Net {
   std::vector<TrainAux> aux_;        // parallel to ops_
   std::vector<ConvOp> dgrads_;
   float* wgrad_scratch_ = nullptr;
+  float* reduce_scratch_ = nullptr;  // per-block partials of the deterministic per-channel reductions
   size_t wgrad_scratch_bytes_ = 0;
   bool params_dev_newer_ = false;    // arena newer than the host ParamBlobs (solver update, BN running statistics)
   bool repack_ = true;               // bf16 GEMM operands must be rebuilt from the arena

@@ -103,20 +103,30 @@ __global__ void colreduce_cl_kernel(ClView x, ClView y, ClView dy, const float* 
     }
   }
   __syncthreads();
+  // per-block partials go to `partial[block][C (x2)]`; colreduce_finish_kernel adds them in block order, so the result does
+  // not depend on the order in which blocks retire (run-to-run reproducible statistics and gradients)
+  float* dst = out + (size_t)blockIdx.x * C * (MODE == 2 ? 2 : 1);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f, b = 0.f;
     for (int l = 0; l < lanes; ++l) {
       a += r1[(size_t)l * C + c];
       if (MODE == 2) b += r2[(size_t)l * C + c];
     }
-    atomicAdd(out + c, a);
-    if (MODE == 2) atomicAdd(out + C + c, b);
+    dst[c] = a;
+    if (MODE == 2) dst[C + c] = b;
   }
+}
+__global__ void colreduce_finish_kernel(const float* __restrict__ partial, int blocks, int n, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float a = 0.f;
+  for (int b = 0; b < blocks; ++b) a += partial[(size_t)b * n + c];
+  out[c] += a;
 }
 
 template <int MODE>
 cudaError_t launch_colreduce(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, int relu, float* out,
-                             cudaStream_t st) {
+                             float* scratch, cudaStream_t st) {
   const long long rows = x.outer * x.inner;
   if (rows == 0 || x.C == 0) return cudaSuccess;
   if (x.C % 8 != 0) return cudaErrorInvalidValue;
@@ -127,9 +137,12 @@ cudaError_t launch_colreduce(ClView x, ClView y, ClView dy, const float* mean, c
   const int lanes = threads / G;
   const size_t smem = (size_t)lanes * x.C * sizeof(float) * (MODE == 2 ? 2 : 1);
   long long blocks = (rows + (long long)lanes * 8 - 1) / ((long long)lanes * 8);  // >= 8 rows per lane
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > kColReduceMaxBlocks) blocks = kColReduceMaxBlocks;
   if (blocks < 1) blocks = 1;
-  colreduce_cl_kernel<MODE><<<(unsigned)blocks, threads, smem, st>>>(x, y, dy, mean, inv_std, relu, out);
+  if (x.C > kColReduceMaxC || !scratch) return cudaErrorInvalidValue;
+  colreduce_cl_kernel<MODE><<<(unsigned)blocks, threads, smem, st>>>(x, y, dy, mean, inv_std, relu, scratch);
+  const int n = x.C * (MODE == 2 ? 2 : 1);
+  colreduce_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(scratch, (int)blocks, n, out);
   return cudaGetLastError();
 }
 
@@ -528,15 +541,15 @@ __global__ void sgd_update_kernel(float* __restrict__ w, float* __restrict__ dif
 }  // namespace
 
 // ================================================================================================
-cudaError_t launch_colsum_cl(ClView x, float* out, cudaStream_t st) {
-  return launch_colreduce<0>(x, x, x, nullptr, nullptr, 0, out, st);
+cudaError_t launch_colsum_cl(ClView x, float* out, float* scratch, cudaStream_t st) {
+  return launch_colreduce<0>(x, x, x, nullptr, nullptr, 0, out, scratch, st);
 }
-cudaError_t launch_colsqdev_cl(ClView x, const float* mean, float* out, cudaStream_t st) {
-  return launch_colreduce<1>(x, x, x, mean, nullptr, 0, out, st);
+cudaError_t launch_colsqdev_cl(ClView x, const float* mean, float* out, float* scratch, cudaStream_t st) {
+  return launch_colreduce<1>(x, x, x, mean, nullptr, 0, out, scratch, st);
 }
 cudaError_t launch_bn_bwd_sums_cl(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, int relu, float* out,
-                                  cudaStream_t st) {
-  return launch_colreduce<2>(x, y, dy, mean, inv_std, relu, out, st);
+                                  float* scratch, cudaStream_t st) {
+  return launch_colreduce<2>(x, y, dy, mean, inv_std, relu, out, scratch, st);
 }
 cudaError_t launch_bn_finish_mean(const float* sum, float* mean, int C, double count, cudaStream_t st) {
   bn_finish_mean_kernel<<<(C + 127) / 128, 128, 0, st>>>(sum, mean, C, count);

@@ -12,14 +12,18 @@
 namespace eco {
 
 // ---- per-channel reductions over a channels-last tensor (rows = outer*inner, C % 8 == 0) ----
+// Deterministic: per-block partials are written to `scratch` (kColReduceScratchFloats floats) and summed in block order.
+constexpr int kColReduceMaxBlocks = 296;   // 2 per SM
+constexpr int kColReduceMaxC = 2048;
+constexpr size_t kColReduceScratchFloats = (size_t)kColReduceMaxBlocks * kColReduceMaxC * 2;
 // out[0..C) += sum_rows x                                   (BN mean numerator, conv bias gradient)
-cudaError_t launch_colsum_cl(ClView x, float* out, cudaStream_t st);
+cudaError_t launch_colsum_cl(ClView x, float* out, float* scratch, cudaStream_t st);
 // out[0..C) += sum_rows (x - mean[c])^2                      (BN biased variance numerator, bn_layer.cpp:141-151)
-cudaError_t launch_colsqdev_cl(ClView x, const float* mean, float* out, cudaStream_t st);
+cudaError_t launch_colsqdev_cl(ClView x, const float* mean, float* out, float* scratch, cudaStream_t st);
 // BN backward sums (bn_layer.cpp:241-262): with g = dy * (y > 0 if relu) and xn = (x - mean) * inv_std
 //   out[0..C) += sum g ;  out[C..2C) += sum g * xn
 cudaError_t launch_bn_bwd_sums_cl(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, int relu,
-                                  float* out, cudaStream_t st);
+                                  float* out, float* scratch, cudaStream_t st);
 
 // BN TRAIN statistics (bn_layer.cpp:107-157): from sum / sqdev numerators to mean, biased variance, inverse std and the
 // running-average update  running = (1 - m) * batch + m * running

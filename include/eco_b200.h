@@ -97,6 +97,7 @@ int eco_net_forward(eco_net* net, int start, int end, float* loss);  /* layer in
  * (Solver::Step does that once per iteration, solver.cpp:178-195). */
 int eco_net_backward(eco_net* net, int start, int end);
 int eco_net_clear_param_diffs(eco_net* net);
+int eco_net_update(eco_net* net);   /* Net::Update (net.cpp:906-910): every parameter blob data -= diff, on the device arenas */
 /* fp32 host copy of a parameter gradient (layer->blobs()[i]->cpu_diff()), synced from the device */
 int eco_net_param_diff_host(eco_net* net, int layer, int blob_idx, float** data, size_t* count);
 
@@ -171,6 +172,14 @@ int eco_net_forward_pipelined(eco_net* net, const float* host_in, size_t count, 
 int eco_net_forward_pipelined_u8(eco_net* net, const unsigned char* host_in, size_t count, const float* mean, int nmean,
                                  float* host_out, size_t out_count, int* ticket);
 int eco_net_wait(eco_net* net, int ticket);
+
+/* ---- online sliding-window recognition (scripts/online_recognition/online_recognition.py:64-93) ----
+ * The reference recomputes the whole net on all N frames of the window for every new frame.  Frames are independent through
+ * the 2-D trunk, so a trunk-only net (the definition cut after `until_blob`, e.g. inception_3c_double_3x3_1_bn: 96x28x28 per
+ * frame) runs on the NEW frames only, their features are appended to the window held in the full net's own feature blob
+ * (older frames shift towards 0), and eco_net_forward(full, first_head_layer, -1) runs the 3-D head once. */
+int eco_net_create_from_string_until(const char* prototxt_text, int phase, const char* until_blob, eco_net** out);
+int eco_net_push_frames(eco_net* dst, int dst_blob, eco_net* src, int src_blob);
 int eco_host_alloc(void** ptr, size_t bytes);   /* page-locked host memory */
 int eco_host_free(void* ptr);
 

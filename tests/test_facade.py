@@ -27,6 +27,16 @@ int main(int argc, char** argv) {
   std::printf("res2b_bn axes=%d count=%d\n", v->num_axes(), v->count());
   try { v->num(); std::printf("legacy ok\n"); } catch (const std::exception& e) { std::printf("legacy: %s\n", e.what()); }
   std::printf("has res3a split: %d unknown: %d\n", (int)net.has_layer("res3a_res3a_2n_0_split"), (int)net.has_blob("nope"));
+  auto conv1 = net.layer_by_name("conv1_7x7_s2");
+  std::printf("conv1 type=%s blobs=%zu w=%dx%dx%dx%d params=%zu layers=%zu\n", conv1->type(), conv1->blobs().size(),
+              conv1->blobs()[0]->num(), conv1->blobs()[0]->channels(), conv1->blobs()[0]->height(), conv1->blobs()[0]->width(),
+              net.params().size(), net.layers().size());
+  conv1->blobs()[1]->mutable_cpu_data()[3] = 0.25f;
+  std::printf("bias[3]=%.2f asum>0:%d offset=%d\n", conv1->blobs()[1]->cpu_data()[3], (int)(conv1->blobs()[0]->asum_data() > 0),
+              conv1->blobs()[0]->offset(1, 2, 3, 4));
+  caffe::Net<float> twin(argv[1], caffe::TEST);
+  twin.ShareTrainedLayersWith(&net);
+  std::printf("shared bias[3]=%.2f\n", twin.layer_by_name("conv1_7x7_s2")->blobs()[1]->cpu_data()[3]);
   float* in = net.input_blobs()[0]->mutable_cpu_data();
   in[0] = 1.f;
   try { net.ForwardPrefilled(); std::printf("forward ok\n"); }
@@ -62,4 +72,7 @@ def test_facade_compiles_and_introspects(tmp_path):
     assert "res2b_bn axes=5 count=%d" % (96 * 16 * 28 * 28) in out
     assert "legacy: " in out and "legacy accessors" in out     # blob.hpp:141 behaviour on 5-D blobs
     assert "has res3a split: 1 unknown: 0" in out
+    assert "conv1 type=Convolution blobs=2 w=64x3x7x7 params=186 layers=116" in out, out
+    assert "bias[3]=0.25 asum>0:1 offset=%d" % (((1 * 3 + 2) * 7 + 3) * 7 + 4) in out
+    assert "shared bias[3]=0.25" in out
     assert ("forward ok" in out) or ("no CUDA device" in out)    # loud failure without a GPU, never a CPU fallback
