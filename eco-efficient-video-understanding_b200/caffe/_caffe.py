@@ -107,6 +107,7 @@ def lib():
     L.eco_host_free.argtypes = [C.c_void_p]
     L.eco_net_last_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.eco_net_profile_forward.argtypes = [C.c_void_p, C.POINTER(OpTime), C.c_int, C.POINTER(C.c_int)]
+    L.eco_net_profile_train.argtypes = [C.c_void_p, C.POINTER(OpTime), C.c_int, C.POINTER(C.c_int)]
     L.eco_net_describe_plan.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.eco_device_count.argtypes = [C.POINTER(C.c_int)]
     _lib = L

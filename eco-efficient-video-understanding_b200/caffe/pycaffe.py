@@ -325,6 +325,12 @@ class Net(object):
             rows.append(d)
         return rows
 
+    def profile_train(self, cap=4096):
+        arr = (_caffe.OpTime * cap)()
+        n = C.c_int()
+        check(lib().eco_net_profile_train(self._h, arr, cap, C.byref(n)))
+        return [dict(name=arr[i].name.decode(), kind=arr[i].kind, ms=arr[i].ms) for i in range(n.value)]
+
     def profile_forward(self, cap=1024):
         arr = (_caffe.OpTime * cap)()
         n = C.c_int()

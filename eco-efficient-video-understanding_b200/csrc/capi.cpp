@@ -396,6 +396,11 @@ int eco_net_profile_forward(eco_net* net, eco_op_time* out, int cap, int* n) {
   *n = N(net).profile(out, cap);
   ECO_API_END
 }
+int eco_net_profile_train(eco_net* net, eco_op_time* out, int cap, int* n) {
+  ECO_API_BEGIN
+  *n = N(net).profile_train(out, cap);
+  ECO_API_END
+}
 int eco_net_describe_plan(eco_net* net, char* buf, size_t cap, size_t* needed) {
   ECO_API_BEGIN
   const std::string d = N(net).describe_plan();

@@ -148,6 +148,8 @@ Net::Net(const std::string& text, int phase, const std::string& until_blob) : ph
 }
 
 Net::~Net() {
+  for (auto& t : tensors_)
+    if (t.h2d_done) cudaEventDestroy(t.h2d_done);
   free_plan();
   if (stage_) cudaFree(stage_);
   if (push_event_) cudaEventDestroy(push_event_);
@@ -676,6 +678,7 @@ void Net::free_plan() {
   slot_index_.clear();
   wgrad_scratch_ = nullptr;
   reduce_scratch_ = nullptr;
+  pool_mask_ = nullptr;
   wgrad_scratch_bytes_ = 0;
   params_dev_newer_ = false;
   repack_ = true;
@@ -2175,6 +2178,9 @@ void Net::upload(Tensor& t) {
   } else {
     CUDA_OK(cudaMemcpyAsync(t.dev, t.host.p, n * 4, cudaMemcpyHostToDevice, stream_));
   }
+  // the copy reads the pinned mirror asynchronously: whoever writes the mirror next must wait for it (host_data)
+  if (!t.h2d_done) CUDA_OK(cudaEventCreateWithFlags(&t.h2d_done, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(t.h2d_done, stream_));
   t.host_newer = false;
   t.dev_newer = false;
 }
@@ -2188,6 +2194,7 @@ float* Net::host_data(int vb, bool for_write, size_t* count) {
                         "keep_all_blobs=1 to materialise every blob");
   if (t.dev_newer && planned_) download(t);
   if (t.host.n != n) t.host.resize(n, true);
+  if (for_write && t.h2d_done) CUDA_OK(cudaEventSynchronize(t.h2d_done));  // a previous forward may still be reading the mirror
   if (for_write) t.host_newer = true;
   if (count) *count = n;
   return t.host.p;
@@ -2261,6 +2268,9 @@ void Net::push_frames(int dst_vb, Net& src, int src_vb) {
     CUDA_OK(cudaMemcpyAsync(base, st, tail, cudaMemcpyDeviceToDevice, stream_));
   }
   CUDA_OK(cudaMemcpyAsync(base + (size_t)(F - k) * row, s.dev, (size_t)k * row, cudaMemcpyDeviceToDevice, stream_));
+  // the source net must not overwrite its blob (next forward on ITS stream) before this copy has read it
+  CUDA_OK(cudaEventRecord(push_event_, stream_));
+  CUDA_OK(cudaStreamWaitEvent(src.stream_, push_event_, 0));
   mark_written(vis_blobs_[dst_vb].tensor);
 }
 

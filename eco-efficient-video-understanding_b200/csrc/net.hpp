@@ -65,6 +65,7 @@ struct Tensor {
   bool needs_grad = false;       // lies downstream of a parameter: Backward computes its diff
   bool diff_host_newer = false;  // host_diff written by the caller (seed for backward)
   bool diff_dev_newer = false;
+  cudaEvent_t h2d_done = nullptr;   // recorded after the last async upload from `host`: writers of the mirror wait for it
   int producer = -1;        // orig layer index that (last) writes it, -1: net input
   std::vector<int> consumers;  // orig layer indices reading it, in order
 
@@ -254,6 +255,8 @@ class Net {
   int num_params(int vis_layer) const;
   void mark_params_dirty(int vis_layer);
   int profile(eco_op_time* out, int cap);
+  // TRAIN nets: one forward + backward with a CUDA event after every op / backward sub-step (wgrad, dgrad, bias, ...)
+  int profile_train(eco_op_time* out, int cap);
   std::string describe_plan();
   int last_launches() const { return last_launches_; }
   // online sliding window (scripts/online_recognition/online_recognition.py:64-93 recomputes all N frames per step): shift the
@@ -365,11 +368,16 @@ class Net {
   std::vector<TrainAux> aux_;        // parallel to ops_
   std::vector<ConvOp> dgrads_;
   float* wgrad_scratch_ = nullptr;
+  unsigned char* pool_mask_ = nullptr;   // first-maximum indices of the MAX pooling being back-propagated
   float* reduce_scratch_ = nullptr;  // per-block partials of the deterministic per-channel reductions
   size_t wgrad_scratch_bytes_ = 0;
   bool params_dev_newer_ = false;    // arena newer than the host ParamBlobs (solver update, BN running statistics)
   bool repack_ = true;               // bf16 GEMM operands must be rebuilt from the arena
   unsigned long long train_iter_ = 0;
+  bool prof_on_ = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> prof_marks_;
+  std::vector<std::string> prof_names_;
+  void prof_mark(const std::string& name);
   int bucket_n_ = 0;
   BucketFn bucket_fn_ = nullptr;
   void* bucket_user_ = nullptr;

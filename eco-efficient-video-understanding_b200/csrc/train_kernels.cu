@@ -289,6 +289,92 @@ __global__ void pool_bwd_cl_kernel(const PoolParams p, const __nv_bfloat16* __re
   }
 }
 
+// MAX pooling backward in two passes (what caffe's max_idx_ mask does, pooling_layer.cpp:206-222 / :301-327, without
+// keeping the mask alive between forward and backward):
+//   1. pool_argmax_cl_kernel: per window and channel the position of the FIRST maximum in scan order, as a byte
+//      (kz * KH + ky) * KW + kx relative to the unclipped window start (255 = empty window)
+//   2. pool_max_bwd_mask_kernel: per input element, the windows that contain it (at most ceil(K/s) per axis) are looked up
+//      in the mask: 8 bytes of mask + 16 bytes of dy per window instead of re-scanning K^3 inputs per window
+__global__ void pool_argmax_cl_kernel(const PoolParams p, unsigned char* __restrict__ mask) {
+  const int G = p.C / 8;
+  const long long total = (long long)p.NB * p.OD * p.OH * p.OW * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long r = t / G;
+    const long long opix = r;
+    const int ox = (int)(r % p.OW); r /= p.OW;
+    const int oy = (int)(r % p.OH); r /= p.OH;
+    const int oz = (int)(r % p.OD);
+    const long long n = r / p.OD;
+    const int z0u = oz * p.sD - p.pD, y0u = oy * p.sH - p.pH, x0u = ox * p.sW - p.pW;
+    const int z1 = min(z0u + p.KD, p.ID), y1 = min(y0u + p.KH, p.IH), x1 = min(x0u + p.KW, p.IW);
+    const int z0 = max(z0u, 0), y0 = max(y0u, 0), x0 = max(x0u, 0);
+    float best[8];
+    unsigned int idx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -FLT_MAX; idx[j] = 255u; }
+    for (int z = z0; z < z1; ++z)
+      for (int yy = y0; yy < y1; ++yy)
+        for (int xx = x0; xx < x1; ++xx) {
+          const long long q = ((n * p.ID + z) * p.IH + yy) * p.IW + xx;
+          float v[8];
+          up8(ld8(p.x + q * p.x_cs + p.x_coff + g * 8), v);
+          const unsigned int code = (unsigned int)(((z - z0u) * p.KH + (yy - y0u)) * p.KW + (xx - x0u));
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (v[j] > best[j]) { best[j] = v[j]; idx[j] = code; }  // strictly greater: the first maximum wins
+        }
+    uint2 o;
+    o.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+    o.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+    *reinterpret_cast<uint2*>(mask + (opix * G + g) * 8) = o;
+  }
+}
+__global__ void pool_max_bwd_mask_kernel(const PoolParams p, const unsigned char* __restrict__ mask,
+                                         const __nv_bfloat16* __restrict__ dy, long long dy_cs, int dy_coff,
+                                         __nv_bfloat16* __restrict__ dx, long long dx_cs, int dx_coff, int accumulate) {
+  const int G = p.C / 8;
+  const long long total = (long long)p.NB * p.ID * p.IH * p.IW * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long r = t / G;
+    const long long ipix = r;
+    const int ix = (int)(r % p.IW); r /= p.IW;
+    const int iy = (int)(r % p.IH); r /= p.IH;
+    const int iz = (int)(r % p.ID);
+    const long long n = r / p.ID;
+    const int oz_lo = max(0, (iz + p.pD - p.KD + p.sD) / p.sD), oz_hi = min(p.OD - 1, (iz + p.pD) / p.sD);
+    const int oy_lo = max(0, (iy + p.pH - p.KH + p.sH) / p.sH), oy_hi = min(p.OH - 1, (iy + p.pH) / p.sH);
+    const int ox_lo = max(0, (ix + p.pW - p.KW + p.sW) / p.sW), ox_hi = min(p.OW - 1, (ix + p.pW) / p.sW);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oz = oz_lo; oz <= oz_hi; ++oz)
+      for (int oy = oy_lo; oy <= oy_hi; ++oy)
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          const long long opix = ((n * p.OD + oz) * p.OH + oy) * p.OW + ox;
+          const unsigned int me = (unsigned int)(((iz - (oz * p.sD - p.pD)) * p.KH + (iy - (oy * p.sH - p.pH))) * p.KW +
+                                                 (ix - (ox * p.sW - p.pW)));
+          const uint2 m = *reinterpret_cast<const uint2*>(mask + (opix * G + g) * 8);
+          float gv[8];
+          up8(ld8(dy + opix * dy_cs + dy_coff + g * 8), gv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (((m.x >> (8 * j)) & 255u) == me) acc[j] += gv[j];
+            if (((m.y >> (8 * j)) & 255u) == me) acc[4 + j] += gv[4 + j];
+          }
+        }
+    __nv_bfloat16* o = dx + ipix * dx_cs + dx_coff + g * 8;
+    if (accumulate) {
+      float old[8];
+      up8(ld8(o), old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += old[j];
+    }
+    *reinterpret_cast<uint4*>(o) = pk8(acc);
+  }
+}
+
 __global__ void global_avg_bwd_cl_kernel(const float* __restrict__ dy, ClView dx, int accumulate) {
   const int G = dx.C / 8;
   const long long total = dx.outer * dx.inner * G;
@@ -577,9 +663,15 @@ cudaError_t launch_bn_bwd_apply_cl(ClView x, ClView y, ClView dy, ClView dx, con
   return cudaGetLastError();
 }
 cudaError_t launch_pool_bwd_cl(const PoolParams& p, const __nv_bfloat16* dy, long long dy_cs, int dy_coff, __nv_bfloat16* dx,
-                               long long dx_cs, int dx_coff, int accumulate, cudaStream_t st) {
+                               long long dx_cs, int dx_coff, int accumulate, unsigned char* mask, cudaStream_t st) {
   const long long n = (long long)p.NB * p.ID * p.IH * p.IW * (p.C / 8);
   if (n == 0) return cudaSuccess;
+  if (p.is_max && mask && p.KD * p.KH * p.KW < 255) {
+    const long long no = (long long)p.NB * p.OD * p.OH * p.OW * (p.C / 8);
+    pool_argmax_cl_kernel<<<grid_for(no, 32), kT, 0, st>>>(p, mask);
+    pool_max_bwd_mask_kernel<<<grid_for(n, 32), kT, 0, st>>>(p, mask, dy, dy_cs, dy_coff, dx, dx_cs, dx_coff, accumulate);
+    return cudaGetLastError();
+  }
   pool_bwd_cl_kernel<<<grid_for(n, 32), kT, 0, st>>>(p, dy, dy_cs, dy_coff, dx, dx_cs, dx_coff, accumulate);
   return cudaGetLastError();
 }

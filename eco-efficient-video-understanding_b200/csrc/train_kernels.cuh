@@ -42,8 +42,11 @@ cudaError_t launch_bn_bwd_apply_cl(ClView x, ClView y, ClView dy, ClView dx, con
 // ---- pooling backward (pooling_layer.cpp:280-377), any 1..3-D window, channels-last bf16 ----
 // MAX: the gradient goes to the FIRST maximum of each window in scan order (the forward pass's strictly-greater update);
 // AVE: dy / pool_size (pad-inclusive divisor) to every in-image element.  Gather formulation: no atomics, deterministic.
+// `mask`: scratch of NB*OD*OH*OW*C bytes for the MAX path (first-maximum index per window and channel); NULL falls
+// back to re-scanning the windows
 cudaError_t launch_pool_bwd_cl(const PoolParams& p, const __nv_bfloat16* dy, long long dy_cs, int dy_coff,
-                               __nv_bfloat16* dx, long long dx_cs, int dx_coff, int accumulate, cudaStream_t st);
+                               __nv_bfloat16* dx, long long dx_cs, int dx_coff, int accumulate, unsigned char* mask,
+                               cudaStream_t st);
 // full-extent average pool: dx[o, i, c] (+)= dy[o, c] / inner
 cudaError_t launch_global_avg_bwd_cl(const float* dy, ClView dx, int accumulate, cudaStream_t st);
 

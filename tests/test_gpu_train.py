@@ -402,3 +402,30 @@ def test_test_phase_loss_and_accuracy(gpu):
     assert abs(float(out["loss"]) - float(want["loss"])) <= 2e-2 * max(1.0, float(want["loss"]))
     assert float(out["top1"]) == float(want["top1"]) == 0.5
     assert float(out["top5"]) == float(want["top5"]) == 1.0
+
+
+def test_backward_is_reproducible_run_to_run(gpu):
+    """Statistics, dgrad and the elementwise backward kernels are order-deterministic (per-block partials summed in block
+    order, no atomics on the activation path): two passes over the same batch give bit-identical blob gradients; only the
+    split-K weight gradient adds its partial sums with fp32 atomics (order varies at the 1e-6 level)."""
+    segments, batch, classes = 4, 2, 20
+    txt = gen.eco_lite_train(segments=segments, classes=classes, batch=batch).replace("dropout_ratio: 0.3", "dropout_ratio: 0")
+    net = train_net(txt)
+    load_params(net, refnet.RefNet(txt, phase="TRAIN").init_params(4321).params_dict())
+    x = refnet.eco_input(batch, segments).reshape(batch, 3 * segments, 224, 224)
+    lab = np.array([3, 11], np.float32).reshape(batch, 1, 1, 1)
+    runs = []
+    for _ in range(2):
+        net.blobs["data"].data[...] = x
+        net.blobs["label"].data[...] = lab
+        loss = float(net.forward()["loss"])
+        net.clear_param_diffs()
+        net.backward()
+        runs.append((loss, net.blobs["conv1_7x7_s2"].diff.copy(), net.blobs["res3a"].diff.copy(),
+                     net.params["conv1_7x7_s2"][0].diff.copy(), net.params["res5b_2"][0].diff.copy(),
+                     net.params["res3a_bn"][0].diff.copy()))
+    a, b = runs
+    assert a[0] == b[0]
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), "blob gradients differ between identical passes"
+    assert np.array_equal(a[5], b[5])
+    assert rel_max(a[3], b[3]) <= 1e-5 and rel_max(a[4], b[4]) <= 1e-5
