@@ -64,3 +64,37 @@ def test_shapes_lite_n16():
     assert s["res2b_bn_pre"] == [2, 16, 96, 28, 28] and s["res2b_bn"] == [2, 96, 16, 28, 28]
     assert s["res4a_1"] == [2, 256, 8, 14, 14] and s["res5b_bn"] == [2, 512, 4, 7, 7]
     assert s["global_pool"] == [2, 512, 1, 1, 1] and s["fc8"] == [2, 101]
+
+
+TRAIN_CASES = [
+    ("models_ECO_Lite/kinetics/ECO_Lite.prototxt", lambda: gen.eco_lite_train(16, 400, "fc8", 17, 0.3)),
+]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("path,make", TRAIN_CASES, ids=[c[0] for c in TRAIN_CASES])
+def test_generated_train_net_equals_reference_after_the_data_layers(path, make):
+    """the train/test definition: everything behind the VideoData layers (which the generator replaces by the two net
+    inputs they produce) must be the reference's graph: names, types, bottoms/tops, phase rules, every numeric parameter"""
+    ref = norm(prototxt.parse_file(os.path.join(REF, path)))
+    mine = norm(prototxt.parse(make()))
+    ref_layers = [l for l in ref["layer"] if l["type"] != ["VideoData"]]
+    assert len(ref_layers) == len(mine["layer"])
+    for a, b in zip(ref_layers, mine["layer"]):
+        assert a["name"] == b["name"] and a["type"] == b["type"], (a["name"], b["name"])
+        assert a.get("bottom") == b.get("bottom") and a.get("top") == b.get("top"), a["name"]
+        assert a.get("include") == b.get("include"), a["name"]
+        for key in ("convolution_param", "pooling_param", "inner_product_param", "reshape_param", "permute_param",
+                    "dropout_param", "accuracy_param", "eltwise_param", "concat_param"):
+            if key in a or key in b:
+                ra, rb = dict(a.get(key, [{}])[0]), dict(b.get(key, [{}])[0])
+                for filler in ("weight_filler", "bias_filler"):
+                    ra.pop(filler, None), rb.pop(filler, None)
+                assert ra == rb, (a["name"], key, ra, rb)
+        if a["type"] == ["BN"]:
+            fa = a.get("bn_param", [{}])[0].get("frozen", [False])
+            fb = b.get("bn_param", [{}])[0].get("frozen", [False])
+            assert fa == fb, a["name"]
+        assert a.get("param") == b.get("param"), (a["name"], a.get("param"), b.get("param"))
+    vd = [l for l in ref["layer"] if l["type"] == ["VideoData"]][0]
+    assert vd["top"] == ["data", "label"]
