@@ -334,6 +334,8 @@ def main():
     ap.add_argument("--buckets", type=int, default=3, help="train: gradient all-reduce buckets")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-calibrate", action="store_true", help="skip the BN calibration forwards of the weight harness (ncu captures)")
+    ap.add_argument("--h2d-chunks", type=int, default=0, help="blocking forward: 0 auto (4 sub-batches), 1 unsplit")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -380,13 +382,14 @@ def main():
     B, N = a.batch, a.segments
     classes = CLASSES if a.model == "lite" else 400
     txt = (gen.eco_full_deploy if a.model == "full" else gen.eco_lite_deploy)(segments=N, classes=classes, batch=B)
-    net = caffe.Net.from_string(txt, caffe.TEST, keep_all_blobs=0, use_graph=0 if a.no_graph else 1)
+    net = caffe.Net.from_string(txt, caffe.TEST, keep_all_blobs=0, use_graph=0 if a.no_graph else 1, h2d_chunks=a.h2d_chunks)
     # harness weights: random init of the right architecture, BN statistics calibrated on the device with a small
     # every-blob net (N=4, one clip) so activations stay O(1) like a trained net's and the parity check below means something
     make = gen.eco_full_deploy if a.model == "full" else gen.eco_lite_deploy
     small = caffe.Net.from_string(make(segments=4, classes=classes, batch=1), caffe.TEST, keep_all_blobs=1)
     harness.init_params(small, 4321)
-    harness.calibrate_bn_on_device(small, harness.synthetic_frames(1, 4))
+    if not a.no_calibrate:
+        harness.calibrate_bn_on_device(small, harness.synthetic_frames(1, 4))
     harness.copy_params(net, small)
     del small
     stream = torch.cuda.Stream()          # a real (non-legacy) stream: the events below are recorded on it
@@ -596,6 +599,9 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "videos/s", "h2d_bytes_per_step": int(count * 4),
                     "d2h_bytes_per_step": int(B * classes * 4), "ms_per_step": max(e2e_ms, wall_ms) / a.steps,
+                    "note": "caffe's blocking net.forward() on the fp32 input blob's (pinned) host mirror; inside the call the batch runs as "
+                            "sub-batches on sub-nets so the copy of slice k+1 overlaps the compute of slice k (option h2d_chunks, "
+                            "bit-identical logits)" if a.h2d_chunks != 1 else "caffe's blocking net.forward(), unsplit (h2d_chunks=1)",
                     "pipelined": {"value": e2e_pipe_value, "unit": "videos/s", "ms_per_step": pipe_ms / a.steps,
                                   "note": "eco_net_forward_pipelined: copy of step k+1 overlaps compute of step k; "
                                           "same bytes per step; wall clock"},

@@ -140,14 +140,24 @@ static int pool_out_dim(int in, int k, int s, int p) {
 }
 
 // =====================================================================================
-Net::Net(const std::string& text, int phase, const std::string& until_blob) : phase_(phase), until_blob_(until_blob) {
+Net::Net(const std::string& text, int phase, const std::string& until_blob) : phase_(phase), until_blob_(until_blob), text_(text) {
   proto_ = pt::parse(text);
   build_graph();
   infer_shapes();
   init_params();
 }
 
+void Net::release_subs() {
+  for (auto& s : sub_)
+    if (s && s->stream_) cudaStreamSynchronize(s->stream_);
+  sub_.clear();
+  for (auto e : sub_done_) cudaEventDestroy(e);
+  sub_done_.clear();
+  sub_params_version_ = ~0ull;
+}
+
 Net::~Net() {
+  release_subs();
   for (auto& t : tensors_)
     if (t.h2d_done) cudaEventDestroy(t.h2d_done);
   free_plan();
@@ -548,9 +558,11 @@ void Net::set_option(const std::string& key, int v) {
   else if (key == "multicast") multicast_ = v;
   else if (key == "fuse_1x1") fuse_1x1_ = v;
   else if (key == "debug_flags") debug_flags_ = v;
+  else if (key == "h2d_chunks") h2d_chunks_ = v;  // blocking forward with a host-newer input: 0 auto, 1 never split, n sub-batches
   else if (key == "precision") precision_ = v;  // 0 bf16 storage (default), 1 split precision (fp32-faithful forward, ~3x the MMA work)
   else if (key == "dual_m") dual_m_ = v;  // 0 off, 1 auto, 2 force wherever the accumulators fit
   else ECO_CHECK(false, "unknown option '" << key << "'");
+  release_subs();
   free_plan();
 }
 
@@ -560,6 +572,86 @@ void Net::set_stream(cudaStream_t s) {
   own_stream_ = false;
   user_stream_ = true;
   graph_valid_ = false;
+}
+
+// One caffe-style blocking forward(), pipelined inside: when the (single, large) input blob was written on the host, the
+// batch is cut into sub-batches of whole videos; sub-net k (same definition, same weights, own stream, own CUDA graph)
+// gets its slice by an asynchronous copy straight from the pinned host mirror and runs while slice k+1 is still on the
+// PCIe bus; the logits land in this net's output blob.  Videos are independent in TEST phase and the kernels' K order does
+// not depend on the batch size, so the result is bit-identical to the unsplit forward (tests/test_gpu_eco.py).
+bool Net::try_chunked_forward(int* launches) {
+  if (is_sub_ || train_ || keep_all_ || precision_ || h2d_chunks_ == 1 || !until_blob_.empty()) return false;
+  if (inputs_.size() != 1 || outputs_.size() != 1) return false;
+  Tensor& in = tensors_[vis_blobs_[inputs_[0]].tensor];
+  Tensor& out = tensors_[vis_blobs_[outputs_[0]].tensor];
+  if (in.kind != Kind::F32 || out.kind != Kind::F32 || in.host.empty() || !in.host.pinned || in.dev_newer) return false;
+  if (in.shape.size() < 2 || out.shape.size() != 2) return false;
+  const int frames = in.shape[0], videos = out.shape[0];
+  if (videos < 2 || frames % videos != 0) return false;
+  int chunks = h2d_chunks_;
+  if (chunks == 0) {  // auto: only when the copy is worth hiding (>= 64 MB) and sub-batches stay >= 4 videos
+    if ((size_t)in.count() * 4 < ((size_t)64 << 20)) return false;
+    chunks = 4;
+    while (chunks > 1 && (videos % chunks != 0 || videos / chunks < 4)) --chunks;
+  }
+  if (chunks < 2 || videos % chunks != 0) return false;
+  const int sub_videos = videos / chunks, sub_frames = frames / chunks;
+  if (sub_.size() != (size_t)chunks || sub_[0]->tensors_[sub_[0]->vis_blobs_[sub_[0]->inputs_[0]].tensor].shape[0] != sub_frames) {
+    release_subs();
+    for (int c = 0; c < chunks; ++c) {
+      std::unique_ptr<Net> n(new Net(text_, phase_));
+      n->is_sub_ = true;
+      n->a_mode_ = a_mode_; n->use_graph_ = use_graph_; n->persistent_ = persistent_; n->dual_m_ = dual_m_; n->halo_ = halo_;
+      n->fuse_1x1_ = fuse_1x1_; n->multicast_ = multicast_; n->pair_ = pair_; n->stem_gather_warps_ = stem_gather_warps_;
+      n->stem_direct_ = stem_direct_; n->pool_commute_ = pool_commute_; n->stem_rows_ = stem_rows_; n->epi_staged_ = epi_staged_;
+      std::vector<int> dims = in.shape;
+      dims[0] = sub_frames;
+      n->reshape_blob(n->inputs_[0], dims);
+      n->reshape();
+      sub_.push_back(std::move(n));
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      sub_done_.push_back(e);
+    }
+  }
+  if (sub_params_version_ != params_version_) {
+    for (auto& n : sub_)
+      for (size_t li = 0; li < layers_.size(); ++li)
+        for (size_t k = 0; k < layers_[li].params.size(); ++k) {
+          n->layers_[li].params[k].data = layers_[li].params[k].data;
+          n->layers_[li].params_dirty = true;
+        }
+    sub_params_version_ = params_version_;
+  }
+  const size_t in_chunk = (size_t)in.count() / chunks, out_chunk = (size_t)out.count() / chunks;
+  int total = 0;
+  // everything already queued on this net's stream (e.g. a previous forward writing the output blob) goes first
+  cudaEvent_t& gate = sub_done_[0];
+  (void)gate;
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  for (int c = 0; c < chunks; ++c) {
+    Net& n = *sub_[c];
+    if (!n.planned_) n.plan();
+    Tensor& nin = n.tensors_[n.vis_blobs_[n.inputs_[0]].tensor];
+    Tensor& nout = n.tensors_[n.vis_blobs_[n.outputs_[0]].tensor];
+    ECO_CHECK(nin.dev && nout.dev && (size_t)nin.count() == in_chunk && (size_t)nout.count() == out_chunk, "chunked forward: sub-net shapes");
+    CUDA_OK(cudaMemcpyAsync(nin.dev, in.host.p + (size_t)c * in_chunk, in_chunk * 4, cudaMemcpyHostToDevice, n.stream_));
+    nin.dev_newer = true;
+    n.forward(0, -1);
+    total += n.last_launches_;
+    CUDA_OK(cudaMemcpyAsync(static_cast<float*>(out.dev) + (size_t)c * out_chunk, nout.dev, out_chunk * 4, cudaMemcpyDeviceToDevice, n.stream_));
+    CUDA_OK(cudaEventRecord(sub_done_[c], n.stream_));
+  }
+  for (int c = 0; c < chunks; ++c) CUDA_OK(cudaStreamWaitEvent(stream_, sub_done_[c], 0));
+  // the host mirror may be rewritten once the last slice has left it
+  if (!in.h2d_done) CUDA_OK(cudaEventCreateWithFlags(&in.h2d_done, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(in.h2d_done, sub_[chunks - 1]->stream_));
+  in.host_newer = false;
+  mark_written(vis_blobs_[outputs_[0]].tensor);
+  chunked_last_ = true;
+  (void)sub_videos;
+  if (launches) *launches = total;
+  return true;
 }
 
 void Net::reshape_blob(int vb, const std::vector<int>& dims) {
@@ -595,10 +687,12 @@ void Net::set_param(int vl, int idx, const float* data, size_t count) {
                                                                        << b.data.size());
   std::memcpy(b.data.data(), data, count * sizeof(float));
   layers_[vis_layers_[vl].orig].params_dirty = true;
+  ++params_version_;
 }
 void Net::mark_params_dirty(int vl) {
   const int o = vis_layers_[vl].orig;
   if (o >= 0) layers_[o].params_dirty = true;
+  ++params_version_;
 }
 
 // =====================================================================================
@@ -2192,6 +2286,13 @@ float* Net::host_data(int vb, bool for_write, size_t* count) {
   ECO_CHECK(!planned_ || t.materialized,
             "blob '" << t.name << "' is fused away in the current plan and has no data; create the net with option "
                         "keep_all_blobs=1 to materialise every blob");
+  if (chunked_last_ && planned_) {
+    bool io = false;
+    for (int q : inputs_) io |= tensors_[vis_blobs_[q].tensor].root == t.root;
+    for (int q : outputs_) io |= tensors_[vis_blobs_[q].tensor].root == t.root;
+    ECO_CHECK(io, "blob '" << t.name << "' was not produced in this net's buffers: the last forward ran split into sub-batches "
+                            "(option h2d_chunks); create the net with h2d_chunks=1 or keep_all_blobs=1 to inspect intermediate blobs");
+  }
   if (t.dev_newer && planned_) download(t);
   if (t.host.n != n) t.host.resize(n, true);
   if (for_write && t.h2d_done) CUDA_OK(cudaEventSynchronize(t.h2d_done));  // a previous forward may still be reading the mirror
@@ -2527,6 +2628,15 @@ float Net::forward(int start, int end) {
       hi = std::max(hi, vis_layers_[v].orig);
     }
   const bool full = (start == 0 && end == NV - 1);
+  chunked_last_ = false;
+  if (full) {
+    int cl = 0;
+    if (try_chunked_forward(&cl)) {
+      last_launches_ = cl;
+      last_loss_ = 0.f;
+      return 0.f;
+    }
+  }
   // host-modified blobs go up first (net inputs are always re-sent: the caller owns that memory)
   for (int vb : inputs_) {
     Tensor& t = tensors_[vis_blobs_[vb].tensor];

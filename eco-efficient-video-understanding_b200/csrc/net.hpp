@@ -289,6 +289,17 @@ class Net {
  private:
   std::shared_ptr<pt::Msg> proto_;
   std::string until_blob_;
+  std::string text_;
+  // chunked blocking forward (option h2d_chunks): the batch is split into sub-batches, each run by a sub-net on its own
+  // stream, so the host->device copy of sub-batch k+1 overlaps the compute of sub-batch k inside ONE caffe-style forward()
+  int h2d_chunks_ = 0;                       // 0 auto, 1 off, n force
+  std::vector<std::unique_ptr<Net>> sub_;
+  std::vector<cudaEvent_t> sub_done_;
+  unsigned long long params_version_ = 0, sub_params_version_ = ~0ull;
+  bool chunked_last_ = false;
+  bool is_sub_ = false;
+  bool try_chunked_forward(int* launches);
+  void release_subs();
   cudaEvent_t push_event_ = nullptr;
   std::vector<std::shared_ptr<pt::Msg>> keep_;
   std::map<std::string, int> tensor_index_;

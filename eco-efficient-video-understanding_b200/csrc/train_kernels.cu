@@ -116,12 +116,23 @@ __global__ void colreduce_cl_kernel(ClView x, ClView y, ClView dy, const float* 
     if (MODE == 2) dst[C + c] = b;
   }
 }
+// 32 channels x 8 slices per CTA: slice s adds the partials of blocks s, s + 8, ... in order, then the 8 slice sums are added
+// in slice order -- a fixed summation tree, so the result is independent of scheduling (and 8 loads are in flight per channel)
 __global__ void colreduce_finish_kernel(const float* __restrict__ partial, int blocks, int n, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+  __shared__ float part[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int sl = threadIdx.y;
   float a = 0.f;
-  for (int b = 0; b < blocks; ++b) a += partial[(size_t)b * n + c];
-  out[c] += a;
+  if (c < n)
+    for (int b = sl; b < blocks; b += 8) a += partial[(size_t)b * n + c];
+  part[sl][threadIdx.x] = a;
+  __syncthreads();
+  if (sl == 0 && c < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += part[q][threadIdx.x];
+    out[c] += t;
+  }
 }
 
 template <int MODE>
@@ -142,7 +153,7 @@ cudaError_t launch_colreduce(ClView x, ClView y, ClView dy, const float* mean, c
   if (x.C > kColReduceMaxC || !scratch) return cudaErrorInvalidValue;
   colreduce_cl_kernel<MODE><<<(unsigned)blocks, threads, smem, st>>>(x, y, dy, mean, inv_std, relu, scratch);
   const int n = x.C * (MODE == 2 ? 2 : 1);
-  colreduce_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(scratch, (int)blocks, n, out);
+  colreduce_finish_kernel<<<(n + 31) / 32, dim3(32, 8, 1), 0, st>>>(scratch, (int)blocks, n, out);
   return cudaGetLastError();
 }
 

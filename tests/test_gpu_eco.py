@@ -208,3 +208,34 @@ def test_pipelined_uint8_frames_match_fp32_path(gpu):
         assert np.array_equal(hout.reshape(batch, 101), want)
     _caffe.lib().eco_host_free(pi)
     _caffe.lib().eco_host_free(po)
+
+
+def test_chunked_blocking_forward_is_bit_identical(gpu):
+    """One caffe-style forward() on a host-written input blob runs split into sub-batches (H2D of slice k+1 under the compute
+    of slice k, option h2d_chunks); videos are independent and the kernels' K order does not depend on the batch size, so
+    the logits are bit-identical to the unsplit forward."""
+    segments, batch = 4, 8
+    txt, ref, _ = oracle_lite(segments, 1)
+    txt = gen.eco_lite_deploy(segments=segments, classes=101, batch=batch)
+    x = refnet.eco_input(batch, segments)
+    plain = make_net(txt, keep_all=False, graph=True, h2d_chunks=1)
+    plain.set_option("persistent", 1)
+    load_params(plain, ref.params_dict())
+    plain.blobs["data"].data[...] = x
+    want = plain.forward()["fc8"].copy()
+    _ = plain.blobs["pool1_3x3_s2"].data          # unsplit: materialised blobs of the fast plan stay readable
+    for chunks in (2, 4):
+        net = make_net(txt, keep_all=False, graph=True, h2d_chunks=chunks)
+        net.set_option("persistent", 1)
+        load_params(net, ref.params_dict())
+        for rep in range(3):                      # repeated calls, rewritten input, CUDA-graph replay in the sub-nets
+            xi = np.roll(x, rep * segments, axis=0)
+            net.blobs["data"].data[...] = xi
+            got = net.forward()["fc8"].copy()
+            assert np.array_equal(got, np.roll(want, rep, axis=0)), (chunks, rep)
+        with pytest.raises(RuntimeError, match="sub-batches"):
+            net.blobs["pool1_3x3_s2"].data
+        # new weights reach the sub-nets
+        net.params["fc8u"][1].data[...] += 1.0
+        net.blobs["data"].data[...] = x
+        assert np.allclose(net.forward()["fc8"], want + 1.0, atol=1e-5)
