@@ -8,6 +8,7 @@
 #include "../../include/eco_b200.h"
 #include "net.hpp"
 #include "solver.hpp"
+#include "transform.cuh"
 
 struct eco_net {
   eco::Net* impl;
@@ -429,6 +430,60 @@ int eco_net_grad_bucket(eco_net* net, int i, size_t* offset, size_t* count) {
   if (i < 0 || i >= (int)b.size()) throw std::runtime_error("bucket index out of range");
   *offset = b[i].off;
   *count = b[i].count;
+  ECO_API_END
+}
+
+/* ---- sampling + DataTransformer on the GPU ---- */
+struct eco_sampler {
+  std::mt19937 frame_rng, transform_rng;
+};
+int eco_sampler_create(unsigned int seed, eco_sampler** out) {
+  ECO_API_BEGIN
+  eco_sampler* s = new eco_sampler;
+  s->frame_rng.seed(seed);
+  s->transform_rng.seed(seed + 1u);
+  *out = s;
+  ECO_API_END
+}
+int eco_sampler_destroy(eco_sampler* s) {
+  ECO_API_BEGIN
+  delete s;
+  ECO_API_END
+}
+int eco_sample_segment_offsets(eco_sampler* s, int num_frames, int num_segments, int new_length, int train, int* offsets) {
+  ECO_API_BEGIN
+  if (!s || !offsets || num_segments <= 0) throw std::runtime_error("bad argument");
+  eco::sample_segment_offsets(num_frames, num_segments, new_length, train != 0, s->frame_rng, offsets);
+  ECO_API_END
+}
+int eco_sample_clip_transform(eco_sampler* s, int H, int W, int crop_size, int train, const eco_transform_param* p, eco_clip_transform* out) {
+  ECO_API_BEGIN
+  if (!s || !p || !out) throw std::runtime_error("null argument");
+  if (crop_size && (H < crop_size || W < crop_size)) throw std::runtime_error("datum smaller than crop_size");  // CHECK_GE :169-170
+  *out = eco::sample_clip_transform(H, W, crop_size, train != 0, *p, s->transform_rng);
+  ECO_API_END
+}
+int eco_crop_size_candidates(int H, int W, int crop_size, int max_distort, const float* ratios, int nratios, int* hw, int* n) {
+  ECO_API_BEGIN
+  auto c = eco::crop_size_candidates(H, W, crop_size, crop_size, max_distort, std::vector<float>(ratios, ratios + (ratios ? nratios : 0)));
+  if ((int)c.size() > *n) throw std::runtime_error("capacity too small");
+  for (size_t i = 0; i < c.size(); ++i) { hw[2 * i] = c[i].first; hw[2 * i + 1] = c[i].second; }
+  *n = (int)c.size();
+  ECO_API_END
+}
+int eco_fix_offset_candidates(int H, int W, int crop_h, int crop_w, int more, int* hw, int* n) {
+  ECO_API_BEGIN
+  auto c = eco::fix_offset_candidates(H, W, crop_h, crop_w, more != 0);
+  if ((int)c.size() > *n) throw std::runtime_error("capacity too small");
+  for (size_t i = 0; i < c.size(); ++i) { hw[2 * i] = c[i].first; hw[2 * i + 1] = c[i].second; }
+  *n = (int)c.size();
+  ECO_API_END
+}
+int eco_net_transform_input_u8(eco_net* net, int blob, const unsigned char* src, int B, int C, int H, int W,
+                               const eco_clip_transform* t, const eco_transform_param* p) {
+  ECO_API_BEGIN
+  if (!src || !t || !p) throw std::runtime_error("null argument");
+  N(net).transform_input_u8(blob, src, B, C, H, W, t, *p);
   ECO_API_END
 }
 

@@ -22,6 +22,7 @@
 #include <stdexcept>
 
 #include "../../include/eco_b200.h"
+#include "transform.cuh"
 
 namespace eco {
 
@@ -162,6 +163,7 @@ Net::~Net() {
     if (t.h2d_done) cudaEventDestroy(t.h2d_done);
   free_plan();
   if (stage_) cudaFree(stage_);
+  if (xf_src_) cudaFree(xf_src_);
   if (push_event_) cudaEventDestroy(push_event_);
   if (own_stream_ && stream_) cudaStreamDestroy(stream_);
 }
@@ -2373,6 +2375,42 @@ void Net::push_frames(int dst_vb, Net& src, int src_vb) {
   CUDA_OK(cudaEventRecord(push_event_, stream_));
   CUDA_OK(cudaStreamWaitEvent(src.stream_, push_event_, 0));
   mark_written(vis_blobs_[dst_vb].tensor);
+}
+
+void Net::transform_input_u8(int vb, const unsigned char* src, int B, int C, int H, int W, const eco_clip_transform* t,
+                             const eco_transform_param& p) {
+  if (!planned_) plan();
+  ECO_CHECK(vb >= 0 && vb < (int)vis_blobs_.size(), "blob index out of range");
+  Tensor& x = tensors_[vis_blobs_[vb].tensor];
+  ECO_CHECK(x.kind == Kind::F32 && x.dev && x.shape.size() == 4, "transform_input_u8: '" << x.name << "' is not a plain fp32 input blob");
+  ECO_CHECK(x.shape[0] == B && x.shape[1] == C && x.shape[2] == x.shape[3], "transform_input_u8: blob is "
+                << x.shape[0] << "x" << x.shape[1] << "x" << x.shape[2] << "x" << x.shape[3] << ", clips are " << B << "x" << C);
+  const int crop = x.shape[2];
+  for (int b = 0; b < B; ++b)
+    ECO_CHECK(t[b].h_off >= 0 && t[b].w_off >= 0 && t[b].crop_h > 0 && t[b].crop_w > 0 && t[b].h_off + t[b].crop_h <= H &&
+                  t[b].w_off + t[b].crop_w <= W, "transform_input_u8: crop window of clip " << b << " leaves the " << H << "x" << W << " datum");
+  const size_t img = (size_t)B * C * H * W;
+  const size_t tb = (size_t)B * sizeof(eco_clip_transform), mb = 16 * sizeof(float);
+  const size_t need = ((img + 255) / 256) * 256 + ((tb + 255) / 256) * 256 + mb;
+  if (need > xf_src_bytes_) {
+    if (xf_src_) { CUDA_OK(cudaStreamSynchronize(stream_)); cudaFree(xf_src_); xf_src_ = nullptr; }
+    CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&xf_src_), need));
+    xf_src_bytes_ = need;
+  }
+  unsigned char* d_img = xf_src_;
+  eco_clip_transform* d_t = reinterpret_cast<eco_clip_transform*>(xf_src_ + ((img + 255) / 256) * 256);
+  float* d_mean = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(d_t) + ((tb + 255) / 256) * 256);
+  CUDA_OK(cudaMemcpyAsync(d_img, src, img, cudaMemcpyHostToDevice, stream_));
+  CUDA_OK(cudaMemcpyAsync(d_t, t, tb, cudaMemcpyHostToDevice, stream_));
+  const int nmean = std::max(0, std::min(16, p.num_mean));
+  if (nmean) CUDA_OK(cudaMemcpyAsync(d_mean, p.mean_value, (size_t)nmean * 4, cudaMemcpyHostToDevice, stream_));
+  CUDA_OK(launch_transform_u8(d_img, static_cast<float*>(x.dev), B, C, H, W, crop, d_t, d_mean, nmean, p.scale == 0.f ? 1.f : p.scale,
+                              p.is_flow, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));  // src / t are the caller's (possibly pageable) memory
+  x.host_newer = false;
+  x.dev_newer = true;
+  for (auto& q : tensors_)
+    if (q.root == x.root && q.materialized) q.dev_newer = true;
 }
 
 void Net::sync() {

@@ -18,6 +18,8 @@
 #include "wgrad_umma.cuh"
 
 struct eco_op_time;
+struct eco_clip_transform;
+struct eco_transform_param;
 
 namespace eco {
 
@@ -263,6 +265,9 @@ class Net {
   // frames (outer index) of a channels-last blob of THIS net towards 0 by the frame count of `src_blob` of net `src` and
   // append those frames at the end, device to device, ordered after src's stream
   void push_frames(int dst_vis_blob, Net& src, int src_vis_blob);
+  // DataTransformer::Transform on the GPU into an fp32 input blob (transform.cuh)
+  void transform_input_u8(int vis_blob, const unsigned char* src, int B, int C, int H, int W, const eco_clip_transform* t,
+                          const eco_transform_param& p);
   void copy_from(const std::string& path);
   void save(const std::string& path) const;
   // ---- training path (train.cpp): Net::BackwardFromTo net.cpp:637-706, params()/diffs ----
@@ -366,6 +371,8 @@ class Net {
   bool plan_halo(ConvOp& c);
   void plan_stem_rows(ConvOp& c);
   bool is_stem_conv(const OrigLayer& L) const;
+  unsigned char* xf_src_ = nullptr;   // staged uint8 clips, transforms and means of transform_input_u8
+  size_t xf_src_bytes_ = 0;
   float* stage_ = nullptr;
   size_t stage_bytes_ = 0;
   float* staging(size_t bytes);

@@ -183,6 +183,33 @@ int eco_net_push_frames(eco_net* dst, int dst_blob, eco_net* src, int src_blob);
 int eco_host_alloc(void** ptr, size_t bytes);   /* page-locked host memory */
 int eco_host_free(void* ptr);
 
+/* ---- the step in front of the path: VideoDataLayer's sampling and DataTransformer::Transform ----
+ * video_data_layer.cpp:134-238 picks N frames per video (TRAIN: a random offset inside each of N equal segments, TEST: the
+ * centres), stacks them as a Datum [3N, H, W] and DataTransformer::Transform (data_transformer.cpp:148-326) crops (multi-scale
+ * sizes x fixed offsets), resizes to crop_size with cv::resize, mirrors, subtracts the mean.  Here the host draws the same
+ * choices (std::mt19937, `rng() % n` like caffe's rng_t) and the GPU does the pixel work straight into the net's input blob.
+ * JPEG decoding is not part of this library: the caller hands over decoded uint8 frames. */
+typedef struct eco_clip_transform { int h_off, w_off, crop_h, crop_w, mirror; } eco_clip_transform;
+typedef struct eco_transform_param {   /* TransformationParameter, caffe.proto */
+  int mirror, multi_scale, fix_crop, more_fix_crop, max_distort, is_flow;
+  int num_scale_ratios;
+  float scale_ratios[8];
+  float scale;
+  int num_mean;
+  float mean_value[16];
+} eco_transform_param;
+typedef struct eco_sampler eco_sampler;   /* holds the mt19937 streams (frame sampling, transform choices) */
+int eco_sampler_create(unsigned int seed, eco_sampler** out);
+int eco_sampler_destroy(eco_sampler* s);
+int eco_sample_segment_offsets(eco_sampler* s, int num_frames, int num_segments, int new_length, int train, int* offsets /* [num_segments] */);
+int eco_sample_clip_transform(eco_sampler* s, int H, int W, int crop_size, int train, const eco_transform_param* p, eco_clip_transform* out);
+int eco_crop_size_candidates(int H, int W, int crop_size, int max_distort, const float* ratios, int nratios, int* hw_pairs, int* n /* in: capacity in pairs */);
+int eco_fix_offset_candidates(int H, int W, int crop_h, int crop_w, int more, int* hw_pairs, int* n);
+/* transform B clips (uint8 Datum layout [B][C][H][W], host memory) into input blob `blob` of the net (fp32 [B][C][crop][crop]
+ * on the device, no host round trip of the floats); `t` = one transform per clip */
+int eco_net_transform_input_u8(eco_net* net, int blob, const unsigned char* src, int B, int C, int H, int W,
+                               const eco_clip_transform* t, const eco_transform_param* p);
+
 /* ---- measurement hooks used by bench.py ---- */
 /* number of kernels this library launched for the last eco_net_forward on this net */
 int eco_net_last_launch_count(const eco_net* net, int* launches);
