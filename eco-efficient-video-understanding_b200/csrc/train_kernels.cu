@@ -50,20 +50,21 @@ inline int grid_for(long long items, int cap_mult = 8) {
 //   MODE 2: g = dy * (y > 0 if relu); S1 = sum g, S2 = sum g * (x - mean) * inv_std
 template <int MODE>
 __global__ void colreduce_cl_kernel(ClView x, ClView y, ClView dy, const float* __restrict__ mean,
-                                    const float* __restrict__ inv_std, int relu, float* __restrict__ out) {
+                                    const float* __restrict__ inv_std, const float* __restrict__ slope,
+                                    const float* __restrict__ bias, int relu, float* __restrict__ out) {
   extern __shared__ float red[];  // [lanes][G*8] (x2 for MODE 2)
   const int G = x.C / 8;
   const long long rows = x.outer * x.inner;
   const int lanes = blockDim.x / G;  // row lanes per block (>= 1: launcher guarantees G <= blockDim.x)
   const int g = threadIdx.x % G, lane = threadIdx.x / G;
-  float s1[8], s2[8], mu[8], is[8];
+  float s1[8], s2[8], mu[8], is[8], sl[8], bi[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; mu[j] = 0.f; is[j] = 1.f; }
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; mu[j] = 0.f; is[j] = 1.f; sl[j] = 1.f; bi[j] = 0.f; }
   if (MODE >= 1 && lane < lanes) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       mu[j] = mean[g * 8 + j];
-      if (MODE == 2) is[j] = inv_std[g * 8 + j];
+      if (MODE == 2) { is[j] = inv_std[g * 8 + j]; sl[j] = slope[g * 8 + j]; bi[j] = bias[g * 8 + j]; }
     }
   }
   if (lane < lanes) {
@@ -77,17 +78,16 @@ __global__ void colreduce_cl_kernel(ClView x, ClView y, ClView dy, const float* 
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = xv[j] - mu[j]; s1[j] = fmaf(d, d, s1[j]); }
       } else {
-        float gv[8], yv[8];
+        float gv[8];
         up8(ld8(dy.ptr + r * dy.cs + dy.coff + g * 8), gv);
-        if (relu) {
-          up8(ld8(y.ptr + r * y.cs + y.coff + g * 8), yv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
-        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          const float xn = (xv[j] - mu[j]) * is[j];
+          // ReLU mask recomputed from x exactly as the forward kernel formed the pre-activation (bf16 keeps fp32's exponent
+          // range, so y > 0 <=> pre-activation > 0): the stored output is not read again
+          if (relu && !(xn * sl[j] + bi[j] > 0.f)) gv[j] = 0.f;
           s1[j] += gv[j];
-          s2[j] = fmaf(gv[j], (xv[j] - mu[j]) * is[j], s2[j]);
+          s2[j] = fmaf(gv[j], xn, s2[j]);
         }
       }
     }
@@ -136,8 +136,8 @@ __global__ void colreduce_finish_kernel(const float* __restrict__ partial, int b
 }
 
 template <int MODE>
-cudaError_t launch_colreduce(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, int relu, float* out,
-                             float* scratch, cudaStream_t st) {
+cudaError_t launch_colreduce(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, const float* slope,
+                             const float* bias, int relu, float* out, float* scratch, cudaStream_t st) {
   const long long rows = x.outer * x.inner;
   if (rows == 0 || x.C == 0) return cudaSuccess;
   if (x.C % 8 != 0) return cudaErrorInvalidValue;
@@ -151,10 +151,83 @@ cudaError_t launch_colreduce(ClView x, ClView y, ClView dy, const float* mean, c
   if (blocks > kColReduceMaxBlocks) blocks = kColReduceMaxBlocks;
   if (blocks < 1) blocks = 1;
   if (x.C > kColReduceMaxC || !scratch) return cudaErrorInvalidValue;
-  colreduce_cl_kernel<MODE><<<(unsigned)blocks, threads, smem, st>>>(x, y, dy, mean, inv_std, relu, scratch);
+  colreduce_cl_kernel<MODE><<<(unsigned)blocks, threads, smem, st>>>(x, y, dy, mean, inv_std, slope, bias, relu, scratch);
   const int n = x.C * (MODE == 2 ? 2 : 1);
   colreduce_finish_kernel<<<(n + 31) / 32, dim3(32, 8, 1), 0, st>>>(scratch, (int)blocks, n, out);
   return cudaGetLastError();
+}
+
+// ---- single-pass batch statistics (Welford per thread, Chan's pairwise combination in a fixed order) ----
+// One read of the tensor gives mean and the sum of squared deviations without the E[x^2] - mean^2 cancellation.
+__device__ __forceinline__ void chan_combine(float& nA, float& meanA, float& m2A, float nB, float meanB, float m2B) {
+  if (nB == 0.f) return;
+  if (nA == 0.f) { nA = nB; meanA = meanB; m2A = m2B; return; }
+  const float n = nA + nB, d = meanB - meanA;
+  meanA += d * (nB / n);
+  m2A += m2B + d * d * (nA * nB / n);
+  nA = n;
+}
+__global__ void bn_welford_cl_kernel(ClView x, float* __restrict__ partial /* [blocks][2C] mean, M2 */, float* __restrict__ counts) {
+  extern __shared__ float red[];  // [lanes][2C] + [lanes] counts
+  const int G = x.C / 8, C = x.C;
+  const long long rows = x.outer * x.inner;
+  const int lanes = blockDim.x / G;
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  float mean[8], m2[8], n = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mean[j] = 0.f; m2[j] = 0.f; }
+  if (lane < lanes) {
+    for (long long r = (long long)blockIdx.x * lanes + lane; r < rows; r += (long long)gridDim.x * lanes) {
+      float v[8];
+      up8(ld8(x.ptr + r * x.cs + x.coff + g * 8), v);
+      n += 1.f;
+      const float inv = 1.f / n;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[j] - mean[j];
+        mean[j] += d * inv;
+        m2[j] = fmaf(d, v[j] - mean[j], m2[j]);
+      }
+    }
+    float* rl = red + (size_t)lane * 2 * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { rl[g * 8 + j] = mean[j]; rl[C + g * 8 + j] = m2[j]; }
+    if (g == 0) red[(size_t)lanes * 2 * C + lane] = n;
+  }
+  __syncthreads();
+  const float* cnt = red + (size_t)lanes * 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float nA = 0.f, mA = 0.f, qA = 0.f;
+    for (int l = 0; l < lanes; ++l) chan_combine(nA, mA, qA, cnt[l], red[(size_t)l * 2 * C + c], red[(size_t)l * 2 * C + C + c]);
+    partial[(size_t)blockIdx.x * 2 * C + c] = mA;
+    partial[(size_t)blockIdx.x * 2 * C + C + c] = qA;
+    if (c == 0) counts[blockIdx.x] = nA;
+  }
+}
+// combine the block partials (8 slices in parallel, each in block order, then the slices in order) and finish the layer's
+// statistics: mean, biased variance, inverse std, running averages (bn_layer.cpp:107-157)
+__global__ void bn_welford_finish_kernel(const float* __restrict__ partial, const float* __restrict__ counts, int blocks, int C,
+                                         float* __restrict__ mean, float* __restrict__ inv_std, float* __restrict__ batch_var,
+                                         float* __restrict__ run_mean, float* __restrict__ run_var, float momentum, float eps) {
+  __shared__ float sn[8][32], sm[8][32], sq[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int sl = threadIdx.y;
+  float nA = 0.f, mA = 0.f, qA = 0.f;
+  if (c < C)
+    for (int b = sl; b < blocks; b += 8) chan_combine(nA, mA, qA, counts[b], partial[(size_t)b * 2 * C + c], partial[(size_t)b * 2 * C + C + c]);
+  sn[sl][threadIdx.x] = nA; sm[sl][threadIdx.x] = mA; sq[sl][threadIdx.x] = qA;
+  __syncthreads();
+  if (sl == 0 && c < C) {
+    float n = 0.f, m = 0.f, q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) chan_combine(n, m, q, sn[k][threadIdx.x], sm[k][threadIdx.x], sq[k][threadIdx.x]);
+    const float var = q / n;  // biased (bn_layer.cpp:141-151)
+    mean[c] = m;
+    batch_var[c] = var;
+    run_mean[c] = (1.f - momentum) * m + momentum * run_mean[c];
+    run_var[c] = (1.f - momentum) * var + momentum * run_var[c];
+    inv_std[c] = powf(var + eps, -0.5f);
+  }
 }
 
 __global__ void bn_finish_mean_kernel(const float* __restrict__ sum, float* __restrict__ mean, int C, double count) {
@@ -186,8 +259,8 @@ __global__ void bn_apply_cl_kernel(ClView x, ClView y, const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = g * 8 + j;
-      float o = (v[j] - mean[c]) * inv_std[c];  // x_norm first, as bn_layer.cpp:132-181 orders it
-      o = o * slope[c] + bias[c];
+      const float xn = (v[j] - mean[c]) * inv_std[c];  // x_norm first, as bn_layer.cpp:132-181 orders it
+      const float o = xn * slope[c] + bias[c];          // (the backward kernels recompute exactly this for the ReLU mask)
       v[j] = relu ? fmaxf(o, 0.f) : o;
     }
     *reinterpret_cast<uint4*>(y.ptr + r * y.cs + y.coff + g * 8) = pk8(v);
@@ -196,7 +269,8 @@ __global__ void bn_apply_cl_kernel(ClView x, ClView y, const float* __restrict__
 
 __global__ void bn_bwd_apply_cl_kernel(ClView x, ClView y, ClView dy, ClView dx, const float* __restrict__ mean,
                                        const float* __restrict__ inv_std, const float* __restrict__ slope,
-                                       const float* __restrict__ sums, float inv_count, int relu, int accumulate) {
+                                       const float* __restrict__ bias, const float* __restrict__ sums, float inv_count, int relu,
+                                       int accumulate) {
   const int G = x.C / 8, C = x.C;
   const long long total = x.outer * x.inner * G;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -205,18 +279,13 @@ __global__ void bn_bwd_apply_cl_kernel(ClView x, ClView y, ClView dy, ClView dx,
     float xv[8], gv[8], o[8];
     up8(ld8(x.ptr + r * x.cs + x.coff + g * 8), xv);
     up8(ld8(dy.ptr + r * dy.cs + dy.coff + g * 8), gv);
-    if (relu) {
-      float yv[8];
-      up8(ld8(y.ptr + r * y.cs + y.coff + g * 8), yv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
-    }
     if (accumulate) up8(ld8(dx.ptr + r * dx.cs + dx.coff + g * 8), o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = g * 8 + j;
       const float is = inv_std[c], sl = slope[c];
       const float xn = (xv[j] - mean[c]) * is;
+      if (relu && !(xn * sl + bias[c] > 0.f)) gv[j] = 0.f;   // same mask as the forward pass, recomputed from x
       const float d = (sl * gv[j] - sl * sums[c] * inv_count - xn * (sl * sums[C + c] * inv_count)) * is;
       o[j] = accumulate ? o[j] + d : d;
     }
@@ -383,6 +452,48 @@ __global__ void pool_max_bwd_mask_kernel(const PoolParams p, const unsigned char
       for (int j = 0; j < 8; ++j) acc[j] += old[j];
     }
     *reinterpret_cast<uint4*>(o) = pk8(acc);
+  }
+}
+
+// generic fp32 pooling backward on plain blobs (ECO-Full's segment consensus), gather form
+__global__ void pool_f32_bwd_kernel(const PoolF32Params p, const float* __restrict__ dy, float* __restrict__ dx, int accumulate) {
+  const long long total = (long long)p.NC * p.ID * p.IH * p.IW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    const int ix = (int)(r % p.IW); r /= p.IW;
+    const int iy = (int)(r % p.IH); r /= p.IH;
+    const int iz = (int)(r % p.ID);
+    const long long nc = r / p.ID;
+    const int oz_lo = max(0, (iz + p.pD - p.KD + p.sD) / p.sD), oz_hi = min(p.OD - 1, (iz + p.pD) / p.sD);
+    const int oy_lo = max(0, (iy + p.pH - p.KH + p.sH) / p.sH), oy_hi = min(p.OH - 1, (iy + p.pH) / p.sH);
+    const int ox_lo = max(0, (ix + p.pW - p.KW + p.sW) / p.sW), ox_hi = min(p.OW - 1, (ix + p.pW) / p.sW);
+    const float* px = p.x + nc * (long long)p.ID * p.IH * p.IW;
+    const float me = px[((long long)iz * p.IH + iy) * p.IW + ix];
+    float acc = 0.f;
+    for (int oz = oz_lo; oz <= oz_hi; ++oz)
+      for (int oy = oy_lo; oy <= oy_hi; ++oy)
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          int z0 = oz * p.sD - p.pD, y0 = oy * p.sH - p.pH, x0 = ox * p.sW - p.pW;
+          const float g = dy[(nc * p.OD + oz) * (long long)p.OH * p.OW + (long long)oy * p.OW + ox];
+          if (!p.is_max) {
+            const int z1 = min(z0 + p.KD, p.ID + p.pD), y1 = min(y0 + p.KH, p.IH + p.pH), x1 = min(x0 + p.KW, p.IW + p.pW);
+            acc += g / (float)((z1 - z0) * (y1 - y0) * (x1 - x0));
+            continue;
+          }
+          const int z1 = min(z0 + p.KD, p.ID), y1 = min(y0 + p.KH, p.IH), x1 = min(x0 + p.KW, p.IW);
+          z0 = max(z0, 0); y0 = max(y0, 0); x0 = max(x0, 0);
+          bool win = true;
+          for (int z = z0; z < z1 && win; ++z)
+            for (int yy = y0; yy < y1 && win; ++yy)
+              for (int xx = x0; xx < x1; ++xx) {
+                if (z == iz && yy == iy && xx == ix) continue;
+                const bool earlier = (z < iz) || (z == iz && (yy < iy || (yy == iy && xx < ix)));
+                const float o = px[((long long)z * p.IH + yy) * p.IW + xx];
+                if (earlier ? !(me > o) : !(me >= o)) { win = false; break; }
+              }
+          if (win) acc += g;
+        }
+    dx[t] = accumulate ? dx[t] + acc : acc;
   }
 }
 
@@ -639,14 +750,35 @@ __global__ void sgd_update_kernel(float* __restrict__ w, float* __restrict__ dif
 
 // ================================================================================================
 cudaError_t launch_colsum_cl(ClView x, float* out, float* scratch, cudaStream_t st) {
-  return launch_colreduce<0>(x, x, x, nullptr, nullptr, 0, out, scratch, st);
+  return launch_colreduce<0>(x, x, x, nullptr, nullptr, nullptr, nullptr, 0, out, scratch, st);
 }
 cudaError_t launch_colsqdev_cl(ClView x, const float* mean, float* out, float* scratch, cudaStream_t st) {
-  return launch_colreduce<1>(x, x, x, mean, nullptr, 0, out, scratch, st);
+  return launch_colreduce<1>(x, x, x, mean, nullptr, nullptr, nullptr, 0, out, scratch, st);
 }
-cudaError_t launch_bn_bwd_sums_cl(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, int relu, float* out,
-                                  float* scratch, cudaStream_t st) {
-  return launch_colreduce<2>(x, y, dy, mean, inv_std, relu, out, scratch, st);
+cudaError_t launch_bn_bwd_sums_cl(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, const float* slope,
+                                  const float* bias, int relu, float* out, float* scratch, cudaStream_t st) {
+  return launch_colreduce<2>(x, y, dy, mean, inv_std, slope, bias, relu, out, scratch, st);
+}
+cudaError_t launch_bn_stats_cl(ClView x, float* mean, float* inv_std, float* batch_var, float* run_mean, float* run_var,
+                               float momentum, float eps, float* scratch, cudaStream_t st) {
+  const long long rows = x.outer * x.inner;
+  if (rows == 0 || x.C == 0) return cudaSuccess;
+  if (x.C % 8 != 0 || x.C > kColReduceMaxC || !scratch) return cudaErrorInvalidValue;
+  const int G = x.C / 8;
+  int threads = 256;
+  while (threads < G) threads *= 2;
+  if (threads > 1024) return cudaErrorInvalidValue;
+  const int lanes = threads / G;
+  const size_t smem = ((size_t)lanes * 2 * x.C + lanes) * sizeof(float);
+  long long blocks = (rows + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
+  if (blocks > kColReduceMaxBlocks) blocks = kColReduceMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  float* counts = scratch + (size_t)kColReduceMaxBlocks * 2 * x.C;   // behind the largest partial table of this layer
+  if ((size_t)kColReduceMaxBlocks * 2 * x.C + kColReduceMaxBlocks > kColReduceScratchFloats) return cudaErrorInvalidValue;
+  bn_welford_cl_kernel<<<(unsigned)blocks, threads, smem, st>>>(x, scratch, counts);
+  bn_welford_finish_kernel<<<(x.C + 31) / 32, dim3(32, 8, 1), 0, st>>>(scratch, counts, (int)blocks, x.C, mean, inv_std, batch_var,
+                                                                       run_mean, run_var, momentum, eps);
+  return cudaGetLastError();
 }
 cudaError_t launch_bn_finish_mean(const float* sum, float* mean, int C, double count, cudaStream_t st) {
   bn_finish_mean_kernel<<<(C + 127) / 128, 128, 0, st>>>(sum, mean, C, count);
@@ -665,11 +797,11 @@ cudaError_t launch_bn_apply_cl(ClView x, ClView y, const float* mean, const floa
   return cudaGetLastError();
 }
 cudaError_t launch_bn_bwd_apply_cl(ClView x, ClView y, ClView dy, ClView dx, const float* mean, const float* inv_std,
-                                   const float* slope, const float* sums, double count, int relu, int accumulate,
+                                   const float* slope, const float* bias, const float* sums, double count, int relu, int accumulate,
                                    float* dslope, float* dbias, cudaStream_t st) {
   const long long n = x.outer * x.inner * (x.C / 8);
   if (n == 0) return cudaSuccess;
-  if (dx.ptr) bn_bwd_apply_cl_kernel<<<grid_for(n, 16), kT, 0, st>>>(x, y, dy, dx, mean, inv_std, slope, sums, (float)(1.0 / count), relu, accumulate);
+  if (dx.ptr) bn_bwd_apply_cl_kernel<<<grid_for(n, 16), kT, 0, st>>>(x, y, dy, dx, mean, inv_std, slope, bias, sums, (float)(1.0 / count), relu, accumulate);
   if (dslope || dbias) bn_param_grads_kernel<<<(x.C + 127) / 128, 128, 0, st>>>(sums, dslope, dbias, x.C);
   return cudaGetLastError();
 }
@@ -684,6 +816,12 @@ cudaError_t launch_pool_bwd_cl(const PoolParams& p, const __nv_bfloat16* dy, lon
     return cudaGetLastError();
   }
   pool_bwd_cl_kernel<<<grid_for(n, 32), kT, 0, st>>>(p, dy, dy_cs, dy_coff, dx, dx_cs, dx_coff, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_f32_bwd(const PoolF32Params& p, const float* dy, float* dx, int accumulate, cudaStream_t st) {
+  const long long n = (long long)p.NC * p.ID * p.IH * p.IW;
+  if (n == 0) return cudaSuccess;
+  pool_f32_bwd_kernel<<<grid_for(n, 16), kT, 0, st>>>(p, dy, dx, accumulate);
   return cudaGetLastError();
 }
 cudaError_t launch_global_avg_bwd_cl(const float* dy, ClView dx, int accumulate, cudaStream_t st) {

@@ -15,18 +15,22 @@ namespace eco {
 // Deterministic: per-block partials are written to `scratch` (kColReduceScratchFloats floats) and summed in block order.
 constexpr int kColReduceMaxBlocks = 296;   // 2 per SM
 constexpr int kColReduceMaxC = 2048;
-constexpr size_t kColReduceScratchFloats = (size_t)kColReduceMaxBlocks * kColReduceMaxC * 2;
+constexpr size_t kColReduceScratchFloats = (size_t)kColReduceMaxBlocks * kColReduceMaxC * 2 + kColReduceMaxBlocks;
 // out[0..C) += sum_rows x                                   (BN mean numerator, conv bias gradient)
 cudaError_t launch_colsum_cl(ClView x, float* out, float* scratch, cudaStream_t st);
 // out[0..C) += sum_rows (x - mean[c])^2                      (BN biased variance numerator, bn_layer.cpp:141-151)
 cudaError_t launch_colsqdev_cl(ClView x, const float* mean, float* out, float* scratch, cudaStream_t st);
-// BN backward sums (bn_layer.cpp:241-262): with g = dy * (y > 0 if relu) and xn = (x - mean) * inv_std
+// BN backward sums (bn_layer.cpp:241-262): with g = dy * (y > 0 if relu; the mask is recomputed from x, y is not read) and
+// xn = (x - mean) * inv_std
 //   out[0..C) += sum g ;  out[C..2C) += sum g * xn
-cudaError_t launch_bn_bwd_sums_cl(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, int relu,
-                                  float* out, float* scratch, cudaStream_t st);
+cudaError_t launch_bn_bwd_sums_cl(ClView x, ClView y, ClView dy, const float* mean, const float* inv_std, const float* slope,
+                                  const float* bias, int relu, float* out, float* scratch, cudaStream_t st);
 
 // BN TRAIN statistics (bn_layer.cpp:107-157): from sum / sqdev numerators to mean, biased variance, inverse std and the
 // running-average update  running = (1 - m) * batch + m * running
+// one-pass variant: Welford per thread + Chan's combination in a fixed order (deterministic), statistics finished in place
+cudaError_t launch_bn_stats_cl(ClView x, float* mean, float* inv_std, float* batch_var, float* run_mean, float* run_var,
+                               float momentum, float eps, float* scratch, cudaStream_t st);
 cudaError_t launch_bn_finish_mean(const float* sum, float* mean, int C, double count, cudaStream_t st);
 cudaError_t launch_bn_finish_var(const float* sqdev, const float* mean, float* inv_std, float* batch_var, float* run_mean,
                                  float* run_var, int C, double count, float momentum, float eps, cudaStream_t st);
@@ -36,7 +40,7 @@ cudaError_t launch_bn_apply_cl(ClView x, ClView y, const float* mean, const floa
 // dx (+)= inv_std * (slope * g - slope * S1 / n - xn * slope * S2 / n)      (bn_layer.cpp:264-334);
 // dslope += S2, dbias += S1 (the gradient arena accumulates like caffe's blobs)
 cudaError_t launch_bn_bwd_apply_cl(ClView x, ClView y, ClView dy, ClView dx, const float* mean, const float* inv_std,
-                                   const float* slope, const float* sums, double count, int relu, int accumulate,
+                                   const float* slope, const float* bias, const float* sums, double count, int relu, int accumulate,
                                    float* dslope, float* dbias, cudaStream_t st);
 
 // ---- pooling backward (pooling_layer.cpp:280-377), any 1..3-D window, channels-last bf16 ----
@@ -47,6 +51,8 @@ cudaError_t launch_bn_bwd_apply_cl(ClView x, ClView y, ClView dy, ClView dx, con
 cudaError_t launch_pool_bwd_cl(const PoolParams& p, const __nv_bfloat16* dy, long long dy_cs, int dy_coff,
                                __nv_bfloat16* dx, long long dx_cs, int dx_coff, int accumulate, unsigned char* mask,
                                cudaStream_t st);
+// generic fp32 pooling on plain blobs (segment consensus of ECO-Full), same rules
+cudaError_t launch_pool_f32_bwd(const PoolF32Params& p, const float* dy, float* dx, int accumulate, cudaStream_t st);
 // full-extent average pool: dx[o, i, c] (+)= dy[o, c] / inner
 cudaError_t launch_global_avg_bwd_cl(const float* dy, ClView dx, int accumulate, cudaStream_t st);
 

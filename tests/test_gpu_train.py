@@ -429,3 +429,15 @@ def test_backward_is_reproducible_run_to_run(gpu):
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), "blob gradients differ between identical passes"
     assert np.array_equal(a[5], b[5])
     assert rel_max(a[3], b[3]) <= 1e-5 and rel_max(a[4], b[4]) <= 1e-5
+
+
+def test_eco_full_train_n4(gpu):
+    """the two-stream ECO-Full train net (models_ECO_Full/kinetics/ECO_full.prototxt geometry) at N=4, two clips: 2-D stream
+    inception_3c..5b with stride-2 convolutions and MAX pools, segment-consensus pooling and Concat on plain blobs, two
+    Dropout layers -- every blob's data and gradient, every parameter gradient (teacher-forced)"""
+    segments, batch, classes = 4, 2, 30
+    txt = gen.eco_full_train(segments=segments, classes=classes, batch=batch, dropout2d=0.0)
+    x = refnet.eco_input(batch, segments).reshape(batch, 3 * segments, 224, 224)
+    lab = np.array([7, 21], np.float32).reshape(batch, 1, 1, 1)
+    run_train_net_against_oracle(txt, {"data": x, "label": lab}, 4321, "dropout", "global_pool_reshape",
+                                 skip_data=("global_pool", "global_pool_reshape", "reshape_data", "global_pool_gn02_reshape"))

@@ -68,6 +68,7 @@ def test_shapes_lite_n16():
 
 TRAIN_CASES = [
     ("models_ECO_Lite/kinetics/ECO_Lite.prototxt", lambda: gen.eco_lite_train(16, 400, "fc8", 17, 0.3)),
+    ("models_ECO_Full/kinetics/ECO_full.prototxt", lambda: gen.eco_full_train(16, 400, "fc8N", 8, 0.5, 0.5)),
 ]
 
 

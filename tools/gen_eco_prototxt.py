@@ -237,14 +237,8 @@ def eco_lite_train(segments=16, classes=400, fc_name="fc8", batch=17, dropout=0.
     return o.f.getvalue()
 
 
-def eco_full_deploy(segments=16, classes=400, fc_name="fc8N", batch=5, dropout3d=0.5, dropout2d=0.6,
-                    net_name="o3d"):
-    """ECO-Full deploy net (cf. models_ECO_Full/kinetics/deploy.prototxt): the Lite graph plus
-    the 2-D stream inception_3c..5b -> global_pool2D -> segment consensus, concatenated
-    with the 3-D feature before the classifier."""
-    o = _W()
-    _header(o, net_name, batch * segments)
-    b3 = _trunk_to_3c(o, "data")
+def _full_body(o, data_blob, segments, classes, fc_name, dropout3d, dropout2d):
+    b3 = _trunk_to_3c(o, data_blob)
     # inception_3c is split around the 3-D head exactly as in the reference file
     t = _cbr2d(o, "inception_3c", "3x3_reduce", b3, 128, 1)
     c3 = _cbr2d(o, "inception_3c", "3x3", t, 160, 3, 2, 1)
@@ -274,6 +268,47 @@ def eco_full_deploy(segments=16, classes=400, fc_name="fc8N", batch=5, dropout3d
     _tail3d(o, segments, dropout3d)
     _concat(o, "gn02_concat", ["pool_fusion_st2D", "global_pool_reshape"], top="global_pool_gn02_reshape", axis=1)
     _fc(o, fc_name, "global_pool_gn02_reshape", classes)
+
+
+def _train_header(o, net_name, batch, segments):
+    o.w('name: "%s"' % net_name)
+    o.w('input: "data"')
+    for d in (batch, 3 * segments, 224, 224):
+        o.w("input_dim: %d" % d)
+    o.w('input: "label"')
+    for d in (batch, 1, 1, 1):
+        o.w("input_dim: %d" % d)
+    o.w('layer { name: "reshape_data" type: "Reshape" bottom: "data" top: "reshape_data" '
+        'reshape_param { shape { dim: -1 dim: 3 dim: 224 dim: 224 } } }')
+
+
+def _loss_tail(o):
+    o.w('layer { name: "loss" type: "SoftmaxWithLoss" bottom: "fc8" bottom: "label" include { phase: TRAIN } top: "loss" }')
+    o.w('layer { name: "loss" type: "SoftmaxWithLoss" bottom: "fc8" bottom: "label" top: "loss" include { phase: TEST } }')
+    o.w('layer { name: "top1" type: "Accuracy" bottom: "fc8" bottom: "label" top: "top1" accuracy_param { top_k: 1 } '
+        'include { phase: TEST } }')
+    o.w('layer { name: "top5" type: "Accuracy" bottom: "fc8" bottom: "label" top: "top5" accuracy_param { top_k: 5 } '
+        'include { phase: TEST } }')
+
+
+def eco_full_deploy(segments=16, classes=400, fc_name="fc8N", batch=5, dropout3d=0.5, dropout2d=0.6,
+                    net_name="o3d"):
+    """ECO-Full deploy net (cf. models_ECO_Full/kinetics/deploy.prototxt): the Lite graph plus
+    the 2-D stream inception_3c..5b -> global_pool2D -> segment consensus, concatenated
+    with the 3-D feature before the classifier."""
+    o = _W()
+    _header(o, net_name, batch * segments)
+    _full_body(o, "data", segments, classes, fc_name, dropout3d, dropout2d)
+    return o.f.getvalue()
+
+
+def eco_full_train(segments=16, classes=400, fc_name="fc8N", batch=8, dropout3d=0.5, dropout2d=0.6, net_name="o3d"):
+    """ECO-Full train/test net (cf. models_ECO_Full/kinetics/ECO_full.prototxt) with the VideoData layers replaced by the two
+    net inputs they produce (see eco_lite_train)."""
+    o = _W()
+    _train_header(o, net_name, batch, segments)
+    _full_body(o, "reshape_data", segments, classes, fc_name, dropout3d, dropout2d)
+    _loss_tail(o)
     return o.f.getvalue()
 
 
