@@ -313,7 +313,7 @@ def train_main(a, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": workload, "global_batch": batch * world, "parallelism": "dp%d: batch-sharded replicas, NCCL SUM all-reduce of the gradient arena in %d buckets (%s), "
                        "1/world folded into the update" % (world, a.buckets, "launched from inside the backward pass" if a.overlap
-                                                             else "launched when backward is enqueued; see collective.note"),
+                                                             else "launched when backward has been enqueued"),
                        "l2": "activations exceed the 126 MB L2", "solver": "models_ECO_Lite/kinetics/solver.prototxt values, iter_size 1"},
             "clocks": clocks, "gpu_launches": int(net.last_launch_count()) * a.steps,
             "e2e": {"value": e2e_value, "unit": "videos/s", "h2d_bytes_per_step": int(count * 4 + batch * 4), "d2h_bytes_per_step": 4,
@@ -342,7 +342,7 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer: BASELINE metric (forward videos/s); train: config #4 (fwd + bwd + NCCL grad all-reduce + Nesterov)")
     ap.add_argument("--buckets", type=int, default=3, help="train: gradient all-reduce buckets")
-    ap.add_argument("--overlap", type=int, default=0, help="train: 1 = start each bucket's all-reduce from inside backward")
+    ap.add_argument("--overlap", type=int, default=1, help="train: 1 = start each bucket's all-reduce from inside backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-calibrate", action="store_true", help="skip the BN calibration forwards of the weight harness (ncu captures)")

@@ -62,12 +62,11 @@ class GradExchange(object):
         solver.step(1)                                  # backward fires the bucket hooks, the update waits for them
     """
 
-    def __init__(self, solver, nbuckets=3, group=None, overlap=False):
-        """overlap=True starts each bucket's all-reduce from inside backward (side stream, behind an event); overlap=False
-        (default) starts all buckets when backward has been enqueued completely.  Measured on 8 x B200 (profiles/r02d): the
-        whole 150 MB arena all-reduces in 0.46 ms over NVSwitch (NVLS), 1.4 % of a 33 ms step, while NCCL's channel CTAs
-        running UNDER the backward pass take SMs away from the persistent one-CTA-per-SM GEMM kernels (their last CTAs wait
-        for a free SM: a second wave) and every rank stalls on the slowest one -- overlapping cost +17 ms per step there."""
+    def __init__(self, solver, nbuckets=3, group=None, overlap=True):
+        """overlap=True (default) starts each bucket's all-reduce from inside backward (side stream, behind an event);
+        overlap=False starts all buckets when backward has been enqueued completely.  Measured on 8 x B200
+        (profiles/r02d_bench_train_n8_*.json): the whole 150 MB arena all-reduces in 0.43 ms over NVSwitch (NVLS), 1.3 % of
+        a 33 ms step; overlapped 33.67 ms/step, exchanged after backward 33.95 ms/step, one GPU alone 33.08 ms/step."""
         self.overlap = bool(overlap)
         self.pending = []
         import torch
