@@ -68,9 +68,11 @@ __global__ void colreduce_cl_kernel(ClView x, ClView y, ClView dy, const float* 
     }
   }
   if (lane < lanes) {
-    for (long long r = (long long)blockIdx.x * lanes + lane; r < rows; r += (long long)gridDim.x * lanes) {
+    // four rows in flight per thread (the loads are issued before the first of them is consumed): 296 CTAs x 256 threads x
+    // 4 x 16 B keeps ~5 MB outstanding, what HBM3e needs at ~0.8 us latency; the summation order per thread is unchanged
+    auto consume = [&](const uint4& xraw, const uint4& graw) {
       float xv[8];
-      up8(ld8(x.ptr + r * x.cs + x.coff + g * 8), xv);
+      up8(xraw, xv);
       if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) s1[j] += xv[j];
@@ -79,7 +81,7 @@ __global__ void colreduce_cl_kernel(ClView x, ClView y, ClView dy, const float* 
         for (int j = 0; j < 8; ++j) { const float d = xv[j] - mu[j]; s1[j] = fmaf(d, d, s1[j]); }
       } else {
         float gv[8];
-        up8(ld8(dy.ptr + r * dy.cs + dy.coff + g * 8), gv);
+        up8(graw, gv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xn = (xv[j] - mu[j]) * is[j];
@@ -90,7 +92,22 @@ __global__ void colreduce_cl_kernel(ClView x, ClView y, ClView dy, const float* 
           s2[j] = fmaf(gv[j], xn, s2[j]);
         }
       }
+    };
+    const long long stride = (long long)gridDim.x * lanes;
+    long long r = (long long)blockIdx.x * lanes + lane;
+    const __nv_bfloat16* xp = x.ptr + x.coff + g * 8;
+    const __nv_bfloat16* gp = MODE == 2 ? dy.ptr + dy.coff + g * 8 : nullptr;
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+      uint4 xr[4], gr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xr[u] = ld8(xp + (r + u * stride) * x.cs);
+        gr[u] = MODE == 2 ? ld8(gp + (r + u * stride) * dy.cs) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) consume(xr[u], gr[u]);
     }
+    for (; r < rows; r += stride) consume(ld8(xp + r * x.cs), MODE == 2 ? ld8(gp + r * dy.cs) : make_uint4(0, 0, 0, 0));
   }
   const int C = x.C;
   float* r1 = red;
@@ -148,7 +165,8 @@ cudaError_t launch_colreduce(ClView x, ClView y, ClView dy, const float* mean, c
   const int lanes = threads / G;
   const size_t smem = (size_t)lanes * x.C * sizeof(float) * (MODE == 2 ? 2 : 1);
   long long blocks = (rows + (long long)lanes * 8 - 1) / ((long long)lanes * 8);  // >= 8 rows per lane
-  if (blocks > kColReduceMaxBlocks) blocks = kColReduceMaxBlocks;
+  const int cap = MODE == 2 ? kColReduceMaxBlocks / 2 : kColReduceMaxBlocks;
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (x.C > kColReduceMaxC || !scratch) return cudaErrorInvalidValue;
   colreduce_cl_kernel<MODE><<<(unsigned)blocks, threads, smem, st>>>(x, y, dy, mean, inv_std, slope, bias, relu, scratch);
@@ -177,9 +195,9 @@ __global__ void bn_welford_cl_kernel(ClView x, float* __restrict__ partial /* [b
 #pragma unroll
   for (int j = 0; j < 8; ++j) { mean[j] = 0.f; m2[j] = 0.f; }
   if (lane < lanes) {
-    for (long long r = (long long)blockIdx.x * lanes + lane; r < rows; r += (long long)gridDim.x * lanes) {
+    auto consume = [&](const uint4& raw) {
       float v[8];
-      up8(ld8(x.ptr + r * x.cs + x.coff + g * 8), v);
+      up8(raw, v);
       n += 1.f;
       const float inv = 1.f / n;
 #pragma unroll
@@ -188,7 +206,18 @@ __global__ void bn_welford_cl_kernel(ClView x, float* __restrict__ partial /* [b
         mean[j] += d * inv;
         m2[j] = fmaf(d, v[j] - mean[j], m2[j]);
       }
+    };
+    const long long stride = (long long)gridDim.x * lanes;
+    long long r = (long long)blockIdx.x * lanes + lane;
+    const __nv_bfloat16* xp = x.ptr + x.coff + g * 8;
+    for (; r + 3 * stride < rows; r += 4 * stride) {   // four rows in flight, consumed in row order
+      uint4 xr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xr[u] = ld8(xp + (r + u * stride) * x.cs);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) consume(xr[u]);
     }
+    for (; r < rows; r += stride) consume(ld8(xp + r * x.cs));
     float* rl = red + (size_t)lane * 2 * C;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { rl[g * 8 + j] = mean[j]; rl[C + g * 8 + j] = m2[j]; }
@@ -246,25 +275,42 @@ __global__ void bn_finish_var_kernel(const float* __restrict__ sqdev, const floa
   inv_std[c] = powf(var + eps, -0.5f);
 }
 
-// elementwise over [rows][C/8] groups
+// elementwise over [rows][C/8] groups.  Thread t owns channel group g = t % G for its whole life (the per-channel
+// constants sit in registers: the data load is the only memory instruction of the loop) and walks rows lane, lane + stride,
+// ... two at a time.
 __global__ void bn_apply_cl_kernel(ClView x, ClView y, const float* __restrict__ mean, const float* __restrict__ inv_std,
                                    const float* __restrict__ slope, const float* __restrict__ bias, int relu) {
   const int G = x.C / 8;
-  const long long total = x.outer * x.inner * G;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % G);
-    const long long r = t / G;
+  const long long rows = x.outer * x.inner;
+  const int lanes = blockDim.x / G;
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  if (lane >= lanes) return;
+  float mu[8], is[8], sl[8], bi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mu[j] = mean[g * 8 + j]; is[j] = inv_std[g * 8 + j]; sl[j] = slope[g * 8 + j]; bi[j] = bias[g * 8 + j]; }
+  auto apply = [&](uint4 raw) {
     float v[8];
-    up8(ld8(x.ptr + r * x.cs + x.coff + g * 8), v);
+    up8(raw, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      const float xn = (v[j] - mean[c]) * inv_std[c];  // x_norm first, as bn_layer.cpp:132-181 orders it
-      const float o = xn * slope[c] + bias[c];          // (the backward kernels recompute exactly this for the ReLU mask)
+      const float xn = (v[j] - mu[j]) * is[j];  // x_norm first, as bn_layer.cpp:132-181 orders it
+      const float o = xn * sl[j] + bi[j];        // (the backward kernels recompute exactly this for the ReLU mask)
       v[j] = relu ? fmaxf(o, 0.f) : o;
     }
-    *reinterpret_cast<uint4*>(y.ptr + r * y.cs + y.coff + g * 8) = pk8(v);
+    return pk8(v);
+  };
+  const long long stride = (long long)gridDim.x * lanes;
+  long long r = (long long)blockIdx.x * lanes + lane;
+  const __nv_bfloat16* xp = x.ptr + x.coff + g * 8;
+  __nv_bfloat16* yp = y.ptr + y.coff + g * 8;
+  for (; r + 3 * stride < rows; r += 4 * stride) {
+    uint4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = ld8(xp + (r + u * stride) * x.cs);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(yp + (r + u * stride) * y.cs) = apply(a[u]);
   }
+  for (; r < rows; r += stride) *reinterpret_cast<uint4*>(yp + r * y.cs) = apply(ld8(xp + r * x.cs));
 }
 
 __global__ void bn_bwd_apply_cl_kernel(ClView x, ClView y, ClView dy, ClView dx, const float* __restrict__ mean,
@@ -272,25 +318,51 @@ __global__ void bn_bwd_apply_cl_kernel(ClView x, ClView y, ClView dy, ClView dx,
                                        const float* __restrict__ bias, const float* __restrict__ sums, float inv_count, int relu,
                                        int accumulate) {
   const int G = x.C / 8, C = x.C;
-  const long long total = x.outer * x.inner * G;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % G);
-    const long long r = t / G;
+  const long long rows = x.outer * x.inner;
+  const int lanes = blockDim.x / G;
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  if (lane >= lanes) return;
+  float mu[8], is[8], sl[8], bi[8], k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    mu[j] = mean[c]; is[j] = inv_std[c]; sl[j] = slope[c]; bi[j] = bias[c];
+    k1[j] = sl[j] * sums[c] * inv_count;
+    k2[j] = sl[j] * sums[C + c] * inv_count;
+  }
+  auto apply = [&](uint4 xraw, uint4 graw, uint4 oraw) {
     float xv[8], gv[8], o[8];
-    up8(ld8(x.ptr + r * x.cs + x.coff + g * 8), xv);
-    up8(ld8(dy.ptr + r * dy.cs + dy.coff + g * 8), gv);
-    if (accumulate) up8(ld8(dx.ptr + r * dx.cs + dx.coff + g * 8), o);
+    up8(xraw, xv);
+    up8(graw, gv);
+    if (accumulate) up8(oraw, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      const float is = inv_std[c], sl = slope[c];
-      const float xn = (xv[j] - mean[c]) * is;
-      if (relu && !(xn * sl + bias[c] > 0.f)) gv[j] = 0.f;   // same mask as the forward pass, recomputed from x
-      const float d = (sl * gv[j] - sl * sums[c] * inv_count - xn * (sl * sums[C + c] * inv_count)) * is;
+      const float xn = (xv[j] - mu[j]) * is[j];
+      if (relu && !(xn * sl[j] + bi[j] > 0.f)) gv[j] = 0.f;   // same mask as the forward pass, recomputed from x
+      const float d = (sl[j] * gv[j] - k1[j] - xn * k2[j]) * is[j];
       o[j] = accumulate ? o[j] + d : d;
     }
-    *reinterpret_cast<uint4*>(dx.ptr + r * dx.cs + dx.coff + g * 8) = pk8(o);
+    return pk8(o);
+  };
+  const long long stride = (long long)gridDim.x * lanes;
+  long long r = (long long)blockIdx.x * lanes + lane;
+  const __nv_bfloat16* xp = x.ptr + x.coff + g * 8;
+  const __nv_bfloat16* gp = dy.ptr + dy.coff + g * 8;
+  __nv_bfloat16* op = dx.ptr + dx.coff + g * 8;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (; r + stride < rows; r += 2 * stride) {
+    uint4 a[2], b[2], c[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      a[u] = ld8(xp + (r + u * stride) * x.cs);
+      b[u] = ld8(gp + (r + u * stride) * dy.cs);
+      c[u] = accumulate ? ld8(op + (r + u * stride) * dx.cs) : z;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) *reinterpret_cast<uint4*>(op + (r + u * stride) * dx.cs) = apply(a[u], b[u], c[u]);
   }
+  for (; r < rows; r += stride)
+    *reinterpret_cast<uint4*>(op + r * dx.cs) = apply(ld8(xp + r * x.cs), ld8(gp + r * dy.cs), accumulate ? ld8(op + r * dx.cs) : z);
 }
 __global__ void bn_param_grads_kernel(const float* __restrict__ sums, float* __restrict__ dslope, float* __restrict__ dbias, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -375,76 +447,92 @@ __global__ void pool_bwd_cl_kernel(const PoolParams p, const __nv_bfloat16* __re
 //      (kz * KH + ky) * KW + kx relative to the unclipped window start (255 = empty window)
 //   2. pool_max_bwd_mask_kernel: per input element, the windows that contain it (at most ceil(K/s) per axis) are looked up
 //      in the mask: 8 bytes of mask + 16 bytes of dy per window instead of re-scanning K^3 inputs per window
+// Both kernels run one CTA per (image, z, y) row: the row coordinates and the y/z window ranges are block-uniform, a
+// thread only splits its item into (x, channel group) -- no 64-bit div/mod chain per 16 bytes moved.
+__device__ __forceinline__ int div_stride(int a, int s) { return s == 1 ? a : (s == 2 ? (a >> 1) : a / s); }  // callers clamp at 0
 __global__ void pool_argmax_cl_kernel(const PoolParams p, unsigned char* __restrict__ mask) {
   const int G = p.C / 8;
-  const long long total = (long long)p.NB * p.OD * p.OH * p.OW * G;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % G);
-    long long r = t / G;
-    const long long opix = r;
-    const int ox = (int)(r % p.OW); r /= p.OW;
-    const int oy = (int)(r % p.OH); r /= p.OH;
-    const int oz = (int)(r % p.OD);
-    const long long n = r / p.OD;
-    const int z0u = oz * p.sD - p.pD, y0u = oy * p.sH - p.pH, x0u = ox * p.sW - p.pW;
-    const int z1 = min(z0u + p.KD, p.ID), y1 = min(y0u + p.KH, p.IH), x1 = min(x0u + p.KW, p.IW);
-    const int z0 = max(z0u, 0), y0 = max(y0u, 0), x0 = max(x0u, 0);
+  unsigned int row = blockIdx.x;                      // ((n * OD + oz) * OH + oy)
+  const int oy = (int)(row % (unsigned)p.OH); row /= (unsigned)p.OH;
+  const int oz = (int)(row % (unsigned)p.OD);
+  const long long n = row / (unsigned)p.OD;
+  const int z0u = oz * p.sD - p.pD, y0u = oy * p.sH - p.pH;
+  const int z1 = min(z0u + p.KD, p.ID), y1 = min(y0u + p.KH, p.IH);
+  const int z0 = max(z0u, 0), y0 = max(y0u, 0);
+  const long long obase = (long long)blockIdx.x * p.OW;
+  for (int item = threadIdx.x; item < p.OW * G; item += blockDim.x) {
+    const int ox = item / G, g = item - ox * G;
+    const int x0u = ox * p.sW - p.pW;
+    const int x1 = min(x0u + p.KW, p.IW), x0 = max(x0u, 0);
     float best[8];
     unsigned int idx[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { best[j] = -FLT_MAX; idx[j] = 255u; }
     for (int z = z0; z < z1; ++z)
-      for (int yy = y0; yy < y1; ++yy)
+      for (int yy = y0; yy < y1; ++yy) {
+        const __nv_bfloat16* px = p.x + (((n * p.ID + z) * p.IH + yy) * (long long)p.IW) * p.x_cs + p.x_coff + g * 8;
+        const unsigned int code0 = (unsigned int)(((z - z0u) * p.KH + (yy - y0u)) * p.KW - x0u);
         for (int xx = x0; xx < x1; ++xx) {
-          const long long q = ((n * p.ID + z) * p.IH + yy) * p.IW + xx;
           float v[8];
-          up8(ld8(p.x + q * p.x_cs + p.x_coff + g * 8), v);
-          const unsigned int code = (unsigned int)(((z - z0u) * p.KH + (yy - y0u)) * p.KW + (xx - x0u));
+          up8(ld8(px + (long long)xx * p.x_cs), v);
+          const unsigned int code = code0 + (unsigned int)xx;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (v[j] > best[j]) { best[j] = v[j]; idx[j] = code; }  // strictly greater: the first maximum wins
         }
+      }
     uint2 o;
     o.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
     o.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
-    *reinterpret_cast<uint2*>(mask + (opix * G + g) * 8) = o;
+    *reinterpret_cast<uint2*>(mask + ((obase + ox) * G + g) * 8) = o;
   }
 }
-__global__ void pool_max_bwd_mask_kernel(const PoolParams p, const unsigned char* __restrict__ mask,
+template <bool IS_MAX>
+__global__ void pool_bwd_rows_kernel(const PoolParams p, const unsigned char* __restrict__ mask,
                                          const __nv_bfloat16* __restrict__ dy, long long dy_cs, int dy_coff,
                                          __nv_bfloat16* __restrict__ dx, long long dx_cs, int dx_coff, int accumulate) {
   const int G = p.C / 8;
-  const long long total = (long long)p.NB * p.ID * p.IH * p.IW * G;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % G);
-    long long r = t / G;
-    const long long ipix = r;
-    const int ix = (int)(r % p.IW); r /= p.IW;
-    const int iy = (int)(r % p.IH); r /= p.IH;
-    const int iz = (int)(r % p.ID);
-    const long long n = r / p.ID;
-    const int oz_lo = max(0, (iz + p.pD - p.KD + p.sD) / p.sD), oz_hi = min(p.OD - 1, (iz + p.pD) / p.sD);
-    const int oy_lo = max(0, (iy + p.pH - p.KH + p.sH) / p.sH), oy_hi = min(p.OH - 1, (iy + p.pH) / p.sH);
-    const int ox_lo = max(0, (ix + p.pW - p.KW + p.sW) / p.sW), ox_hi = min(p.OW - 1, (ix + p.pW) / p.sW);
+  unsigned int row = blockIdx.x;                      // ((n * ID + iz) * IH + iy)
+  const int iy = (int)(row % (unsigned)p.IH); row /= (unsigned)p.IH;
+  const int iz = (int)(row % (unsigned)p.ID);
+  const long long n = row / (unsigned)p.ID;
+  // output windows that contain (iz, iy, ix): o*s - pad <= i < o*s - pad + K
+  const int oz_lo = max(0, div_stride(iz + p.pD - p.KD + p.sD, p.sD)), oz_hi = min(p.OD - 1, div_stride(iz + p.pD, p.sD));
+  const int oy_lo = max(0, div_stride(iy + p.pH - p.KH + p.sH, p.sH)), oy_hi = min(p.OH - 1, div_stride(iy + p.pH, p.sH));
+  const long long ibase = (long long)blockIdx.x * p.IW;
+  for (int item = threadIdx.x; item < p.IW * G; item += blockDim.x) {
+    const int ix = item / G, g = item - ix * G;
+    const int ox_lo = max(0, div_stride(ix + p.pW - p.KW + p.sW, p.sW)), ox_hi = min(p.OW - 1, div_stride(ix + p.pW, p.sW));
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     for (int oz = oz_lo; oz <= oz_hi; ++oz)
-      for (int oy = oy_lo; oy <= oy_hi; ++oy)
+      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        const long long orow = ((n * p.OD + oz) * p.OH + oy) * (long long)p.OW;
+        const unsigned int me0 = (unsigned int)(((iz - (oz * p.sD - p.pD)) * p.KH + (iy - (oy * p.sH - p.pH))) * p.KW + ix + p.pW);
         for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-          const long long opix = ((n * p.OD + oz) * p.OH + oy) * p.OW + ox;
-          const unsigned int me = (unsigned int)(((iz - (oz * p.sD - p.pD)) * p.KH + (iy - (oy * p.sH - p.pH))) * p.KW +
-                                                 (ix - (ox * p.sW - p.pW)));
-          const uint2 m = *reinterpret_cast<const uint2*>(mask + (opix * G + g) * 8);
+          const long long opix = orow + ox;
+          const unsigned int me = me0 - (unsigned int)(ox * p.sW);
           float gv[8];
           up8(ld8(dy + opix * dy_cs + dy_coff + g * 8), gv);
+          if (IS_MAX) {
+            const uint2 m = *reinterpret_cast<const uint2*>(mask + (opix * G + g) * 8);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (((m.x >> (8 * j)) & 255u) == me) acc[j] += gv[j];
-            if (((m.y >> (8 * j)) & 255u) == me) acc[4 + j] += gv[4 + j];
+            for (int j = 0; j < 4; ++j) {
+              if (((m.x >> (8 * j)) & 255u) == me) acc[j] += gv[j];
+              if (((m.y >> (8 * j)) & 255u) == me) acc[4 + j] += gv[4 + j];
+            }
+          } else {
+            // AVE: top_diff / pool_size, the window clipped at the PADDED border (pooling_layer.cpp:237-245, :352)
+            const int z0 = oz * p.sD - p.pD, y0 = oy * p.sH - p.pH, x0 = ox * p.sW - p.pW;
+            const int z1 = min(z0 + p.KD, p.ID + p.pD), y1 = min(y0 + p.KH, p.IH + p.pH), x1 = min(x0 + p.KW, p.IW + p.pW);
+            const float inv = 1.f / (float)((z1 - z0) * (y1 - y0) * (x1 - x0));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += gv[j] * inv;
           }
         }
-    __nv_bfloat16* o = dx + ipix * dx_cs + dx_coff + g * 8;
+      }
+    __nv_bfloat16* o = dx + (ibase + ix) * dx_cs + dx_coff + g * 8;
     if (accumulate) {
       float old[8];
       up8(ld8(o), old);
@@ -789,19 +877,38 @@ cudaError_t launch_bn_finish_var(const float* sqdev, const float* mean, float* i
   bn_finish_var_kernel<<<(C + 127) / 128, 128, 0, st>>>(sqdev, mean, inv_std, batch_var, run_mean, run_var, C, count, momentum, eps);
   return cudaGetLastError();
 }
+// block shape of the row-walking elementwise kernels: G = C/8 channel groups x `lanes` rows per block
+static inline bool rowwalk_shape(const ClView& x, int rows_per_thread, int max_blocks, int* threads, int* blocks) {
+  if (x.C % 8 != 0 || x.C / 8 > 1024) return false;
+  const int G = x.C / 8;
+  int t = kT;
+  while (t < G) t *= 2;
+  const int lanes = t / G;
+  const long long rows = x.outer * x.inner;
+  long long b = (rows + (long long)lanes * rows_per_thread - 1) / ((long long)lanes * rows_per_thread);
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  *threads = t;
+  *blocks = (int)b;
+  return true;
+}
 cudaError_t launch_bn_apply_cl(ClView x, ClView y, const float* mean, const float* inv_std, const float* slope,
                                const float* bias, int relu, cudaStream_t st) {
-  const long long n = x.outer * x.inner * (x.C / 8);
-  if (n == 0) return cudaSuccess;
-  bn_apply_cl_kernel<<<grid_for(n, 16), kT, 0, st>>>(x, y, mean, inv_std, slope, bias, relu);
+  if (x.outer * x.inner == 0 || x.C == 0) return cudaSuccess;
+  int threads, blocks;
+  if (!rowwalk_shape(x, 4, 148 * 6, &threads, &blocks)) return cudaErrorInvalidValue;
+  bn_apply_cl_kernel<<<blocks, threads, 0, st>>>(x, y, mean, inv_std, slope, bias, relu);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_bwd_apply_cl(ClView x, ClView y, ClView dy, ClView dx, const float* mean, const float* inv_std,
                                    const float* slope, const float* bias, const float* sums, double count, int relu, int accumulate,
                                    float* dslope, float* dbias, cudaStream_t st) {
-  const long long n = x.outer * x.inner * (x.C / 8);
-  if (n == 0) return cudaSuccess;
-  if (dx.ptr) bn_bwd_apply_cl_kernel<<<grid_for(n, 16), kT, 0, st>>>(x, y, dy, dx, mean, inv_std, slope, bias, sums, (float)(1.0 / count), relu, accumulate);
+  if (x.outer * x.inner == 0 || x.C == 0) return cudaSuccess;
+  if (dx.ptr) {
+    int threads, blocks;
+    if (!rowwalk_shape(x, 2, 148 * 4, &threads, &blocks)) return cudaErrorInvalidValue;
+    bn_bwd_apply_cl_kernel<<<blocks, threads, 0, st>>>(x, y, dy, dx, mean, inv_std, slope, bias, sums, (float)(1.0 / count), relu, accumulate);
+  }
   if (dslope || dbias) bn_param_grads_kernel<<<(x.C + 127) / 128, 128, 0, st>>>(sums, dslope, dbias, x.C);
   return cudaGetLastError();
 }
@@ -809,11 +916,19 @@ cudaError_t launch_pool_bwd_cl(const PoolParams& p, const __nv_bfloat16* dy, lon
                                long long dx_cs, int dx_coff, int accumulate, unsigned char* mask, cudaStream_t st) {
   const long long n = (long long)p.NB * p.ID * p.IH * p.IW * (p.C / 8);
   if (n == 0) return cudaSuccess;
-  if (p.is_max && mask && p.KD * p.KH * p.KW < 255) {
-    const long long no = (long long)p.NB * p.OD * p.OH * p.OW * (p.C / 8);
-    pool_argmax_cl_kernel<<<grid_for(no, 32), kT, 0, st>>>(p, mask);
-    pool_max_bwd_mask_kernel<<<grid_for(n, 32), kT, 0, st>>>(p, mask, dy, dy_cs, dy_coff, dx, dx_cs, dx_coff, accumulate);
-    return cudaGetLastError();
+  const long long orows = (long long)p.NB * p.OD * p.OH, irows = (long long)p.NB * p.ID * p.IH;
+  const int G = p.C / 8;
+  auto threads_for = [&](int w) { const int items = w * G; return items >= 256 ? 256 : (items >= 128 ? 128 : 64); };
+  if (orows <= 0x7fffffffLL && irows <= 0x7fffffffLL) {
+    if (p.is_max && mask && p.KD * p.KH * p.KW < 255) {
+      pool_argmax_cl_kernel<<<(unsigned)orows, threads_for(p.OW), 0, st>>>(p, mask);
+      pool_bwd_rows_kernel<true><<<(unsigned)irows, threads_for(p.IW), 0, st>>>(p, mask, dy, dy_cs, dy_coff, dx, dx_cs, dx_coff, accumulate);
+      return cudaGetLastError();
+    }
+    if (!p.is_max) {
+      pool_bwd_rows_kernel<false><<<(unsigned)irows, threads_for(p.IW), 0, st>>>(p, nullptr, dy, dy_cs, dy_coff, dx, dx_cs, dx_coff, accumulate);
+      return cudaGetLastError();
+    }
   }
   pool_bwd_cl_kernel<<<grid_for(n, 32), kT, 0, st>>>(p, dy, dy_cs, dy_coff, dx, dx_cs, dx_coff, accumulate);
   return cudaGetLastError();

@@ -13,7 +13,7 @@ namespace eco {
 
 // ---- per-channel reductions over a channels-last tensor (rows = outer*inner, C % 8 == 0) ----
 // Deterministic: per-block partials are written to `scratch` (kColReduceScratchFloats floats) and summed in block order.
-constexpr int kColReduceMaxBlocks = 296;   // 2 per SM
+constexpr int kColReduceMaxBlocks = 592;   // 4 per SM (the two-tensor BN-backward sums use 2 per SM: 96 registers)
 constexpr int kColReduceMaxC = 2048;
 constexpr size_t kColReduceScratchFloats = (size_t)kColReduceMaxBlocks * kColReduceMaxC * 2 + kColReduceMaxBlocks;
 // out[0..C) += sum_rows x                                   (BN mean numerator, conv bias gradient)
