@@ -528,8 +528,12 @@ def main():
     net.set_input_device("data", frames.data_ptr(), count)
     conv_ms, conv_flops, conv_n, other_ms = 0.0, 0.0, 0, 0.0
     prof_iters = 3
+    per_op = {}
     for _ in range(prof_iters):
         for op in net.profile_forward():
+            t = per_op.setdefault(op["name"], [0.0, 0.0])
+            t[0] += op["ms"] / prof_iters
+            t[1] = op["flops"]
             if op["kind"] == 0:
                 conv_ms += op["ms"]
                 conv_flops += op["flops"]
@@ -570,6 +574,8 @@ def main():
                 "traffic_source": traffic_src,
                 "conv_ms_per_step": conv_ms_step, "other_ms_per_step": ms_step - conv_ms_step,
                 "share_of_step": share,
+                "top_ops_eager": [{"op": k, "ms": round(v[0], 4), "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[0] > 0 and v[1] else None}
+                                  for k, v in sorted(per_op.items(), key=lambda kv: -kv[1][0])[:8]],
                 "method": "share of the conv launches in a per-launch CUDA-event profile (eager: %.3f + %.3f ms) applied to the "
                           "graph-timed ms_per_step" % (eager_conv_ms, eager_other_ms)}
 

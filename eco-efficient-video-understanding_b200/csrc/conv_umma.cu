@@ -1866,11 +1866,48 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
     uint32_t cm[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) cm[j] = 0u;
+    bool pend = false;
+    uint32_t pend_buf = 0;
+    long long pend_row = 0;
+    auto emit_flush_fn = [&]() {
+      if (!pend) return;
+      pend = false;
+      const long long tb = clock64();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      w_bar += clock64() - tb;
+      if (p.debug_flags & 1) return;
+      const uint32_t rowbuf = pend_buf;
+      __nv_bfloat16* orow = p.out + pend_row * p.PW * p.out_cs + p.out_coff;
+      for (int item = te; item < p.PW * 8; item += 256) {
+        const int q = item >> 3, g = item & 7;
+        const int x0 = 2 * q;
+        uint4 m;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w)
+                     : "r"(rowbuf + (uint32_t)x0 * 128u + ((uint32_t)(g ^ (x0 & 7)) << 4)));
+#pragma unroll
+        for (int d = 1; d < 3; ++d) {
+          const int xd = x0 + d;
+          if (xd < p.OW) {
+            uint4 t;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+                         : "r"(rowbuf + (uint32_t)xd * 128u + ((uint32_t)(g ^ (xd & 7)) << 4)));
+            m.x = hmax2_u32(m.x, t.x); m.y = hmax2_u32(m.y, t.y); m.z = hmax2_u32(m.z, t.z); m.w = hmax2_u32(m.w, t.w);
+          }
+        }
+        if (p.relu) { m.x = hmax2_u32(m.x, 0u); m.y = hmax2_u32(m.y, 0u); m.z = hmax2_u32(m.z, 0u); m.w = hmax2_u32(m.w, 0u); }
+        *reinterpret_cast<uint4*>(orow + (long long)q * p.out_cs + g * 8) = m;
+      }
+    };
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       int f, r0, r1, p0;
       unit_rows(u, f, r0, r1, p0);
-      // pooled row `pr` of this frame from the per-thread column maxima `w` (POOL only)
-      auto emit = [&](int pr, const uint32_t (&w)[16]) {
+      // pooled row `pr` of this frame from the per-thread column maxima `w` (POOL only), in two halves: emit_store puts
+      // the thread's column into the row buffer, emit_flush (barrier + horizontal 3-max + ReLU + global store) runs one conv
+      // row later, right after that row's TMEM load has been issued -- the barrier skew and the shared/global latency of
+      // the second half hide behind the load instead of sitting on the per-row chain.  ReLU commutes with both maxima, so
+      // it is applied once per pooled element here instead of once per conv element.
+      auto emit_store = [&](int pr, const uint32_t (&w)[16]) {
+        emit_flush_fn();
         const uint32_t rowbuf = sRow + (em & 1u) * 16384u;
         ++em;
         if (x_ok) {
@@ -1881,29 +1918,7 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
                          "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
           }
         }
-        const long long tb = clock64();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        w_bar += clock64() - tb;
-        if (p.debug_flags & 1) return;
-        __nv_bfloat16* orow = p.out + ((long long)f * p.PH + pr) * p.PW * p.out_cs + p.out_coff;
-        for (int item = te; item < p.PW * 8; item += 256) {
-          const int q = item >> 3, g = item & 7;
-          const int x0 = 2 * q;
-          uint4 m;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w)
-                       : "r"(rowbuf + (uint32_t)x0 * 128u + ((uint32_t)(g ^ (x0 & 7)) << 4)));
-#pragma unroll
-          for (int d = 1; d < 3; ++d) {
-            const int xd = x0 + d;
-            if (xd < p.OW) {
-              uint4 t;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
-                           : "r"(rowbuf + (uint32_t)xd * 128u + ((uint32_t)(g ^ (xd & 7)) << 4)));
-              m.x = hmax2_u32(m.x, t.x); m.y = hmax2_u32(m.y, t.y); m.z = hmax2_u32(m.z, t.z); m.w = hmax2_u32(m.w, t.w);
-            }
-          }
-          *reinterpret_cast<uint4*>(orow + (long long)q * p.out_cs + g * 8) = m;
-        }
+        pend = true; pend_buf = rowbuf; pend_row = (long long)f * p.PH + pr;
       };
       for (int y = r0; y < r1; ++y) {
         const uint32_t ridx = ir + (uint32_t)(y - r0);
@@ -1913,8 +1928,10 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
         uint32_t v[32];
         if (!(p.debug_flags & 2)) {
           tmem_ld32_nowait(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 64u + (uint32_t)(half * 32), v);
+          if (POOL) emit_flush_fn();  // second half of the previous pooled row, under the TMEM load's latency
           tmem_wait_ld();
         } else {
+          if (POOL) emit_flush_fn();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0x3f800000u;
         }
@@ -1930,7 +1947,7 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
           fv[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z);
           fv[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w);
         }
-        if (p.relu) {
+        if (p.relu && !POOL) {  // (POOL: after the pooling maxima, in emit_flush)
 #pragma unroll
           for (int j = 0; j < 32; ++j) fv[j] = fmaxf(fv[j], 0.f);
         }
@@ -1949,7 +1966,7 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
               uint32_t t[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) t[j] = hmax2_u32(cm[j], w[j]);
-              emit(p0 + ((y - r0) >> 1) - 1, t);
+              emit_store(p0 + ((y - r0) >> 1) - 1, t);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) cm[j] = w[j];
@@ -1959,9 +1976,10 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
           }
         }
       }
-      if (POOL && ((r1 - r0) & 1) == 0 && r1 > r0) emit(p0 + ((r1 - r0) >> 1) - 1, cm);  // clipped last window
+      if (POOL && ((r1 - r0) & 1) == 0 && r1 > r0) emit_store(p0 + ((r1 - r0) >> 1) - 1, cm);  // clipped last window
       ir += (uint32_t)(r1 - r0);
     }
+    emit_flush_fn();
     if ((p.debug_flags & 16) && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9))
       printf("stem_rows cta0 warp %d: epilogue waited %lld (accumulators) + %lld (row barrier) cycles of %lld\n", warp, w_epi,
              w_bar, clock64() - t_start);
