@@ -20,7 +20,14 @@ def main(src, dst, title):
             rows.append((name, float(r["Metric Value"].replace(",", "")) / 1000.0, r["Grid Size"], r["Block Size"]))
     starts = [i for i, r in enumerate(rows) if "stem_rows" in r[0]]
     assert len(starts) >= 2, "need at least two forwards in the capture"
-    fw = rows[starts[-2]:starts[-1]]
+    # the capture also holds the chunked e2e forwards (sub-batches on sub-nets): keep to the full-batch forwards, i.e. the
+    # ones whose stem launch has the largest grid, and take the last complete one of them
+    def grid0(i):
+        return int(rows[i][2].strip("()").split(",")[0])
+    gmax = max(grid0(i) for i in starts)
+    full = [k for k, i in enumerate(starts[:-1]) if grid0(i) == gmax and grid0(starts[k + 1]) == gmax]
+    assert full, "no complete full-batch forward in the capture"
+    fw = rows[starts[full[-1]]:starts[full[-1] + 1]]
     tot = sum(r[1] for r in fw)
     agg = {}
     for n, t, g, b in fw:
