@@ -1872,10 +1872,7 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
     auto emit_flush_fn = [&]() {
       if (!pend) return;
       pend = false;
-      const long long tb = clock64();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      w_bar += clock64() - tb;
-      if (p.debug_flags & 1) return;
       const uint32_t rowbuf = pend_buf;
       __nv_bfloat16* orow = p.out + pend_row * p.PW * p.out_cs + p.out_coff;
       for (int item = te; item < p.PW * 8; item += 256) {
@@ -1920,59 +1917,78 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
         }
         pend = true; pend_buf = rowbuf; pend_row = (long long)f * p.PH + pr;
       };
-      for (int y = r0; y < r1; ++y) {
+      // one accumulator row: TMEM -> 32 fp32 columns of this thread's output pixel; the slot goes back to the MMA issuer
+      // as soon as the load has landed.  (No alternative data path in here: a second definition of v[] makes ptxas copy
+      // all 32 registers per row -- the r02 source-level profile showed 64 MOVs per row from exactly that.)
+      auto load_row = [&](int y, uint32_t (&v)[32]) {
         const uint32_t ridx = ir + (uint32_t)(y - r0);
         const uint32_t slot = ridx % (uint32_t)kStemSlots;
         w_epi += mbar_wait_timed(bar_acc_full + 8 * slot, (ridx / (uint32_t)kStemSlots) & 1u, p.error_flag, 4);
         tc_fence_after();
-        uint32_t v[32];
-        if (!(p.debug_flags & 2)) {
-          tmem_ld32_nowait(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 64u + (uint32_t)(half * 32), v);
-          if (POOL) emit_flush_fn();  // second half of the previous pooled row, under the TMEM load's latency
-          tmem_wait_ld();
-        } else {
-          if (POOL) emit_flush_fn();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0x3f800000u;
-        }
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 64u + (uint32_t)(half * 32), v);
+        if (POOL) emit_flush_fn();  // second half of the previous pooled row, under the TMEM load's latency
+        tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acc_empty + 8 * slot) : "memory");
-        float fv[32];
+      };
+      if (!POOL) {
+        for (int y = r0; y < r1; ++y) {
+          uint32_t v[32];
+          load_row(y, v);
+          float fv[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 a = reinterpret_cast<const float4*>(sc)[j], b = reinterpret_cast<const float4*>(sh)[j];
-          fv[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), a.x, b.x);
-          fv[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y);
-          fv[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z);
-          fv[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w);
-        }
-        if (p.relu && !POOL) {  // (POOL: after the pooling maxima, in emit_flush)
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = reinterpret_cast<const float4*>(sc)[j], b = reinterpret_cast<const float4*>(sh)[j];
+            fv[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), a.x, b.x);
+            fv[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y);
+            fv[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z);
+            fv[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w);
+          }
+          if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) fv[j] = fmaxf(fv[j], 0.f);
-        }
-        if (!POOL) {
-          if (x_ok && !(p.debug_flags & 1)) {
+            for (int j = 0; j < 32; ++j) fv[j] = fmaxf(fv[j], 0.f);
+          }
+          if (x_ok) {
             __nv_bfloat16* dst = p.out + (((long long)f * p.OH + y) * p.OW + x) * p.out_cs + p.out_coff + half * 32;
             store16_bf16(dst, *reinterpret_cast<const float (*)[16]>(&fv[0]), 16);
             store16_bf16(dst + 16, *reinterpret_cast<const float (*)[16]>(&fv[16]), 16);
           }
-        } else {
-          uint32_t w[16];
+        }
+      } else {
+        // scale/shift (conv bias + BN folded) and pack to bf16 pairs; ReLU waits until after the pooling maxima
+        auto bn_pack = [&](const uint32_t (&v)[32], uint32_t (&w)[16]) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(fv[2 * j], fv[2 * j + 1]);
-          if (((y - r0) & 1) == 0) {
-            if (y > r0) {
-              uint32_t t[16];
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = reinterpret_cast<const float4*>(sc)[j], b = reinterpret_cast<const float4*>(sh)[j];
+            w[2 * j] = pack_bf16x2(fmaf(__uint_as_float(v[4 * j + 0]), a.x, b.x), fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y));
+            w[2 * j + 1] = pack_bf16x2(fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z), fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w));
+          }
+        };
+        // rows in pairs (even, odd index inside the unit): pooled row k = max(rows 2k, 2k+1, 2k+2).  `cm` carries
+        // max(2k, 2k+1) into the even row that completes the window; the even row's own values live in `we` until the
+        // odd row has been folded in -- no register array is ever copied.
+        for (int y = r0; y < r1; y += 2) {
+          uint32_t we[16];
+          {
+            uint32_t v[32];
+            load_row(y, v);
+            bn_pack(v, we);
+          }
+          if (y > r0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) t[j] = hmax2_u32(cm[j], w[j]);
-              emit_store(p0 + ((y - r0) >> 1) - 1, t);
+            for (int j = 0; j < 16; ++j) cm[j] = hmax2_u32(cm[j], we[j]);
+            emit_store(p0 + ((y - r0) >> 1) - 1, cm);
+          }
+          if (y + 1 < r1) {
+            uint32_t wo[16];
+            {
+              uint32_t v[32];
+              load_row(y + 1, v);
+              bn_pack(v, wo);
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) cm[j] = w[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) cm[j] = hmax2_u32(cm[j], w[j]);
+            for (int j = 0; j < 16; ++j) cm[j] = hmax2_u32(we[j], wo[j]);
           }
         }
       }
