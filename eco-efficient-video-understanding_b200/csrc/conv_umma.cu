@@ -1804,28 +1804,34 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
           const bool yok0 = (unsigned)(2 * Y - 3) < (unsigned)p.H, yok1 = (unsigned)(2 * Y - 2) < (unsigned)p.H;
           for (int X = lane; X < CW; X += 32) {
             float v[12];
+            // pixel columns 2X-3, 2X-2 of image rows 2Y-3, 2Y-2: one base address per cell, the six (row, channel) planes
+            // at uniform offsets from it, the second column at +1 element
+            const int xa = 2 * X - 3;
+            const bool okx0 = (unsigned)xa < (unsigned)p.W, okx1 = (unsigned)(xa + 1) < (unsigned)p.W;
+            const uint32_t a0 = raw + (uint32_t)xa * (SRC == 1 ? 4u : 1u);  // (wraps for xa < 0: never dereferenced then)
+            const uint32_t planeb = (uint32_t)p.W * (SRC == 1 ? 4u : 1u);
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
+            for (int dy = 0; dy < 2; ++dy) {
+              const bool yok = dy ? yok1 : yok0;
 #pragma unroll
-              for (int dx = 0; dx < 2; ++dx) {
-                const int x = 2 * X - 3 + dx;
-                const bool ok = (dy ? yok1 : yok0) && (unsigned)x < (unsigned)p.W;
+              for (int c = 0; c < 3; ++c) {
+                const uint32_t a = a0 + (uint32_t)(dy * 3 + c) * planeb;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
+                for (int dx = 0; dx < 2; ++dx) {
                   float t = 0.f;
-                  if (ok) {
-                    const uint32_t a = raw + (uint32_t)((dy * 3 + c) * p.W + x) * (SRC == 1 ? 4u : 1u);
+                  if (yok && (dx ? okx1 : okx0)) {
                     if (SRC == 1) {
-                      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(a));
+                      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(a + (uint32_t)dx * 4u));
                     } else {
                       uint32_t b;
-                      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(a));
+                      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(a + (uint32_t)dx));
                       t = (float)b - mean[c];
                     }
                   }
                   v[(dy * 2 + dx) * 3 + c] = t;
                 }
               }
+            }
             uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 6; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
@@ -1869,30 +1875,41 @@ stem_rows_kernel(const StemRowsParams p, const __grid_constant__ CUtensorMap tmX
     bool pend = false;
     uint32_t pend_buf = 0;
     long long pend_row = 0;
+    // second half of a pooled row: thread te owns channel group fg of pooled columns fq0, fq0 + 32, ...  Column q reads
+    // conv columns 2q, 2q+1, 2q+2 of the row buffer; (2q) & 7 is the same for every q of a thread, so the three swizzled
+    // offsets are per-thread constants and a step of 32 columns is +8192 bytes.
+    const int fg = te & 7, fq0 = te >> 3;
+    const uint32_t fsw = (uint32_t)(2 * (fq0 & 3));
+    const uint32_t foff0 = (uint32_t)(2 * fq0) * 128u + (((uint32_t)fg ^ fsw) << 4);
+    const uint32_t foff1 = (uint32_t)(2 * fq0 + 1) * 128u + (((uint32_t)fg ^ (fsw + 1u)) << 4);
+    const uint32_t foff2 = (uint32_t)(2 * fq0 + 2) * 128u + (((uint32_t)fg ^ ((fsw + 2u) & 7u)) << 4);
+    const uint32_t neg_inf2 = 0xff80ff80u;  // bf16x2 (-inf, -inf): the neutral element of the maximum
+    auto lds128_if = [&](uint32_t addr, bool ok) {
+      uint4 t;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t"
+          "mov.b32 %0, %6;\n\tmov.b32 %1, %6;\n\tmov.b32 %2, %6;\n\tmov.b32 %3, %6;\n\t"
+          "@p ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
+          : "=&r"(t.x), "=&r"(t.y), "=&r"(t.z), "=&r"(t.w)
+          : "r"(addr), "r"((uint32_t)ok), "r"(neg_inf2));
+      return t;
+    };
     auto emit_flush_fn = [&]() {
       if (!pend) return;
       pend = false;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const uint32_t rowbuf = pend_buf;
-      __nv_bfloat16* orow = p.out + pend_row * p.PW * p.out_cs + p.out_coff;
-      for (int item = te; item < p.PW * 8; item += 256) {
-        const int q = item >> 3, g = item & 7;
-        const int x0 = 2 * q;
+      uint32_t rb = pend_buf;
+      __nv_bfloat16* o = p.out + (pend_row * p.PW + fq0) * p.out_cs + p.out_coff + fg * 8;
+      const long long ostep = 32 * p.out_cs;
+      for (int q = fq0; q < p.PW; q += 32, rb += 8192u, o += ostep) {
         uint4 m;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w)
-                     : "r"(rowbuf + (uint32_t)x0 * 128u + ((uint32_t)(g ^ (x0 & 7)) << 4)));
-#pragma unroll
-        for (int d = 1; d < 3; ++d) {
-          const int xd = x0 + d;
-          if (xd < p.OW) {
-            uint4 t;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
-                         : "r"(rowbuf + (uint32_t)xd * 128u + ((uint32_t)(g ^ (xd & 7)) << 4)));
-            m.x = hmax2_u32(m.x, t.x); m.y = hmax2_u32(m.y, t.y); m.z = hmax2_u32(m.z, t.z); m.w = hmax2_u32(m.w, t.w);
-          }
-        }
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(rb + foff0));
+        const uint4 t1 = lds128_if(rb + foff1, 2 * q + 1 < p.OW);
+        const uint4 t2 = lds128_if(rb + foff2, 2 * q + 2 < p.OW);
+        m.x = hmax2_u32(hmax2_u32(m.x, t1.x), t2.x); m.y = hmax2_u32(hmax2_u32(m.y, t1.y), t2.y);
+        m.z = hmax2_u32(hmax2_u32(m.z, t1.z), t2.z); m.w = hmax2_u32(hmax2_u32(m.w, t1.w), t2.w);
         if (p.relu) { m.x = hmax2_u32(m.x, 0u); m.y = hmax2_u32(m.y, 0u); m.z = hmax2_u32(m.z, 0u); m.w = hmax2_u32(m.w, 0u); }
-        *reinterpret_cast<uint4*>(orow + (long long)q * p.out_cs + g * 8) = m;
+        *reinterpret_cast<uint4*>(o) = m;
       }
     };
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
