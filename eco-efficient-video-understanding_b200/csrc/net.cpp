@@ -2682,7 +2682,8 @@ float Net::forward(int start, int end) {
   }
   for (auto& t : tensors_)
     if (t.host_newer && t.root >= 0) upload(t);
-  for (int vb : inputs_) tensors_[vis_blobs_[vb].tensor].dev_newer = false;
+  // (an input written on the device -- set_input_device, transform_input_u8 -- keeps dev_newer: its host mirror is stale
+  // until somebody asks for it, and the device copy stays the one the next forward reads)
   // blobs that are views of an input (reshape_data of the train/test nets) read their host mirror back from the device
   for (int vb : inputs_) {
     const int it = vis_blobs_[vb].tensor;
