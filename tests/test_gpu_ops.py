@@ -260,6 +260,18 @@ def test_conv_without_bn_and_plain_relu(gpu):
     run_case(txt2, shape, 0, check=("c",))
 
 
+def test_bn_after_in_place_relu_is_not_fused_into_the_conv(gpu):
+    """conv -> ReLU (in place on the conv top) -> BN: the reference computes BN(relu(conv)).  The planner may fuse a BN
+    that reads the conv top into the conv epilogue only when no in-place layer rewrites that top in between
+    (round-1 advisor finding: it used to produce relu-after-BN silently)."""
+    shape = (2, 8, 6, 6)
+    txt = conv_net(shape, 32, [3, 3], [1, 1], [1, 1], bn=False)
+    txt += 'layer { name: "r" type: "ReLU" bottom: "c" top: "c" }\n'
+    txt += 'layer { name: "c_bn" type: "BN" bottom: "c" top: "c_bn" }\n'
+    for keep_all in (True, False):
+        run_case(txt, shape, 0, check=("c_bn",) if not keep_all else ("c", "c_bn"), keep_all=keep_all)
+
+
 RES_NET = """name: "res"
 input: "data" input_shape { dim: 2 dim: 8 dim: 4 dim: 6 dim: 6 }
 layer { name: "s" type: "Convolution" bottom: "data" top: "s" convolution_param { num_output: 64 kernel_size: [1,1,1] } }
