@@ -154,7 +154,9 @@ int eco_blob_host_data(eco_net* net, int blob, int for_write, float** data, size
 int eco_blob_host_diff(eco_net* net, int blob, int for_write, float** data, size_t* count);
 
 /* ---- fast paths beyond caffe's surface (device-resident I/O for serving) ---- */
-/* copy `count` fp32 values already on the device (caffe layout) into an input blob, no host hop */
+/* copy `count` fp32 values already on the device (caffe layout) into an input blob, no host hop.  The device copy
+ * stays the blob's content for every following forward until the caller asks for the blob's host memory again
+ * (eco_blob_host_data downloads it first and then makes the host mirror the source, as for any caffe blob). */
 int eco_net_set_input_device(eco_net* net, int blob, const void* dev_f32, size_t count);
 /* device pointer of a plain fp32 blob (e.g. fc8) valid until reshape; NULL/err for fused-away blobs */
 int eco_blob_device_f32(eco_net* net, int blob, const float** dev, size_t* count);
