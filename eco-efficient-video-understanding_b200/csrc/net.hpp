@@ -184,6 +184,7 @@ struct TrainAux {
   int x_tensor = -1, y_tensor = -1;
   // convolution backward
   bool has_dgrad = false, dilated = false;
+  bool compact = false;             // 1x1 strided convolution: dgrad on the compact dY, then a strided scatter into dX
   int dg = -1;                      // index into dgrads_ (a ConvOp describing dX = conv(dY', flipped W^T))
   __nv_bfloat16* dil = nullptr;     // zero-dilated dY for strided convolutions [NB, E..., Cout]
   int E[3] = {1, 1, 1};

@@ -647,6 +647,41 @@ __global__ void dilate_cl_kernel(ClView s, int OD, int OH, int OW, __nv_bfloat16
   }
 }
 
+// one thread per (dX position, 8 channels); src is dense [NB][OD][OH][OW][C]
+__global__ void scatter_stride_cl_kernel(const __nv_bfloat16* __restrict__ src, int OD, int OH, int OW, ClView dx, int ID, int IH,
+                                         int IW, int sD, int sH, int sW, int accumulate) {
+  const unsigned G = (unsigned)dx.C / 8u;
+  const unsigned long long total = (unsigned long long)dx.outer * dx.inner * G;
+  for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < total;
+       t += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned g = (unsigned)(t % G);
+    unsigned long long r = t / G;
+    const unsigned long long pix = r;
+    const unsigned ix = (unsigned)(r % (unsigned)IW); r /= (unsigned)IW;
+    const unsigned iy = (unsigned)(r % (unsigned)IH); r /= (unsigned)IH;
+    const unsigned iz = (unsigned)(r % (unsigned)ID);
+    const unsigned long long n = r / (unsigned)ID;
+    const unsigned oz = iz / (unsigned)sD, oy = iy / (unsigned)sH, ox = ix / (unsigned)sW;
+    const bool on = oz * sD == iz && oy * sH == iy && ox * sW == ix && oz < (unsigned)OD && oy < (unsigned)OH && ox < (unsigned)OW;
+    __nv_bfloat16* d = dx.ptr + pix * dx.cs + dx.coff + g * 8;
+    if (!on) {
+      if (!accumulate) *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const uint4 v = ld8(src + ((((n * OD + oz) * OH + oy) * OW + ox) * (unsigned long long)dx.C) + g * 8);
+    if (!accumulate) {
+      *reinterpret_cast<uint4*>(d) = v;
+    } else {
+      float a[8], b[8];
+      up8(v, a);
+      up8(ld8(d), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] += a[j];
+      *reinterpret_cast<uint4*>(d) = pk8(b);
+    }
+  }
+}
+
 // counter-based RNG: one 64-bit mix (splitmix64 finaliser) per element; the same (seed, index) gives the same draw in
 // the forward and the backward pass, so no mask is stored
 __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
@@ -961,6 +996,14 @@ cudaError_t launch_dilate_cl(ClView src, int OD, int OH, int OW, __nv_bfloat16* 
   const long long n = src.outer * src.inner * (src.C / 8);
   if (n == 0) return cudaSuccess;
   dilate_cl_kernel<<<grid_for(n, 16), kT, 0, st>>>(src, OD, OH, OW, dst, ED, EH, EW, sD, sH, sW);
+  return cudaGetLastError();
+}
+cudaError_t launch_scatter_stride_cl(const __nv_bfloat16* src, int C, int OD, int OH, int OW, ClView dx, int ID, int IH, int IW,
+                                     int sD, int sH, int sW, int accumulate, cudaStream_t st) {
+  if (dx.C != C || C % 8 != 0 || dx.inner != (long long)ID * IH * IW) return cudaErrorInvalidValue;
+  const long long n = dx.outer * dx.inner * (C / 8);
+  if (n == 0) return cudaSuccess;
+  scatter_stride_cl_kernel<<<grid_for(n, 16), kT, 0, st>>>(src, OD, OH, OW, dx, ID, IH, IW, sD, sH, sW, accumulate);
   return cudaGetLastError();
 }
 cudaError_t launch_dropout_f32(const float* x, float* y, long long n, float ratio, uint64_t seed, cudaStream_t st) {

@@ -61,6 +61,10 @@ cudaError_t launch_cl_axpy(ClView x, ClView y, int accumulate, cudaStream_t st);
 // y[i] (+)= a * x[i], fp32
 cudaError_t launch_f32_axpy(const float* x, float* y, long long n, float a, int accumulate, cudaStream_t st);
 // scatter a strided-convolution output gradient into its zero-dilated form (zeros are written once at plan time)
+// dX[n, z*sD, y*sH, x*sW, :] (+)= src[n, z, y, x, :], every other position of dX = 0 unless `accumulate` (then untouched):
+// the input gradient of a 1x1 strided convolution from its compact form
+cudaError_t launch_scatter_stride_cl(const __nv_bfloat16* src, int C, int OD, int OH, int OW, ClView dx, int ID, int IH, int IW,
+                                     int sD, int sH, int sW, int accumulate, cudaStream_t st);
 cudaError_t launch_dilate_cl(ClView src, int OD, int OH, int OW, __nv_bfloat16* dst, int ED, int EH, int EW, int sD, int sH,
                              int sW, cudaStream_t st);
 

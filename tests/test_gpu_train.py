@@ -64,6 +64,7 @@ CONV_BWD = [
     ("3d_cin256_cout512", (2, 8, 2, 7, 7), 256, 512, [3, 3, 3], [1, 1, 1], [1, 1, 1]),
     ("3d_1x1_s2_down", (2, 8, 4, 8, 8), 128, 256, [1, 1, 1], [2, 2, 2], [0, 0, 0]),
     ("3d_s2_tiny_m64", (2, 8, 2, 4, 4), 32, 64, [3, 3, 3], [2, 2, 2], [1, 1, 1]),   # fewer positions than one 128-row tile
+    ("2d_1x1_s2_compact", (2, 8, 15, 12), 64, 96, [1, 1], [2, 2], [0, 0]),   # strided 1x1: dgrad on the compact grid + scatter
     ("3d_s1_tiny_m64", (2, 8, 2, 4, 4), 48, 32, [3, 3, 3], [1, 1, 1], [1, 1, 1]),
 ]
 
@@ -112,8 +113,12 @@ def test_two_consumers_accumulate_into_one_gradient(gpu):
     dgrad adds into the buffer the first one wrote (residual operand of the GEMM epilogue)"""
     shape = (2, 8, 2, 8, 8)
     one, zero = [1, 1, 1], [0, 0, 0]
+    two = [2, 2, 2]
+    # (g, f: strided 1x1 convolutions -- their dgrad runs on the compact grid and is scattered; g adds into the buffer, f,
+    # the last layer = the first one to run backward, overwrites it)
     txt = header(shape) + conv("a", "data", 32, one, one, zero) + conv("c", "a", 64, [3, 3, 3], [2, 2, 2], [1, 1, 1]) + \
-        conv("d", "a", 48, [3, 3, 3], [2, 2, 2], [1, 1, 1]) + conv("e", "a", 16, one, one, zero)
+        conv("g", "a", 32, one, two, zero) + conv("d", "a", 48, [3, 3, 3], [2, 2, 2], [1, 1, 1]) + conv("e", "a", 16, one, one, zero) + \
+        conv("f", "a", 24, one, two, zero)
     ref = refnet.RefNet(txt, phase="TRAIN").init_params(8)
     P = {k: [bf(v[0]), v[1]] for k, v in ref.params_dict().items()}
     rng = np.random.default_rng(2)
@@ -123,12 +128,13 @@ def test_two_consumers_accumulate_into_one_gradient(gpu):
     net.blobs["data"].data[...] = x
     net.forward()
     a_dev = net.blobs["a"].data.copy()
-    dys = {n: bf(rng.normal(size=net.blobs[n].data.shape)) for n in ("c", "d", "e")}
+    dys = {n: bf(rng.normal(size=net.blobs[n].data.shape)) for n in ("c", "g", "d", "e", "f")}
     net.clear_param_diffs()
     net.backward(**dys)
     total = np.zeros_like(a_dev)
     parts = {}
-    for n, (k, s_, p_) in {"c": ([3, 3, 3], [2, 2, 2], [1, 1, 1]), "d": ([3, 3, 3], [2, 2, 2], [1, 1, 1]), "e": (one, one, zero)}.items():
+    for n, (k, s_, p_) in {"c": ([3, 3, 3], [2, 2, 2], [1, 1, 1]), "d": ([3, 3, 3], [2, 2, 2], [1, 1, 1]), "e": (one, one, zero),
+                           "g": (one, two, zero), "f": (one, two, zero)}.items():
         dx, dw, _ = refnet.conv_backward(a_dev, P[n][0], dys[n], k, s_, p_)
         parts[n] = dx
         total += dx
