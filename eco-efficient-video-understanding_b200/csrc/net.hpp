@@ -184,6 +184,7 @@ struct TrainAux {
   int x_tensor = -1, y_tensor = -1;
   // convolution backward
   bool has_dgrad = false, dilated = false;
+  bool db_zero = false;             // the only reader of the conv top is a batch-statistics BN: its bias gradient is identically 0
   bool compact = false;             // 1x1 strided convolution: dgrad on the compact dY, then a strided scatter into dX
   int dg = -1;                      // index into dgrads_ (a ConvOp describing dX = conv(dY', flipped W^T))
   __nv_bfloat16* dil = nullptr;     // zero-dilated dY for strided convolutions [NB, E..., Cout]
@@ -387,6 +388,8 @@ class Net {
   std::vector<TrainAux> aux_;        // parallel to ops_
   std::vector<ConvOp> dgrads_;
   float* wgrad_scratch_ = nullptr;
+  std::vector<char> bwd_seeded_;      // per backward() call: storage roots whose gradient the caller seeded from the host
+  bool bwd_whole_ = false;
   unsigned char* pool_mask_ = nullptr;   // first-maximum indices of the MAX pooling being back-propagated
   float* reduce_scratch_ = nullptr;  // per-block partials of the deterministic per-channel reductions
   size_t wgrad_scratch_bytes_ = 0;
