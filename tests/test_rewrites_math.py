@@ -6,7 +6,11 @@
   "cell row y+i times weight K block i" (the sliding-row accumulation into the TMEM ring);
 * `pool_commute`: AVE 3x3/s1/p1 pooling followed by a 1x1 convolution == the 1x1 convolution without bias followed by
   the pooling plus bias (caffe's AVE divides every window by 9 here and padding contributes zeros);
-* `fuse_1x1`: sibling 1x1 convolutions as one GEMM over concatenated output channels.
+* `fuse_1x1`: sibling 1x1 convolutions as one GEMM over concatenated output channels;
+* training: the input gradient of a strided 1x1 convolution == W^T dY on the compact output grid scattered to every S-th
+  input position (net_train.inc: `compact`); the input gradient of a strided 3x3x3 convolution == the stride-1 convolution of
+  the zero-dilated dY with the flipped, transposed filter (`setup_dgrad`); the bias gradient of a convolution read only by a
+  batch-statistics BN is zero up to rounding (`db_zero`).
 """
 import numpy as np
 
@@ -91,3 +95,51 @@ def test_sibling_1x1_convs_as_one_gemm():
         one = refnet.conv_forward(x, w, b, [1, 1], [1, 1], [0, 0])
         assert np.array_equal(fused[:, off:off + w.shape[0]], one)  # same K order per output channel: bit-identical
         off += w.shape[0]
+
+
+def test_strided_1x1_input_gradient_is_a_scatter_of_the_compact_gemm():
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(2, 24, 5, 9, 8)).astype(np.float32)
+    w = rng.normal(size=(40, 24, 1, 1, 1)).astype(np.float32)
+    k, s, p = [1, 1, 1], [2, 2, 2], [0, 0, 0]
+    od, oh, ow = (5 - 1) // 2 + 1, (9 - 1) // 2 + 1, (8 - 1) // 2 + 1
+    dy = rng.normal(size=(2, 40, od, oh, ow)).astype(np.float32)
+    dx, _, _ = refnet.conv_backward(x, w, dy, k, s, p)
+    compact = np.einsum("oc,nozyx->nczyx", w[:, :, 0, 0, 0], dy)      # W^T dY on the output grid
+    want = np.zeros_like(x)
+    want[:, :, ::2, ::2, ::2][:, :, :od, :oh, :ow] = compact
+    assert np.abs(dx - want).max() <= 1e-4 * np.abs(want).max()
+    # positions the strided convolution never read get exactly zero
+    mask = np.ones(x.shape[2:], bool)
+    mask[::2, ::2, ::2] = False
+    assert not np.any(dx[:, :, mask])
+
+
+def test_strided_input_gradient_is_a_stride1_conv_of_the_dilated_gradient():
+    rng = np.random.default_rng(6)
+    cin, cout, I = 6, 10, (4, 7, 6)
+    x = rng.normal(size=(1, cin) + I).astype(np.float32)
+    w = rng.normal(size=(cout, cin, 3, 3, 3)).astype(np.float32)
+    k, s, p = [3, 3, 3], [2, 2, 2], [1, 1, 1]
+    O = tuple((i + 2 - 3) // 2 + 1 for i in I)
+    dy = rng.normal(size=(1, cout) + O).astype(np.float32)
+    dx, _, _ = refnet.conv_backward(x, w, dy, k, s, p)
+    E = tuple(i + 2 - 3 + 1 for i in I)                                 # dilated extent: I + 2 pad - K + 1
+    dil = np.zeros((1, cout) + E, np.float32)
+    dil[:, :, ::2, ::2, ::2][:, :, :O[0], :O[1], :O[2]] = dy
+    wt = np.ascontiguousarray(np.flip(w, axis=(2, 3, 4)).transpose(1, 0, 2, 3, 4))  # [cin][cout][flipped taps]
+    got = refnet.conv_forward(dil, wt, np.zeros(cin, np.float32), k, [1, 1, 1], [1, 1, 1])   # pad_new = K - 1 - pad
+    assert got.shape == dx.shape
+    assert np.abs(got - dx).max() <= 1e-4 * np.abs(dx).max()
+
+
+def test_bias_gradient_in_front_of_a_batch_statistics_bn_is_rounding_noise():
+    rng = np.random.default_rng(7)
+    x = rng.normal(size=(4, 16, 6, 6)).astype(np.float32) * 3 + 1
+    slope = rng.uniform(0.5, 1.5, 16).astype(np.float32)
+    dy = rng.normal(size=x.shape).astype(np.float32)
+    mean = x.mean(axis=(0, 2, 3))
+    var = x.var(axis=(0, 2, 3))
+    dx, _, _ = refnet.bn_backward_train(x, dy, slope, mean, var)
+    colsum = dx.sum(axis=(0, 2, 3))                                      # what backward_cpu_bias would accumulate
+    assert np.abs(colsum).max() <= 1e-4 * np.abs(dx).sum(axis=(0, 2, 3)).max()
