@@ -143,3 +143,36 @@ def test_bias_gradient_in_front_of_a_batch_statistics_bn_is_rounding_noise():
     dx, _, _ = refnet.bn_backward_train(x, dy, slope, mean, var)
     colsum = dx.sum(axis=(0, 2, 3))                                      # what backward_cpu_bias would accumulate
     assert np.abs(colsum).max() <= 1e-4 * np.abs(dx).sum(axis=(0, 2, 3)).max()
+
+
+def test_strided_3x3_input_gradient_as_parity_class_convolutions():
+    """dX of a 3x3x3 / stride 2 / pad 1 convolution split by the parity of the input position -- class
+    (pz,py,px) is a STRIDE-1 convolution of the compact dY with the 1- or 2-tap sub-filter per axis that has the matching
+    parity (27 taps in total over the 8 classes), instead of 27 taps over a dilated map that is 7/8 zeros."""
+    rng = np.random.default_rng(8)
+    cin, cout, I = 5, 7, (4, 6, 8)
+    x = rng.normal(size=(1, cin) + I).astype(np.float32)
+    w = rng.normal(size=(cout, cin, 3, 3, 3)).astype(np.float32)
+    O = tuple((i + 2 - 3) // 2 + 1 for i in I)
+    dy = rng.normal(size=(1, cout) + O).astype(np.float32)
+    want, _, _ = refnet.conv_backward(x, w, dy, [3, 3, 3], [2, 2, 2], [1, 1, 1])
+    got = np.zeros_like(want)
+    taps_total = 0
+    # input index i = 2a + q reads dY[(i + 1 - k) / 2] for the k with i + 1 - k even: q = 0 -> k = 1 (dY[a]);
+    # q = 1 -> k = 0 (dY[a + 1]) and k = 2 (dY[a])
+    sub = {0: [(1, 0)], 1: [(0, 1), (2, 0)]}   # parity -> [(tap k, offset into the compact grid)]
+    dyp = np.pad(dy, ((0, 0), (0, 0), (0, 1), (0, 1), (0, 1)))   # a + 1 may run one past the grid: zero
+    for qz in (0, 1):
+        for qy in (0, 1):
+            for qx in (0, 1):
+                nz, ny, nx = len(range(qz, I[0], 2)), len(range(qy, I[1], 2)), len(range(qx, I[2], 2))
+                acc = np.zeros((1, cin, nz, ny, nx), np.float32)
+                for kz, oz in sub[qz]:
+                    for ky, oy in sub[qy]:
+                        for kx, ox in sub[qx]:
+                            taps_total += 1
+                            g = dyp[:, :, oz:oz + nz, oy:oy + ny, ox:ox + nx]
+                            acc += np.einsum("oc,nozyx->nczyx", w[:, :, kz, ky, kx], g)
+                got[:, :, qz::2, qy::2, qx::2] = acc
+    assert taps_total == 27
+    assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
